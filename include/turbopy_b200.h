@@ -1,0 +1,203 @@
+/*
+ * turbopy_b200 -- C ABI of the B200-native turboPy particle hot path.
+ *
+ * This header is the drop-in boundary: plain pointers, sizes and POD structs,
+ * no torch / C++ types.  The reference (arichar6/turbopy) is pure Python with
+ * no FFI of its own; each entry point below cites the reference method whose
+ * arithmetic it replaces.  The Python ComputeTools in turbopy_b200/tools.py
+ * bind these through ctypes (INTEGRATION.md shows the binding a turboPy
+ * maintainer would add).
+ *
+ * Conventions
+ *   - every function returns int: 0 = TP_OK, >0 = a cudaError_t, <0 = TP_E_*;
+ *     tp_error_string() turns either into text.  Nothing here falls back to
+ *     the CPU: without a CUDA device every compute entry point fails.
+ *   - all device pointers are fp64 (double) unless stated otherwise; `stream`
+ *     is a cudaStream_t passed as void* (0 = legacy default stream); calls are
+ *     asynchronous on that stream and may be captured into a CUDA graph.
+ *   - a "(n,3) array" is described by (ptr, stride_n, stride_c) in ELEMENTS:
+ *     element (i,c) lives at ptr[i*stride_n + c*stride_c].  Two layouts are
+ *     accelerated: SoA (stride_n = 1, stride_c = ld >= n) and AoS, numpy's
+ *     C-order (stride_n = 3, stride_c = 1).  Anything else -> TP_E_LAYOUT.
+ *   - arithmetic: IEEE fp64, round-to-nearest, no FMA contraction, operation
+ *     order of the reference; results are bit-identical to the reference's
+ *     numpy on the same inputs ("Arithmetic contract").
+ */
+#ifndef TURBOPY_B200_H
+#define TURBOPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TP_VERSION 100            /* 0.1.0 */
+
+/* ---- error codes (negative; positive values are cudaError_t) ------------ */
+#define TP_OK            0
+#define TP_E_ARG        -1        /* bad argument (null pointer, n < 0, ...)    */
+#define TP_E_LAYOUT     -2        /* strides are neither SoA nor AoS            */
+#define TP_E_NODEVICE   -3        /* no CUDA device / not an sm_100 device      */
+#define TP_E_GRID       -4        /* fewer than 2 grid nodes, dr <= 0, ...      */
+#define TP_E_MODE       -5        /* unknown field mode / formula / axis        */
+#define TP_E_GRAPH      -6        /* graph capture misuse                       */
+
+/* ---- how E / B are given to tp_boris_push_f64 ---------------------------- */
+#define TP_FIELD_UNIFORM_HOST 0   /* ptr -> 3 doubles in HOST memory, read at call time   */
+#define TP_FIELD_UNIFORM_DEV  1   /* ptr -> 3 doubles in DEVICE memory, read by the kernel */
+#define TP_FIELD_PER_PARTICLE 2   /* ptr -> (n,3) DEVICE array with its own strides        */
+
+/* ---- linear-gather formulas (they round differently) --------- */
+#define TP_INTERP_A 1             /* Grid.create_interpolator          turbopy/core.py:711-755 */
+#define TP_INTERP_B 2             /* interp1d, 1-D y  -> numpy.interp  turbopy/computetools.py:480 */
+#define TP_INTERP_C 3             /* interp1d, N-D y  -> scipy _call_linear (same call site) */
+
+/* ---- per-particle status bits written by the gather kernels -------------- */
+#define TP_ST_BELOW      1        /* coordinate < r[0]   (interp1d: ValueError; core.py:726 assert) */
+#define TP_ST_ABOVE      2        /* coordinate > r[ng-1](interp1d: ValueError; core.py:727 assert) */
+#define TP_ST_BAD_WINDOW 4        /* formula A found 0 or >2 nodes in (x-dr, x+dr): core.py:729 assert */
+
+typedef void* tp_stream_t;
+
+/* (n,3) position and momentum arrays, updated IN PLACE (same storage the
+ * caller published to other modules: turbopy/core.py:334-339,371-383). */
+typedef struct tp_particles {
+    double* pos;  int64_t pos_stride_n;  int64_t pos_stride_c;
+    double* mom;  int64_t mom_stride_n;  int64_t mom_stride_c;
+    int64_t n;
+} tp_particles;
+
+/* scalars of BorisPush.push(position, momentum, charge, mass, E, B)
+ * (turbopy/computetools.py:407,427): dt = owner.clock.dt read at call time,
+ * c2 = BorisPush.c2 (:405).  mass_sq is the caller's `mass**2` (:430) -- the
+ * only way the push uses the mass -- evaluated by the host language so that it
+ * carries the reference's own rounding of that power. */
+typedef struct tp_push_consts {
+    double charge;
+    double mass_sq;
+    double dt;
+    double c2;
+} tp_push_consts;
+
+/* 1-D grid fields for the fused gather.  r: ng node coordinates (Grid.r,
+ * turbopy/core.py:666-667), dr: Grid.dr (:625); r_first / r_last: host copies
+ * of r[0] and r[ng-1] (Grid.r_min / r_max for a Grid), the bounds the kernels
+ * check every coordinate against.  comp[0..2] = Ex,Ey,Ez and
+ * comp[3..5] = Bx,By,Bz: DEVICE pointers to node 0 of each component, NULL
+ * for a component that is identically zero; node j of component c is
+ * comp[c][j*comp_stride[c]] (stride 1 for a (ng,) field, 3 for a column of a
+ * Grid.generate_field(3) array, :675-698). */
+typedef struct tp_grid_fields {
+    const double* r;
+    int64_t       ng;
+    double        dr;
+    double        r_first;
+    double        r_last;
+    const double* comp[6];
+    int64_t       comp_stride[6];
+} tp_grid_fields;
+
+/* ---- library / device ----------------------------------------------------- */
+int         tp_version(void);
+const char* tp_error_string(int code);
+/* sm_count, compute capability, L2 bytes, max opt-in shared memory per block */
+int         tp_device_info(int* sm_count, int* cc_major, int* cc_minor,
+                           int64_t* l2_bytes, int64_t* smem_optin_bytes);
+
+/* ---- kernel 1a: BorisPush.push  (turbopy/computetools.py:407-441) -------- */
+int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
+                      const double* E, int e_mode, int64_t e_stride_n, int64_t e_stride_c,
+                      const double* B, int b_mode, int64_t b_stride_n, int64_t b_stride_c,
+                      tp_stream_t stream);
+
+/* ---- kernel 1b: fused linear gather + BorisPush.push ---------------------
+ * E,B at each particle = linear interpolation of the grid fields at
+ * pos[:,axis] (the gather of ChargedParticle.update,
+ * tests/fixtures/particle_in_field/particle_in_field.py:61-63, vectorised over
+ * particles), then the push above.  status: 4 device uint64 words
+ * {count of flagged particles, lowest flagged index, OR of TP_ST_* bits, 0},
+ * initialised by tp_status_reset; flagged particles are left untouched.
+ * Node coordinates and fields are staged into shared memory by TMA bulk copies
+ * when they fit (query with tp_gather_smem_bytes), else read through L2. */
+int tp_gather_push_f64(const tp_particles* p, const tp_push_consts* k,
+                       const tp_grid_fields* g, int axis, int formula,
+                       uint64_t* status, tp_stream_t stream);
+int tp_status_reset(uint64_t* status, tp_stream_t stream);
+/* shared-memory bytes the staged variant would need; *staged = 1 if it fits */
+int tp_gather_smem_bytes(const tp_grid_fields* g, int64_t* bytes, int* staged);
+
+/* ---- gather only: Interpolators.interpolate1D(x, y)(x_new)
+ * (turbopy/computetools.py:459-481) for ncomp fields at n points.
+ * xq: n query points (stride xq_stride); y: component c, node j at
+ * y[c*y_stride_c + j*y_stride_n]; out: component c, point i at
+ * out[c*out_stride_c + i].  status as above (out-of-range points get NaN). */
+int tp_interp1d_f64(const double* r, int64_t ng, double dr, double r_first, double r_last,
+                    const double* y, int ncomp, int64_t y_stride_c, int64_t y_stride_n,
+                    const double* xq, int64_t xq_stride, int64_t n,
+                    double* out, int64_t out_stride_c, int formula,
+                    uint64_t* status, tp_stream_t stream);
+
+/* ---- kernel 2: FiniteDifference 1-D stencils ------------------------------
+ * centered_difference (turbopy/computetools.py:104-120): d[i]=(y[i+1]-y[i-1])/two_dr,
+ *   two_dr = 2*dr formed by the caller as the reference does; d[0]=d[n-1]=0.
+ * upwind_left (:122-138): d[i]=(y[i]-y[i-1])/widths[i-1], d[0]=0 (widths: n-1).
+ * del2_radial apply (:189-223, `del2_radial() @ f`): tridiagonal rows rebuilt in
+ *   the kernel from r and dr with scipy's dia-matvec summation order. */
+int tp_fd_centered_f64(const double* y, double* d, int64_t n, double two_dr, tp_stream_t stream);
+int tp_fd_upwind_left_f64(const double* y, const double* widths, double* d, int64_t n,
+                          tp_stream_t stream);
+int tp_fd_del2_radial_apply_f64(const double* f, const double* r, double* out, int64_t n,
+                                double g1 /* 1/(2.0*dr), :197 */, double g2 /* 1/(dr**2), :211 */,
+                                tp_stream_t stream);
+/* generic banded operator apply (the dia_matrix objects the other builders
+ * return, :140-187,225-381): out[i] = sum_k data[k][i+off[k]] * x[i+off[k]] in
+ * the given diagonal order; data is (ndiag, n) row-major DEVICE memory,
+ * offsets ndiag HOST ints (|off| <= 2, ndiag <= 5). */
+int tp_fd_dia_apply_f64(const double* data, const int* offsets, int ndiag,
+                        const double* x, double* out, int64_t n, tp_stream_t stream);
+
+/* ---- kernel 3: energy / moment reduction (new; no reference function) ----
+ * out8 (device) = {KE, Px, Py, Pz, sum|p|^2, n, 0, 0} with
+ * KE = sum |p|^2/(m1+mass), m1 = sqrt(mass_sq + |p|^2/c2) (the gamma*m of
+ * turbopy/computetools.py:430-431).  Deterministic two-pass reduction:
+ * scratch must hold tp_reduce_scratch_doubles() doubles. */
+int64_t tp_reduce_scratch_doubles(void);
+int tp_reduce_moments_f64(const double* mom, int64_t stride_n, int64_t stride_c, int64_t n,
+                          double mass, double mass_sq, double c2,
+                          double* out8, double* scratch, tp_stream_t stream);
+
+/* ---- end-to-end call on HOST buffers --------------------------------------
+ * Same contract as tp_boris_push_f64 / tp_gather_push_f64 but pos/mom (and
+ * per-particle E,B) are HOST arrays (numpy's (n,3) C-order or SoA): the call
+ * streams them through the device in chunks (H2D, kernel, D2H overlapped on
+ * internal streams) and returns when the host arrays hold the result.
+ * Grid fields in tp_grid_fields are HOST pointers here and are uploaded by
+ * the call.  status_host: 4 uint64 words, filled on return (may be NULL). */
+int tp_boris_push_host_f64(const tp_particles* p_host, const tp_push_consts* k,
+                           const double* E_host, int e_per_particle,
+                           const double* B_host, int b_per_particle);
+int tp_gather_push_host_f64(const tp_particles* p_host, const tp_push_consts* k,
+                            const tp_grid_fields* g_host, int axis, int formula,
+                            uint64_t* status_host);
+/* bytes moved by the last host call (for bench.py's e2e accounting) */
+int tp_host_last_transfer(int64_t* h2d_bytes, int64_t* d2h_bytes);
+int tp_host_release(void);        /* free the internal staging buffers/streams */
+
+/* ---- CUDA-graph capture of a sequence of the calls above ------------------ */
+int tp_graph_begin(tp_stream_t stream);
+int tp_graph_end(tp_stream_t stream, void** graph_exec);
+int tp_graph_launch(void* graph_exec, tp_stream_t stream);
+int tp_graph_destroy(void* graph_exec);
+
+/* ---- launch accounting and self tests -------------------------------------- */
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t tp_launch_count(void);
+/* device self-test of the shared-reciprocal division against IEEE a/b on n
+ * pseudo-random pairs; *mismatches must come back 0 */
+int tp_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches, tp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURBOPY_B200_H */

@@ -1,0 +1,40 @@
+"""turbopy_b200 -- B200-native implementation of turboPy's particle hot path.
+
+``BorisPush.push`` fused with the linear 1-D field gather, the
+``FiniteDifference`` stencils and the energy / moment reductions, as hand-written
+sm_100a CUDA kernels behind a C ABI (include/turbopy_b200.h), exposed as drop-in
+``ComputeTool``s under the reference's own registry names.
+
+    import turbopy, turbopy_b200          # the second import overrides the stock tools
+    sim = turbopy.Simulation(config)      # "BorisPush", "Interpolators", "FiniteDifference"
+                                          # in config["Tools"] now resolve to the B200 tools
+
+There is no CPU fallback: calls raise if libturbopy_b200.so or a B200 is missing.
+"""
+import os
+
+from . import _lib
+from ._host import ComputeTool, Diagnostic, HAVE_TURBOPY
+from .diagnostics import KineticEnergyDiagnostic, reduce_moments
+from .graph import StepGraph
+from .particles import soa_particles, to_soa
+from .tools import BandedOperator, BorisPush, FiniteDifference, GridOnDevice, Interpolators
+
+__version__ = "0.1.0"
+
+TOOL_CLASSES = {"BorisPush": BorisPush, "Interpolators": Interpolators, "FiniteDifference": FiniteDifference}
+DIAGNOSTIC_CLASSES = {"kinetic_energy": KineticEnergyDiagnostic}
+
+
+def register_tools(override=True):
+    """Register the B200 tools under the stock names.  The names are already
+    taken once ``turbopy`` is imported (turbopy/computetools.py:484-487), hence
+    ``override=True`` (turbopy/core.py:302-312)."""
+    for name, cls in TOOL_CLASSES.items():
+        ComputeTool.register(name, cls, override=override)
+    for name, cls in DIAGNOSTIC_CLASSES.items():
+        Diagnostic.register(name, cls, override=override)
+
+
+if not os.environ.get("TURBOPY_B200_NO_AUTOREGISTER"):
+    register_tools(override=True)

@@ -1,0 +1,72 @@
+// BorisPush.push arithmetic for one particle, in the reference's operation
+// order (turbopy/computetools.py:427-441; line-by-line spec: oracle/boris.py
+// push_soa).  Compiled with -fmad=false: every * and + below rounds on its own.
+#pragma once
+#include "common.cuh"
+
+namespace tp {
+
+struct PushK {            // kernel-side constants of one push call
+    double dt, q, mm;     // clock.dt, charge, mass**2
+    ConstRecip c2;        // BorisPush.c2 and RN(1/c2)
+};
+
+struct Vec3 { double x, y, z; };
+
+// (dt*F)*q : the field-dependent numerator shared by the half kick (E) and the
+// rotation vector (B); computetools.py:429,433 evaluate dt*F first, then *charge.
+__device__ __forceinline__ Vec3 dt_field_q(const PushK& k, const Vec3& F) {
+    Vec3 r;
+    r.x = (k.dt * F.x) * k.q;
+    r.y = (k.dt * F.y) * k.q;
+    r.z = (k.dt * F.z) * k.q;
+    return r;
+}
+
+// One Boris step.  eq = (dt*E)*q, bq = (dt*B)*q (see dt_field_q); x and p are
+// updated in place.  Divisions by 2 are exact multiplications by 0.5; the three
+// quotients that share a denominator (m1, 1+|t|^2, m2) use one correctly
+// rounded reciprocal plus a Markstein correction each (common.cuh) and are
+// bit-identical to IEEE division.
+__device__ __forceinline__ void boris_step(const PushK& k, const Vec3& eq, const Vec3& bq,
+                                           Vec3& x, Vec3& p) {
+    // :429  vminus = momentum + dt*E*charge/2
+    const double hx = eq.x * 0.5, hy = eq.y * 0.5, hz = eq.z * 0.5;
+    const double vmx = p.x + hx, vmy = p.y + hy, vmz = p.z + hz;
+    // :430-431  m1 = sqrt(mass**2 + sum(p*p)/c2)   (old momentum)
+    const double pp = (p.x * p.x + p.y * p.y) + p.z * p.z;
+    const double m1 = sqrt(k.mm + div_const(pp, k.c2));
+    // :433  t = dt*B*charge/m1/2
+    const Recip r1 = make_recip(m1);
+    const double tx = div_shared(bq.x, r1) * 0.5;
+    const double ty = div_shared(bq.y, r1) * 0.5;
+    const double tz = div_shared(bq.z, r1) * 0.5;
+    // :434  s = 2*t/(1 + sum(t*t))
+    const double den = 1.0 + ((tx * tx + ty * ty) + tz * tz);
+    const Recip rd = make_recip(den);
+    const double sx = div_shared(2.0 * tx, rd);
+    const double sy = div_shared(2.0 * ty, rd);
+    const double sz = div_shared(2.0 * tz, rd);
+    // :436  vprime = vminus + cross(vminus, t)
+    const double vpx = vmx + (vmy * tz - vmz * ty);
+    const double vpy = vmy + (vmz * tx - vmx * tz);
+    const double vpz = vmz + (vmx * ty - vmy * tx);
+    // :437  vplus = vminus + cross(vprime, s)
+    const double plx = vmx + (vpy * sz - vpz * sy);
+    const double ply = vmy + (vpz * sx - vpx * sz);
+    const double plz = vmz + (vpx * sy - vpy * sx);
+    // :438  momentum = vplus + dt*E*charge/2
+    p.x = plx + hx;
+    p.y = ply + hy;
+    p.z = plz + hz;
+    // :439-440  m2 from the new momentum
+    const double qq = (p.x * p.x + p.y * p.y) + p.z * p.z;
+    const double m2 = sqrt(k.mm + div_const(qq, k.c2));
+    // :441  position = position + dt*momentum/m2
+    const Recip r2 = make_recip(m2);
+    x.x = x.x + div_shared(k.dt * p.x, r2);
+    x.y = x.y + div_shared(k.dt * p.y, r2);
+    x.z = x.z + div_shared(k.dt * p.z, r2);
+}
+
+}  // namespace tp

@@ -1,0 +1,228 @@
+// End-to-end calls on HOST buffers: the path a turboPy user with numpy arrays
+// takes (BorisPush.push(position, momentum, ...) on (n,3) host arrays,
+// turbopy/computetools.py:407).  The particle arrays are streamed through the
+// device in chunks on three internal streams so that the H2D copy of chunk c+1,
+// the kernel of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full
+// duplex); the arithmetic is done by the same device kernels as the resident
+// path -- there is no CPU compute here.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace tp {
+
+int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
+                       int formula, uint64_t* status, cudaStream_t s);
+
+namespace {
+
+constexpr int kBufs = 3;
+constexpr int64_t kChunk = 4ll << 20;          // most particles per chunk (192 MB of state)
+constexpr int64_t kMinChunk = 256ll << 10;
+
+// Chunk length: about n/8 so that copies and kernels of different chunks
+// overlap, within [256 Ki, 4 Mi] particles, even (keeps SoA blocks 16-B aligned).
+inline int64_t chunk_for(int64_t n) {
+    int64_t c = (n + 7) / 8;
+    c = std::max(kMinChunk, std::min(kChunk, c));
+    c = std::min(c, std::max<int64_t>(n, 2));
+    return ((c + 1) / 2) * 2;
+}
+
+struct HostCtx {
+    cudaStream_t stream[kBufs] = {nullptr, nullptr, nullptr};
+    double* dev[kBufs] = {nullptr, nullptr, nullptr};   // 12 * cap doubles each: pos, mom, E, B
+    int64_t cap = 0;
+    double* grid_dev = nullptr; int64_t grid_cap = 0;   // uploaded grid (r + components)
+    uint64_t* status_dev = nullptr;
+    int64_t h2d = 0, d2h = 0;
+    bool init = false;
+};
+HostCtx g_ctx;
+
+int ensure_ctx(int64_t chunk, int64_t grid_doubles) {
+    HostCtx& c = g_ctx;
+    if (!c.init) {
+        for (int b = 0; b < kBufs; ++b) TP_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream[b], cudaStreamNonBlocking));
+        TP_CUDA_TRY(cudaMalloc(&c.status_dev, 4 * sizeof(uint64_t)));
+        c.init = true;
+    }
+    if (chunk > c.cap) {
+        for (int b = 0; b < kBufs; ++b) {
+            if (c.dev[b]) cudaFree(c.dev[b]);
+            c.dev[b] = nullptr;
+            TP_CUDA_TRY(cudaMalloc(&c.dev[b], sizeof(double) * 12 * chunk));
+        }
+        c.cap = chunk;
+    }
+    if (grid_doubles > c.grid_cap) {
+        if (c.grid_dev) cudaFree(c.grid_dev);
+        c.grid_dev = nullptr;
+        TP_CUDA_TRY(cudaMalloc(&c.grid_dev, sizeof(double) * grid_doubles));
+        c.grid_cap = grid_doubles;
+    }
+    return TP_OK;
+}
+
+// Copy a chunk [i0, i0+m) of an (n,3) host array to/from a device block of 3*ld doubles.
+// SoA host arrays are copied component by component (device block is SoA with
+// ld = chunk length); AoS host arrays are one contiguous copy (device block AoS).
+int copy_chunk(double* dev, double* host, int64_t sn, int64_t sc, int64_t i0, int64_t m, int64_t ld, bool to_dev,
+               cudaStream_t s, int64_t& bytes) {
+    const cudaMemcpyKind kind = to_dev ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (sn == 3 && sc == 1) {
+        double* h = host + 3 * i0;
+        TP_CUDA_TRY(to_dev ? cudaMemcpyAsync(dev, h, sizeof(double) * 3 * m, kind, s)
+                           : cudaMemcpyAsync(h, dev, sizeof(double) * 3 * m, kind, s));
+    } else {
+        for (int c = 0; c < 3; ++c) {
+            double* h = host + c * sc + i0;
+            double* d = dev + c * ld;
+            TP_CUDA_TRY(to_dev ? cudaMemcpyAsync(d, h, sizeof(double) * m, kind, s)
+                               : cudaMemcpyAsync(h, d, sizeof(double) * m, kind, s));
+        }
+    }
+    bytes += static_cast<int64_t>(sizeof(double)) * 3 * m;
+    return TP_OK;
+}
+
+int check_host_layout(const tp_particles* p) {
+    if (!p || p->n < 0 || (p->n > 0 && (!p->pos || !p->mom))) return TP_E_ARG;
+    const int lp = layout_of(p->pos_stride_n, p->pos_stride_c, p->n);
+    const int lm = layout_of(p->mom_stride_n, p->mom_stride_c, p->n);
+    if (lp < 0 || lm < 0) return TP_E_LAYOUT;
+    return TP_OK;
+}
+
+// Shared driver: `launch(chunk particles, buffer index, first particle, stream)` runs the kernel.
+template <typename Launch>
+int run_chunks(const tp_particles* p, const double* E_host, bool e_pp, const double* B_host, bool b_pp,
+               Launch launch) {
+    HostCtx& c = g_ctx;
+    const int64_t n = p->n;
+    const int64_t chunk = chunk_for(n);
+    int rc = TP_OK;
+    int idx = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += chunk, ++idx) {
+        const int b = idx % kBufs;
+        const int64_t m = std::min(chunk, n - i0);
+        cudaStream_t s = c.stream[b];
+        double* base = c.dev[b];
+        if ((rc = copy_chunk(base, p->pos, p->pos_stride_n, p->pos_stride_c, i0, m, chunk, true, s, c.h2d))) return rc;
+        if ((rc = copy_chunk(base + 3 * chunk, p->mom, p->mom_stride_n, p->mom_stride_c, i0, m, chunk, true, s, c.h2d)))
+            return rc;
+        if (e_pp && (rc = copy_chunk(base + 6 * chunk, const_cast<double*>(E_host), 3, 1, i0, m, chunk, true, s, c.h2d)))
+            return rc;
+        if (b_pp && (rc = copy_chunk(base + 9 * chunk, const_cast<double*>(B_host), 3, 1, i0, m, chunk, true, s, c.h2d)))
+            return rc;
+        tp_particles dp;
+        const bool pos_aos = p->pos_stride_n == 3, mom_aos = p->mom_stride_n == 3;
+        dp.pos = base;              dp.pos_stride_n = pos_aos ? 3 : 1; dp.pos_stride_c = pos_aos ? 1 : chunk;
+        dp.mom = base + 3 * chunk;  dp.mom_stride_n = mom_aos ? 3 : 1; dp.mom_stride_c = mom_aos ? 1 : chunk;
+        dp.n = m;
+        if ((rc = launch(dp, base, chunk, s))) return rc;
+        if ((rc = copy_chunk(base, p->pos, p->pos_stride_n, p->pos_stride_c, i0, m, chunk, false, s, c.d2h))) return rc;
+        if ((rc = copy_chunk(base + 3 * chunk, p->mom, p->mom_stride_n, p->mom_stride_c, i0, m, chunk, false, s, c.d2h)))
+            return rc;
+    }
+    for (int b = 0; b < kBufs; ++b) TP_CUDA_TRY(cudaStreamSynchronize(c.stream[b]));
+    return TP_OK;
+}
+
+}  // namespace
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" int tp_boris_push_host_f64(const tp_particles* p, const tp_push_consts* k, const double* E_host,
+                                      int e_per_particle, const double* B_host, int b_per_particle) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    int rc = check_host_layout(p);
+    if (rc) return rc;
+    if (!k || !E_host || !B_host) return TP_E_ARG;
+    if (p->n == 0) return TP_OK;
+    const int64_t chunk = chunk_for(p->n);
+    if ((rc = ensure_ctx(chunk, 0))) return rc;
+    g_ctx.h2d = g_ctx.d2h = 0;
+    return run_chunks(p, E_host, e_per_particle != 0, B_host, b_per_particle != 0,
+                      [&](const tp_particles& dp, double* base, int64_t ch, cudaStream_t s) {
+                          const double* E = e_per_particle ? base + 6 * ch : E_host;
+                          const double* B = b_per_particle ? base + 9 * ch : B_host;
+                          return tp_boris_push_f64(&dp, k, E, e_per_particle ? TP_FIELD_PER_PARTICLE : TP_FIELD_UNIFORM_HOST,
+                                                   3, 1, B, b_per_particle ? TP_FIELD_PER_PARTICLE : TP_FIELD_UNIFORM_HOST,
+                                                   3, 1, s);
+                      });
+}
+
+extern "C" int tp_gather_push_host_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g,
+                                       int axis, int formula, uint64_t* status_host) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    int rc = check_host_layout(p);
+    if (rc) return rc;
+    if (!k || !g || !g->r) return TP_E_ARG;
+    if (g->ng < 2) return TP_E_GRID;
+    // upload the grid: r, then each present component densely (stride 1)
+    int ncomp = 0;
+    for (int c = 0; c < 6; ++c) ncomp += g->comp[c] ? 1 : 0;
+    const int64_t ngp = (g->ng + 1) & ~1ll;                        // keep every block 16-byte aligned
+    const int64_t chunk = chunk_for(p->n);
+    if ((rc = ensure_ctx(chunk, ngp * (1 + ncomp)))) return rc;
+    HostCtx& c = g_ctx;
+    c.h2d = c.d2h = 0;
+    cudaStream_t s0 = c.stream[0];
+    tp_grid_fields dg = *g;
+    dg.r = c.grid_dev;
+    TP_CUDA_TRY(cudaMemcpyAsync(c.grid_dev, g->r, sizeof(double) * g->ng, cudaMemcpyHostToDevice, s0));
+    c.h2d += sizeof(double) * g->ng;
+    int slot = 1;
+    for (int cc = 0; cc < 6; ++cc) {
+        if (!g->comp[cc]) continue;
+        double* dst = c.grid_dev + ngp * slot++;
+        if (g->comp_stride[cc] == 1) {
+            TP_CUDA_TRY(cudaMemcpyAsync(dst, g->comp[cc], sizeof(double) * g->ng, cudaMemcpyHostToDevice, s0));
+        } else {
+            TP_CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(double), g->comp[cc], sizeof(double) * g->comp_stride[cc],
+                                          sizeof(double), g->ng, cudaMemcpyHostToDevice, s0));
+        }
+        c.h2d += sizeof(double) * g->ng;
+        dg.comp[cc] = dst;
+        dg.comp_stride[cc] = 1;
+    }
+    if ((rc = tp_status_reset(c.status_dev, s0))) return rc;
+    TP_CUDA_TRY(cudaStreamSynchronize(s0));
+    if (p->n > 0) {
+        rc = run_chunks(p, nullptr, false, nullptr, false,
+                        [&](const tp_particles& dp, double*, int64_t, cudaStream_t s) {
+                            return gather_push_device(&dp, k, &dg, axis, formula, c.status_dev, s);
+                        });
+        if (rc) return rc;
+    }
+    if (status_host) {
+        TP_CUDA_TRY(cudaMemcpy(status_host, c.status_dev, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        c.d2h += 4 * sizeof(uint64_t);
+    }
+    return TP_OK;
+}
+
+extern "C" int tp_host_last_transfer(int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (h2d_bytes) *h2d_bytes = g_ctx.h2d;
+    if (d2h_bytes) *d2h_bytes = g_ctx.d2h;
+    return TP_OK;
+}
+
+extern "C" int tp_host_release(void) {
+    HostCtx& c = g_ctx;
+    for (int b = 0; b < kBufs; ++b) {
+        if (c.dev[b]) cudaFree(c.dev[b]);
+        c.dev[b] = nullptr;
+        if (c.stream[b]) cudaStreamDestroy(c.stream[b]);
+        c.stream[b] = nullptr;
+    }
+    if (c.grid_dev) cudaFree(c.grid_dev);
+    if (c.status_dev) cudaFree(c.status_dev);
+    c.grid_dev = nullptr; c.status_dev = nullptr; c.cap = 0; c.grid_cap = 0; c.init = false;
+    return TP_OK;
+}

@@ -1,0 +1,640 @@
+// Kernel 1 of the hot path: BorisPush.push and the fused linear gather + push.
+//
+//   push_kernel         reference: turbopy/computetools.py:407-441
+//   gather_push_kernel  reference: the gather of ChargedParticle.update
+//                       (tests/fixtures/particle_in_field/particle_in_field.py:61-63;
+//                       turbopy/core.py:711-755, turbopy/computetools.py:459-481)
+//                       fused with the push above
+//   interp_kernel       reference: Interpolators.interpolate1D(x, y)(x_new)
+//
+// HBM-bound streaming kernels: 96 B of particle state per particle-step
+// (6 doubles read + 6 written), fp64 math in registers, no tensor cores.  The
+// fast path reads/writes the SoA arrays with 128-bit accesses (two particles per
+// thread per array); the 1-D node coordinates and field components are staged
+// once per CTA into shared memory with TMA bulk copies (cp.async.bulk +
+// mbarrier), overlapped with the CTA's first particle loads.
+#include "boris_math.cuh"
+#include "gather_math.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace tp {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------
+// kernel parameter blocks
+// ---------------------------------------------------------------------------
+struct ParticleArgs {
+    double* pos; int64_t pos_sn, pos_sc;
+    double* mom; int64_t mom_sn, mom_sc;
+    int64_t n;
+};
+
+struct FieldArg {           // E or B of the un-fused push
+    const double* ptr;      // device pointer (modes 1, 2)
+    int mode;               // TP_FIELD_*
+    int64_t sn, sc;         // per-particle strides
+    double u[3];            // uniform value (mode 0)
+};
+
+struct PushArgs {
+    ParticleArgs p;
+    PushK k;
+    FieldArg E, B;
+};
+
+constexpr int kMaxSeg = 7;  // node coordinates + up to six separately stored components
+
+struct StageSeg {
+    const double* src;      // global source, first element
+    uint32_t smem_off;      // byte offset of that element in dynamic shared memory
+    uint32_t tma_bytes;     // leading part moved by one cp.async.bulk (multiple of 16, src 16-B aligned)
+    uint32_t n_doubles;     // total elements of the segment
+};
+
+struct GatherArgs {
+    ParticleArgs p;
+    PushK k;
+    // global view (also the source of the staging copies)
+    const double* r;
+    const double* comp[6];
+    int stride[6];
+    int ng;
+    double r_first, r_last, inv_dr, dr;
+    int axis;
+    // staging plan (staged variant only)
+    int nseg;
+    StageSeg seg[kMaxSeg];
+    uint32_t r_smem_off;
+    uint32_t comp_smem_off[6];
+    unsigned long long* status;
+};
+
+// ---------------------------------------------------------------------------
+// particle I/O
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_pair(const ParticleArgs& a, int64_t i, Vec3 (&x)[2], Vec3 (&p)[2]) {
+    const double2 x0 = ld2(a.pos + i);
+    const double2 x1 = ld2(a.pos + a.pos_sc + i);
+    const double2 x2 = ld2(a.pos + 2 * a.pos_sc + i);
+    const double2 p0 = ld2(a.mom + i);
+    const double2 p1 = ld2(a.mom + a.mom_sc + i);
+    const double2 p2 = ld2(a.mom + 2 * a.mom_sc + i);
+    x[0].x = x0.x; x[1].x = x0.y; x[0].y = x1.x; x[1].y = x1.y; x[0].z = x2.x; x[1].z = x2.y;
+    p[0].x = p0.x; p[1].x = p0.y; p[0].y = p1.x; p[1].y = p1.y; p[0].z = p2.x; p[1].z = p2.y;
+}
+
+__device__ __forceinline__ void store_pair(const ParticleArgs& a, int64_t i, const Vec3 (&x)[2], const Vec3 (&p)[2]) {
+    st2(a.pos + i, make_double2(x[0].x, x[1].x));
+    st2(a.pos + a.pos_sc + i, make_double2(x[0].y, x[1].y));
+    st2(a.pos + 2 * a.pos_sc + i, make_double2(x[0].z, x[1].z));
+    st2(a.mom + i, make_double2(p[0].x, p[1].x));
+    st2(a.mom + a.mom_sc + i, make_double2(p[0].y, p[1].y));
+    st2(a.mom + 2 * a.mom_sc + i, make_double2(p[0].z, p[1].z));
+}
+
+__device__ __forceinline__ void load_one(const ParticleArgs& a, int64_t i, Vec3& x, Vec3& p) {
+    const double* xs = a.pos + i * a.pos_sn;
+    const double* ps = a.mom + i * a.mom_sn;
+    x.x = xs[0]; x.y = xs[a.pos_sc]; x.z = xs[2 * a.pos_sc];
+    p.x = ps[0]; p.y = ps[a.mom_sc]; p.z = ps[2 * a.mom_sc];
+}
+
+__device__ __forceinline__ void store_one(const ParticleArgs& a, int64_t i, const Vec3& x, const Vec3& p) {
+    double* xs = a.pos + i * a.pos_sn;
+    double* ps = a.mom + i * a.mom_sn;
+    xs[0] = x.x; xs[a.pos_sc] = x.y; xs[2 * a.pos_sc] = x.z;
+    ps[0] = p.x; ps[a.mom_sc] = p.y; ps[2 * a.mom_sc] = p.z;
+}
+
+__device__ __forceinline__ Vec3 field_at(const FieldArg& f, const Vec3& uni, int64_t i) {
+    if (f.mode != TP_FIELD_PER_PARTICLE) return uni;
+    const double* s = f.ptr + i * f.sn;
+    Vec3 v; v.x = s[0]; v.y = s[f.sc]; v.z = s[2 * f.sc];
+    return v;
+}
+
+__device__ __forceinline__ Vec3 uniform_of(const FieldArg& f) {
+    Vec3 v; v.x = f.u[0]; v.y = f.u[1]; v.z = f.u[2];
+    if (f.mode == TP_FIELD_UNIFORM_DEV) { v.x = f.ptr[0]; v.y = f.ptr[1]; v.z = f.ptr[2]; }
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// push (E, B given per call)
+// ---------------------------------------------------------------------------
+template <bool VEC2>
+__global__ void __launch_bounds__(kThreads, 2) push_kernel(const __grid_constant__ PushArgs a) {
+    const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
+    const bool all_uniform = a.E.mode != TP_FIELD_PER_PARTICLE && a.B.mode != TP_FIELD_PER_PARTICLE;
+    const Vec3 equ = dt_field_q(a.k, Eu), bqu = dt_field_q(a.k, Bu);
+    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kThreads;
+    if (VEC2) {
+        const int64_t npairs = a.p.n >> 1;
+        for (int64_t pr = gtid; pr < npairs; pr += gstride) {
+            const int64_t i = pr * 2;
+            Vec3 x[2], p[2];
+            load_pair(a.p, i, x, p);
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                if (all_uniform) {
+                    boris_step(a.k, equ, bqu, x[v], p[v]);
+                } else {
+                    const Vec3 eq = dt_field_q(a.k, field_at(a.E, Eu, i + v));
+                    const Vec3 bq = dt_field_q(a.k, field_at(a.B, Bu, i + v));
+                    boris_step(a.k, eq, bq, x[v], p[v]);
+                }
+            }
+            store_pair(a.p, i, x, p);
+        }
+        if ((a.p.n & 1) && gtid == 0) {               // odd tail
+            const int64_t i = a.p.n - 1;
+            Vec3 x, p;
+            load_one(a.p, i, x, p);
+            const Vec3 eq = dt_field_q(a.k, field_at(a.E, Eu, i));
+            const Vec3 bq = dt_field_q(a.k, field_at(a.B, Bu, i));
+            boris_step(a.k, eq, bq, x, p);
+            store_one(a.p, i, x, p);
+        }
+    } else {
+        for (int64_t i = gtid; i < a.p.n; i += gstride) {
+            Vec3 x, p;
+            load_one(a.p, i, x, p);
+            const Vec3 eq = dt_field_q(a.k, field_at(a.E, Eu, i));
+            const Vec3 bq = dt_field_q(a.k, field_at(a.B, Bu, i));
+            boris_step(a.k, eq, bq, x, p);
+            store_one(a.p, i, x, p);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TMA bulk staging of the grid into shared memory
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr uint32_t kSmemHeader = 128;   // mbarrier lives in the first 8 bytes
+
+// Issue the staging copies (one elected thread drives the TMA; pieces the TMA
+// cannot take -- a source that is not 16-byte aligned, an 8-byte tail -- are
+// copied by the CTA's threads).  Completion: stage_wait().
+__device__ __forceinline__ void stage_issue(const GatherArgs& a, unsigned char* smem) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int s = 0; s < a.nseg; ++s) total += a.seg[s].tma_bytes;
+        mbar_expect_tx(bar, total);
+        for (int s = 0; s < a.nseg; ++s)
+            if (a.seg[s].tma_bytes)
+                tma_bulk_g2s(smem + a.seg[s].smem_off, a.seg[s].src, a.seg[s].tma_bytes, bar);
+    }
+    for (int s = 0; s < a.nseg; ++s) {
+        const uint32_t first = a.seg[s].tma_bytes >> 3;
+        double* dst = reinterpret_cast<double*>(smem + a.seg[s].smem_off);
+        for (uint32_t e = first + threadIdx.x; e < a.seg[s].n_doubles; e += kThreads) dst[e] = a.seg[s].src[e];
+    }
+}
+
+__device__ __forceinline__ void stage_wait(unsigned char* smem) {
+    mbar_wait(reinterpret_cast<uint64_t*>(smem), 0);
+    __syncthreads();                 // the thread-copied pieces
+}
+
+template <bool STAGED>
+__device__ __forceinline__ GridView make_view(const GatherArgs& a, unsigned char* smem) {
+    GridView g;
+    g.ng = a.ng; g.r_first = a.r_first; g.r_last = a.r_last; g.inv_dr = a.inv_dr; g.dr = a.dr;
+    if (STAGED) {
+        g.r = reinterpret_cast<const double*>(smem + a.r_smem_off);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            g.comp[c] = a.comp[c] ? reinterpret_cast<const double*>(smem + a.comp_smem_off[c]) : nullptr;
+            g.stride[c] = a.stride[c];
+        }
+    } else {
+        g.r = a.r;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { g.comp[c] = a.comp[c]; g.stride[c] = a.stride[c]; }
+    }
+    return g;
+}
+
+__device__ __forceinline__ void flag_particle(unsigned long long* status, int64_t i, unsigned st) {
+    atomicAdd(&status[0], 1ull);
+    atomicMin(&status[1], static_cast<unsigned long long>(i));
+    atomicOr(&status[2], static_cast<unsigned long long>(st));
+}
+
+__device__ __forceinline__ double axis_of(const Vec3& x, int axis) {
+    return axis == 0 ? x.x : (axis == 1 ? x.y : x.z);
+}
+
+template <int FORMULA>
+__device__ __forceinline__ bool gather_and_step(const GatherArgs& a, const GridView& g, int64_t i, Vec3& x, Vec3& p) {
+    double F[6];
+    const unsigned st = gather6<FORMULA>(g, axis_of(x, a.axis), F);
+    if (__builtin_expect(st != 0u, 0)) {
+        flag_particle(a.status, i, st);
+        return false;                // flagged particles are left untouched
+    }
+    Vec3 E, B;
+    E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
+    boris_step(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p);
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// fused gather + push
+// ---------------------------------------------------------------------------
+template <bool VEC2, int FORMULA, bool STAGED>
+__global__ void __launch_bounds__(kThreads, 2) gather_push_kernel(const __grid_constant__ GatherArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (STAGED) stage_issue(a, smem);
+    const GridView g = make_view<STAGED>(a, smem);
+    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kThreads;
+    // The loops are rotated: the first particle loads are issued before the
+    // (CTA-uniform) wait for the staged grid, so they overlap the TMA copies.
+    if (VEC2) {
+        const int64_t npairs = a.p.n >> 1;
+        int64_t pr = gtid;
+        Vec3 x[2], p[2];
+        if (pr < npairs) load_pair(a.p, pr * 2, x, p);
+        if (STAGED) stage_wait(smem);
+        while (pr < npairs) {
+            const int64_t i = pr * 2;
+            const bool w0 = gather_and_step<FORMULA>(a, g, i, x[0], p[0]);
+            const bool w1 = gather_and_step<FORMULA>(a, g, i + 1, x[1], p[1]);
+            if (__builtin_expect(w0 && w1, 1)) {
+                store_pair(a.p, i, x, p);
+            } else {
+                if (w0) store_one(a.p, i, x[0], p[0]);
+                if (w1) store_one(a.p, i + 1, x[1], p[1]);
+            }
+            pr += gstride;
+            if (pr < npairs) load_pair(a.p, pr * 2, x, p);
+        }
+        if ((a.p.n & 1) && gtid == 0) {
+            const int64_t i = a.p.n - 1;
+            Vec3 x1, p1;
+            load_one(a.p, i, x1, p1);
+            if (gather_and_step<FORMULA>(a, g, i, x1, p1)) store_one(a.p, i, x1, p1);
+        }
+    } else {
+        int64_t i = gtid;
+        Vec3 x, p;
+        if (i < a.p.n) load_one(a.p, i, x, p);
+        if (STAGED) stage_wait(smem);
+        while (i < a.p.n) {
+            if (gather_and_step<FORMULA>(a, g, i, x, p)) store_one(a.p, i, x, p);
+            i += gstride;
+            if (i < a.p.n) load_one(a.p, i, x, p);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// gather only (Interpolators.interpolate1D(x, y)(x_new))
+// ---------------------------------------------------------------------------
+struct InterpArgs {
+    GatherArgs g;               // particle part unused
+    const double* xq; int64_t xq_stride; int64_t n;
+    double* out; int64_t out_stride_c;
+    int ncomp;
+};
+
+template <int FORMULA, bool STAGED>
+__global__ void __launch_bounds__(kThreads, 2) interp_kernel(const __grid_constant__ InterpArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (STAGED) { stage_issue(a.g, smem); stage_wait(smem); }
+    const GridView g = make_view<STAGED>(a.g, smem);
+    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kThreads;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int64_t i = gtid; i < a.n; i += gstride) {
+        const double x = a.xq[i * a.xq_stride];
+        for (int c0 = 0; c0 < a.ncomp; c0 += 6) {            // six components per pass
+            GridView gv = g;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const bool on = c0 + c < a.ncomp;
+                gv.comp[c] = on ? g.comp[0] + static_cast<int64_t>(c0 + c) * a.g.stride[1] : nullptr;
+                gv.stride[c] = g.stride[0];
+            }
+            double F[6];
+            const unsigned st = gather6<FORMULA>(gv, x, F);
+            if (st != 0u && c0 == 0) flag_particle(a.g.status, i, st);
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                if (c0 + c < a.ncomp) a.out[static_cast<int64_t>(c0 + c) * a.out_stride_c + i] = st ? nan : F[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int fill_particles(const tp_particles* p, ParticleArgs& a, bool& vec2) {
+    if (!p || p->n < 0) return TP_E_ARG;
+    if (p->n > 0 && (!p->pos || !p->mom)) return TP_E_ARG;
+    if (p->pos_stride_n <= 0 || p->pos_stride_c <= 0 || p->mom_stride_n <= 0 || p->mom_stride_c <= 0)
+        return TP_E_LAYOUT;
+    a.pos = p->pos; a.pos_sn = p->pos_stride_n; a.pos_sc = p->pos_stride_c;
+    a.mom = p->mom; a.mom_sn = p->mom_stride_n; a.mom_sc = p->mom_stride_c;
+    a.n = p->n;
+    vec2 = layout_of(a.pos_sn, a.pos_sc, a.n) == kLayoutSoA && layout_of(a.mom_sn, a.mom_sc, a.n) == kLayoutSoA &&
+           aligned16(a.pos) && aligned16(a.mom) && (a.pos_sc % 2 == 0) && (a.mom_sc % 2 == 0) && a.n >= 2;
+    return TP_OK;
+}
+
+static int fill_consts(const tp_push_consts* k, PushK& o) {
+    if (!k) return TP_E_ARG;
+    o.dt = k->dt; o.q = k->charge; o.mm = k->mass_sq;
+    o.c2.b = k->c2;
+    o.c2.rb = 1.0 / k->c2;                      // IEEE on the host: RN(1/c2)
+    o.c2.ok = std::isfinite(o.c2.rb) && std::fabs(o.c2.rb) >= 0x1p-960 && std::fabs(o.c2.rb) <= 0x1p960;
+    return TP_OK;
+}
+
+static int grid_blocks(const void* kernel, size_t smem, int64_t work_items) {
+    const DeviceProps& d = device_props();
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    const int64_t full = static_cast<int64_t>(d.sm_count) * per_sm;     // one resident wave, persistent loop
+    const int64_t need = (work_items + kThreads - 1) / kThreads;
+    return static_cast<int>(std::max<int64_t>(1, std::min(full, need)));
+}
+
+static int fill_field(const double* ptr, int mode, int64_t sn, int64_t sc, FieldArg& f) {
+    f.ptr = ptr; f.mode = mode; f.sn = sn; f.sc = sc; f.u[0] = f.u[1] = f.u[2] = 0.0;
+    if (!ptr) return TP_E_ARG;
+    if (mode == TP_FIELD_UNIFORM_HOST) { f.u[0] = ptr[0]; f.u[1] = ptr[1]; f.u[2] = ptr[2]; f.ptr = nullptr; }
+    else if (mode == TP_FIELD_PER_PARTICLE) { if (sn <= 0 || sc <= 0) return TP_E_LAYOUT; }
+    else if (mode != TP_FIELD_UNIFORM_DEV) return TP_E_MODE;
+    return TP_OK;
+}
+
+// Build the global view and (if it fits) the shared-memory staging plan.
+static int fill_grid(const tp_grid_fields* g, GatherArgs& a, size_t& smem_bytes, bool& staged,
+                     int64_t comp0_extent = 0) {
+    if (!g || !g->r) return TP_E_ARG;
+    if (g->ng < 2 || g->ng > (1ll << 31) - 8 || !(g->dr > 0.0)) return TP_E_GRID;
+    a.r = g->r; a.ng = static_cast<int>(g->ng); a.dr = g->dr; a.inv_dr = 1.0 / g->dr;
+    a.r_first = g->r_first; a.r_last = g->r_last;
+    struct Range { uintptr_t lo, hi; };
+    Range rng[kMaxSeg]; int nr = 0;
+    rng[nr++] = {reinterpret_cast<uintptr_t>(g->r), reinterpret_cast<uintptr_t>(g->r + g->ng)};
+    bool stride_ok = true;
+    for (int c = 0; c < 6; ++c) {
+        a.comp[c] = g->comp[c];
+        a.stride[c] = 1;
+        if (!g->comp[c]) continue;
+        if (g->comp_stride[c] <= 0 || g->comp_stride[c] > (1 << 20)) return TP_E_LAYOUT;
+        a.stride[c] = static_cast<int>(g->comp_stride[c]);
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(g->comp[c]);
+        const int64_t extent = (c == 0 && comp0_extent > 0) ? comp0_extent : (g->ng - 1) * g->comp_stride[c] + 1;
+        rng[nr++] = {lo, lo + extent * sizeof(double)};
+        if (g->comp_stride[c] > 8) stride_ok = false;       // too sparse to be worth staging
+    }
+    // merge overlapping / touching ranges (columns of one interleaved (ng,3) array)
+    std::sort(rng, rng + nr, [](const Range& x, const Range& y) { return x.lo < y.lo; });
+    Range seg[kMaxSeg]; int ns = 0;
+    for (int i = 0; i < nr; ++i) {
+        if (ns && rng[i].lo <= seg[ns - 1].hi) seg[ns - 1].hi = std::max(seg[ns - 1].hi, rng[i].hi);
+        else seg[ns++] = rng[i];
+    }
+    uint32_t off = kSmemHeader;
+    uint64_t total = kSmemHeader;
+    a.nseg = ns;
+    for (int s = 0; s < ns; ++s) {
+        const uint64_t bytes = seg[s].hi - seg[s].lo;
+        total += (bytes + 15) & ~15ull;
+        if (total > (1u << 20)) { total = ~0ull >> 1; break; }
+        a.seg[s].src = reinterpret_cast<const double*>(seg[s].lo);
+        a.seg[s].smem_off = off;
+        a.seg[s].n_doubles = static_cast<uint32_t>(bytes / sizeof(double));
+        a.seg[s].tma_bytes = (seg[s].lo & 15u) ? 0u : static_cast<uint32_t>(bytes & ~15ull);
+        off += static_cast<uint32_t>((bytes + 15) & ~15ull);
+    }
+    const DeviceProps& d = device_props();
+    staged = stride_ok && total <= static_cast<uint64_t>(d.smem_optin) - 1024;
+    smem_bytes = staged ? static_cast<size_t>(total) : 0;
+    if (staged) {
+        auto smem_of = [&](const double* ptr) -> uint32_t {
+            const uintptr_t u = reinterpret_cast<uintptr_t>(ptr);
+            for (int s = 0; s < ns; ++s)
+                if (u >= seg[s].lo && u < seg[s].hi) return a.seg[s].smem_off + static_cast<uint32_t>(u - seg[s].lo);
+            return 0;
+        };
+        a.r_smem_off = smem_of(g->r);
+        for (int c = 0; c < 6; ++c) a.comp_smem_off[c] = g->comp[c] ? smem_of(g->comp[c]) : 0;
+    } else {
+        a.nseg = 0;
+    }
+    return TP_OK;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t smem) {
+    if (smem > 48 * 1024)
+        TP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    return TP_OK;
+}
+
+template <bool VEC2, int FORMULA, bool STAGED>
+static int launch_gather_push(const GatherArgs& a, size_t smem, cudaStream_t s) {
+    auto kern = gather_push_kernel<VEC2, FORMULA, STAGED>;
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    const int64_t items = VEC2 ? (a.p.n + 1) / 2 : a.p.n;
+    const int blocks = grid_blocks(reinterpret_cast<const void*>(kern), smem, items);
+    kern<<<blocks, kThreads, smem, s>>>(a);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+template <bool VEC2, int FORMULA>
+static int launch_gather_push_s(const GatherArgs& a, size_t smem, bool staged, cudaStream_t s) {
+    return staged ? launch_gather_push<VEC2, FORMULA, true>(a, smem, s)
+                  : launch_gather_push<VEC2, FORMULA, false>(a, 0, s);
+}
+
+template <bool VEC2>
+static int launch_gather_push_f(const GatherArgs& a, int formula, size_t smem, bool staged, cudaStream_t s) {
+    switch (formula) {
+        case TP_INTERP_A: return launch_gather_push_s<VEC2, TP_INTERP_A>(a, smem, staged, s);
+        case TP_INTERP_B: return launch_gather_push_s<VEC2, TP_INTERP_B>(a, smem, staged, s);
+        case TP_INTERP_C: return launch_gather_push_s<VEC2, TP_INTERP_C>(a, smem, staged, s);
+        default: return TP_E_MODE;
+    }
+}
+
+template <int FORMULA, bool STAGED>
+static int launch_interp(const InterpArgs& a, size_t smem, cudaStream_t s) {
+    auto kern = interp_kernel<FORMULA, STAGED>;
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    const int blocks = grid_blocks(reinterpret_cast<const void*>(kern), smem, a.n);
+    kern<<<blocks, kThreads, smem, s>>>(a);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+// Entry point shared with host_path.cu
+int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
+                       int formula, uint64_t* status, cudaStream_t s) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    GatherArgs a;
+    std::memset(&a, 0, sizeof(a));
+    bool vec2 = false;
+    int rc = fill_particles(p, a.p, vec2);
+    if (rc) return rc;
+    if ((rc = fill_consts(k, a.k))) return rc;
+    if (axis < 0 || axis > 2) return TP_E_MODE;
+    if (!status) return TP_E_ARG;
+    size_t smem = 0; bool staged = false;
+    if ((rc = fill_grid(g, a, smem, staged))) return rc;
+    a.axis = axis;
+    a.status = reinterpret_cast<unsigned long long*>(status);
+    if (a.p.n == 0) return TP_OK;
+    return vec2 ? launch_gather_push_f<true>(a, formula, smem, staged, s)
+                : launch_gather_push_f<false>(a, formula, smem, staged, s);
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k, const double* E, int e_mode,
+                                 int64_t e_sn, int64_t e_sc, const double* B, int b_mode, int64_t b_sn,
+                                 int64_t b_sc, tp_stream_t stream) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    PushArgs a;
+    std::memset(&a, 0, sizeof(a));
+    bool vec2 = false;
+    int rc = fill_particles(p, a.p, vec2);
+    if (rc) return rc;
+    if ((rc = fill_consts(k, a.k))) return rc;
+    if ((rc = fill_field(E, e_mode, e_sn, e_sc, a.E))) return rc;
+    if ((rc = fill_field(B, b_mode, b_sn, b_sc, a.B))) return rc;
+    if (a.p.n == 0) return TP_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (vec2) {
+        const int blocks = grid_blocks(reinterpret_cast<const void*>(push_kernel<true>), 0, (a.p.n + 1) / 2);
+        push_kernel<true><<<blocks, kThreads, 0, s>>>(a);
+    } else {
+        const int blocks = grid_blocks(reinterpret_cast<const void*>(push_kernel<false>), 0, a.p.n);
+        push_kernel<false><<<blocks, kThreads, 0, s>>>(a);
+    }
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int tp_gather_push_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
+                                  int formula, uint64_t* status, tp_stream_t stream) {
+    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tp_status_reset(uint64_t* status, tp_stream_t stream) {
+    if (!status) return TP_E_ARG;
+    static const uint64_t init[4] = {0ull, ~0ull, 0ull, 0ull};
+    return static_cast<int>(cudaMemcpyAsync(status, init, sizeof(init), cudaMemcpyHostToDevice,
+                                            static_cast<cudaStream_t>(stream)));
+}
+
+extern "C" int tp_gather_smem_bytes(const tp_grid_fields* g, int64_t* bytes, int* staged) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    GatherArgs a;
+    std::memset(&a, 0, sizeof(a));
+    size_t smem = 0; bool st = false;
+    int rc = fill_grid(g, a, smem, st);
+    if (rc) return rc;
+    if (bytes) *bytes = static_cast<int64_t>(smem);
+    if (staged) *staged = st ? 1 : 0;
+    return TP_OK;
+}
+
+extern "C" int tp_interp1d_f64(const double* r, int64_t ng, double dr, double r_first, double r_last,
+                               const double* y, int ncomp, int64_t y_stride_c, int64_t y_stride_n,
+                               const double* xq, int64_t xq_stride, int64_t n, double* out,
+                               int64_t out_stride_c, int formula, uint64_t* status, tp_stream_t stream) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    if (!r || !y || !xq || !out || !status || n < 0 || ncomp < 1) return TP_E_ARG;
+    if (y_stride_n <= 0 || y_stride_c <= 0 || xq_stride <= 0 || out_stride_c < n) return TP_E_LAYOUT;
+    if (y_stride_c > 0x7fffffff) return TP_E_LAYOUT;
+    if (formula < TP_INTERP_A || formula > TP_INTERP_C) return TP_E_MODE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // The whole y block is described as "component 0" (with its full extent) so
+    // that the staging plan copies it once; the kernel walks the components.
+    tp_grid_fields g;
+    std::memset(&g, 0, sizeof(g));
+    g.r = r; g.ng = ng; g.dr = dr; g.r_first = r_first; g.r_last = r_last;
+    g.comp[0] = y; g.comp_stride[0] = y_stride_n;
+    InterpArgs a;
+    std::memset(&a, 0, sizeof(a));
+    size_t smem = 0; bool staged = false;
+    const int64_t extent = (ncomp - 1) * y_stride_c + (ng - 1) * y_stride_n + 1;
+    int rc = fill_grid(&g, a.g, smem, staged, extent);
+    if (rc) return rc;
+    a.g.stride[1] = static_cast<int>(y_stride_c);      // component stride rides in slot 1
+    a.g.status = reinterpret_cast<unsigned long long*>(status);
+    a.xq = xq; a.xq_stride = xq_stride; a.n = n; a.out = out; a.out_stride_c = out_stride_c; a.ncomp = ncomp;
+    if (n == 0) return TP_OK;
+    if (staged) {
+        switch (formula) {
+            case TP_INTERP_A: return launch_interp<TP_INTERP_A, true>(a, smem, s);
+            case TP_INTERP_B: return launch_interp<TP_INTERP_B, true>(a, smem, s);
+            default: return launch_interp<TP_INTERP_C, true>(a, smem, s);
+        }
+    }
+    switch (formula) {
+        case TP_INTERP_A: return launch_interp<TP_INTERP_A, false>(a, 0, s);
+        case TP_INTERP_B: return launch_interp<TP_INTERP_B, false>(a, 0, s);
+        default: return launch_interp<TP_INTERP_C, false>(a, 0, s);
+    }
+}

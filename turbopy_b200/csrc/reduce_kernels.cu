@@ -1,0 +1,119 @@
+// Kernel 3 of the hot path: kinetic-energy / momentum reduction for the
+// energy / moment Diagnostics.  The reference has no such function (parity
+// unpinned; definition and tolerance in oracle/moments.py): per particle
+//   m1 = sqrt(mass_sq + |p|^2/c2)         (gamma*m of turbopy/computetools.py:430-431)
+//   ke = |p|^2 / (m1 + mass)
+// and the sums {KE, Px, Py, Pz, sum|p|^2, n}.  24 B read per particle.
+// Deterministic: per-thread serial sums -> warp shuffle tree -> shared-memory
+// tree -> per-CTA partials; a second single-CTA pass folds the partials in a
+// fixed order (no atomics), so two runs on the same data agree bit for bit.
+#include "common.cuh"
+
+#include <cmath>
+
+namespace tp {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxBlocks = 2048;
+constexpr int kRedVals = 5;               // KE, Px, Py, Pz, |p|^2
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void block_sum(double (&v)[kRedVals], double* out) {
+    __shared__ double sh[kRedVals][kRedThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kRedVals; ++k) {
+        const double w = warp_sum(v[k]);
+        if (lane == 0) sh[k][warp] = w;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < kRedVals; ++k) {
+            double w = lane < kRedThreads / 32 ? sh[k][lane] : 0.0;
+            w = warp_sum(w);
+            if (lane == 0) out[k] = w;
+        }
+    }
+}
+
+__device__ __forceinline__ void accumulate(double px, double py, double pz, double mass, double mm,
+                                           const ConstRecip& c2, double (&acc)[kRedVals]) {
+    const double p2 = (px * px + py * py) + pz * pz;
+    const double m1 = sqrt(mm + div_const(p2, c2));
+    acc[0] += p2 / (m1 + mass);
+    acc[1] += px; acc[2] += py; acc[3] += pz; acc[4] += p2;
+}
+
+__global__ void __launch_bounds__(kRedThreads) moments_partial_kernel(const double* __restrict__ mom, int64_t sn,
+                                                                      int64_t sc, int64_t n, double mass, double mm,
+                                                                      ConstRecip c2, bool vec, double* scratch) {
+    double acc[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kRedThreads + threadIdx.x;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kRedThreads;
+    if (vec) {                                            // SoA, 128-bit loads
+        const int64_t npairs = n >> 1;
+        for (int64_t pr = gtid; pr < npairs; pr += gstride) {
+            const double2 a = ld2(mom + 2 * pr), b = ld2(mom + sc + 2 * pr), c = ld2(mom + 2 * sc + 2 * pr);
+            accumulate(a.x, b.x, c.x, mass, mm, c2, acc);
+            accumulate(a.y, b.y, c.y, mass, mm, c2, acc);
+        }
+        if ((n & 1) && gtid == 0) accumulate(mom[n - 1], mom[sc + n - 1], mom[2 * sc + n - 1], mass, mm, c2, acc);
+    } else {
+        for (int64_t i = gtid; i < n; i += gstride) {
+            const double* p = mom + i * sn;
+            accumulate(p[0], p[sc], p[2 * sc], mass, mm, c2, acc);
+        }
+    }
+    block_sum(acc, scratch + static_cast<int64_t>(blockIdx.x) * 8);
+}
+
+__global__ void __launch_bounds__(kRedThreads) moments_final_kernel(const double* scratch, int nblocks, int64_t n,
+                                                                    double* out8) {
+    double acc[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < nblocks; b += kRedThreads)
+#pragma unroll
+        for (int k = 0; k < kRedVals; ++k) acc[k] += scratch[static_cast<int64_t>(b) * 8 + k];
+    __shared__ double res[8];
+    block_sum(acc, res);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out8[0] = res[0]; out8[1] = res[1]; out8[2] = res[2]; out8[3] = res[3]; out8[4] = res[4];
+        out8[5] = static_cast<double>(n); out8[6] = 0.0; out8[7] = 0.0;
+    }
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" int64_t tp_reduce_scratch_doubles(void) { return static_cast<int64_t>(kRedMaxBlocks) * 8; }
+
+extern "C" int tp_reduce_moments_f64(const double* mom, int64_t stride_n, int64_t stride_c, int64_t n, double mass,
+                                     double mass_sq, double c2, double* out8, double* scratch, tp_stream_t stream) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    if (n < 0 || !out8 || !scratch || (n > 0 && !mom)) return TP_E_ARG;
+    if (stride_n <= 0 || stride_c <= 0) return TP_E_LAYOUT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ConstRecip c;
+    c.b = c2; c.rb = 1.0 / c2;
+    c.ok = std::isfinite(c.rb) && std::fabs(c.rb) >= 0x1p-960 && std::fabs(c.rb) <= 0x1p960;
+    const bool vec = layout_of(stride_n, stride_c, n) == kLayoutSoA && aligned16(mom) && (stride_c % 2 == 0) && n >= 2;
+    const int64_t items = vec ? (n + 1) / 2 : n;
+    int64_t blocks = (items + kRedThreads - 1) / kRedThreads;
+    const int64_t full = static_cast<int64_t>(d.sm_count) * 8;
+    if (blocks > full) blocks = full;
+    if (blocks > kRedMaxBlocks) blocks = kRedMaxBlocks;
+    if (blocks < 1) blocks = 1;
+    moments_partial_kernel<<<static_cast<int>(blocks), kRedThreads, 0, s>>>(mom, stride_n, stride_c, n, mass, mass_sq, c,
+                                                                          vec, scratch);
+    moments_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, static_cast<int>(blocks), n, out8);
+    count_launch(2);
+    return static_cast<int>(cudaGetLastError());
+}

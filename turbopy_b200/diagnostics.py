@@ -1,0 +1,119 @@
+"""Energy / moment diagnostics on device-resident particles (kernel 3).
+
+The reference has no energy diagnostic (turbopy/diagnostics.py holds only
+point / field / grid / clock diagnostics), so this is a NEW ``Diagnostic``
+registered through ``Diagnostic.register`` (turbopy/core.py:835-836) that
+follows the stock plumbing: ``inspect_resource`` grabs the shared momentum
+array, ``diagnose()`` runs every step, ``finalize()`` writes a CSV the way
+``CSVOutputUtility`` does (turbopy/diagnostics.py:14-59: one row per diagnose
+call, ``np.savetxt(..., delimiter=",")``).
+
+Per diagnose: one deterministic fp64 reduction (tp_reduce_moments_f64) into a
+row of a device buffer and, when torch.distributed is initialised, one
+all-reduce (NCCL) of that 8-double row -- no host sync until finalize().
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._host import Diagnostic
+from .sharding import allreduce_sum_
+
+MOMENT_NAMES = ("kinetic_energy", "px", "py", "pz", "p_squared", "count")
+
+
+def reduce_moments(momentum, mass, c2, out=None, scratch=None):
+    """``[KE, Px, Py, Pz, sum|p|^2, n, 0, 0]`` of an (n,3) CUDA momentum tensor,
+    with KE = sum |p|^2/(m1+mass), m1 = sqrt(mass**2 + |p|^2/c2) (the gamma*m
+    of turbopy/computetools.py:430-431).  Asynchronous; returns the 8-double
+    device tensor."""
+    if not (isinstance(momentum, torch.Tensor) and momentum.is_cuda and momentum.dtype == torch.float64):
+        raise TypeError("momentum must be a CUDA float64 tensor")
+    if momentum.ndim != 2 or momentum.shape[1] != 3:
+        raise ValueError("momentum must have shape (n,3)")
+    dev = momentum.device
+    lib = _lib.lib()
+    if out is None:
+        out = torch.empty(8, dtype=torch.float64, device=dev)
+    if scratch is None:
+        scratch = torch.empty(int(lib.tp_reduce_scratch_doubles()), dtype=torch.float64, device=dev)
+    sn, sc = momentum.stride()
+    if momentum.shape[0] <= 1:
+        sn = max(sn, 1)
+    with torch.cuda.device(dev):
+        _lib.check(lib.tp_reduce_moments_f64(
+            C.c_void_p(momentum.data_ptr()), sn, sc, momentum.shape[0],
+            float(mass), float(mass ** 2), float(c2),
+            C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()),
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
+
+
+class KineticEnergyDiagnostic(Diagnostic):
+    """``input_data``: ``"momentum"`` (resource name of the shared (n,3)
+    momentum tensor), ``"mass"``, optional ``"c2"`` (default BorisPush's
+    2.9979e8**2), ``"interval"`` (steps between reductions, default 1),
+    ``"filename"`` / ``"directory"`` for the CSV, ``"allreduce"`` (default
+    True: sum over ranks when torch.distributed is initialised)."""
+
+    def __init__(self, owner, input_data):
+        super().__init__(owner, input_data)
+        self.momentum = None
+        self.mass = float(input_data["mass"])
+        self.c2 = float(input_data.get("c2", 2.9979e8 ** 2))
+        self.interval = int(input_data.get("interval", 1))
+        self.allreduce = bool(input_data.get("allreduce", True))
+        self.rows = None
+        self._scratch = None
+        self._calls = 0
+        self._used = 0
+
+    def inspect_resource(self, resource):
+        name = self.input_data["momentum"]
+        if name in resource:
+            self.momentum = resource[name]
+
+    def initialize(self):
+        steps = int(self.owner.clock.num_steps)
+        self._capacity = steps // self.interval + 2
+
+    def diagnose(self):
+        self._calls += 1
+        if (self._calls - 1) % self.interval:
+            return
+        if self.momentum is None:
+            raise RuntimeError("Diagnostic field {} not found".format(self.input_data["momentum"]))
+        if self.rows is None:
+            dev = self.momentum.device
+            cap = getattr(self, "_capacity", 1024)
+            self.rows = torch.zeros((cap, 8), dtype=torch.float64, device=dev)
+        if self._used >= self.rows.shape[0]:
+            self.rows = torch.cat([self.rows, torch.zeros_like(self.rows)])
+        row = self.rows[self._used]
+        if self._scratch is None:
+            self._scratch = torch.empty(int(_lib.lib().tp_reduce_scratch_doubles()), dtype=torch.float64,
+                                        device=self.momentum.device)
+        reduce_moments(self.momentum, self.mass, self.c2, out=row, scratch=self._scratch)
+        if self.allreduce:
+            allreduce_sum_(row)
+        self._used += 1
+
+    def values(self):
+        """Host copy of the rows recorded so far: (k, 6) [KE, Px, Py, Pz, |p|^2, n]."""
+        if self.rows is None:
+            return np.zeros((0, 6))
+        return self.rows[:self._used, :6].cpu().numpy()
+
+    def finalize(self):
+        self.diagnose()
+        filename = self.input_data.get("filename")
+        if filename:
+            directory = self.input_data.get("directory", "")
+            if directory:
+                os.makedirs(directory, exist_ok=True)
+                filename = os.path.join(directory, filename)
+            with open(filename, "wb") as f:
+                np.savetxt(f, self.values(), delimiter=",")

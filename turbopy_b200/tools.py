@@ -1,0 +1,565 @@
+"""Drop-in ComputeTools for turboPy's particle hot path, backed by the sm_100a
+kernels in libturbopy_b200.so.
+
+Same registry names, constructor and call signatures as the stock tools in
+turbopy/computetools.py, so Simulation / PhysicsModule / Grid / Clock /
+Diagnostic code is untouched:
+
+* ``BorisPush.push(position, momentum, charge, mass, E, B)``   (computetools.py:407)
+* ``Interpolators.interpolate1D(x, y, kind='linear')``           (computetools.py:459)
+* ``FiniteDifference.setup_ddx / centered_difference / upwind_left / del2_radial``
+                                                               (computetools.py:87-223)
+
+plus one additive method, ``BorisPush.gather_push``, the fused field gather +
+push of ``ChargedParticle.update`` (tests/fixtures/particle_in_field/
+particle_in_field.py:61-63) for N particles.
+
+Arrays: resident ``torch.float64`` CUDA tensors (any of the layouts the C ABI
+accepts; SoA from :func:`turbopy_b200.particles.soa_particles` is the fast one)
+are updated in place on the current CUDA stream, asynchronously.  numpy arrays
+(what the reference's callers pass) take the end-to-end host path: they are
+streamed through the GPU by the library and hold the result on return.  Either
+way the arithmetic runs in the CUDA kernels; there is no CPU implementation in
+this package, and calls raise if the library or a B200 is missing.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._host import ComputeTool
+
+_FORMULAS = {
+    "A": _lib.TP_INTERP_A, "create_interpolator": _lib.TP_INTERP_A,
+    "B": _lib.TP_INTERP_B, "interp": _lib.TP_INTERP_B, "linear": _lib.TP_INTERP_B,
+    "C": _lib.TP_INTERP_C, "interp1d_nd": _lib.TP_INTERP_C,
+}
+
+
+# --------------------------------------------------------------------------- helpers
+def _is_cuda(t):
+    return isinstance(t, torch.Tensor) and t.is_cuda
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_f64(t, what):
+    dt = t.dtype
+    if dt not in (torch.float64, np.dtype(np.float64)):
+        raise TypeError(f"{what} must be float64, got {dt}")
+
+
+def _n3_strides(t, what):
+    """(stride_n, stride_c) in elements of a logical (n,3) array."""
+    if t.ndim != 2:
+        # the reference fails the same way on (3,) particles (m1[:, np.newaxis])
+        raise IndexError(f"{what} must be a 2-D (n,3) array, got shape {tuple(t.shape)}")
+    if t.shape[1] != 3:
+        raise ValueError(f"{what} must have shape (n,3), got {tuple(t.shape)}")
+    _require_f64(t, what)
+    if isinstance(t, torch.Tensor):
+        sn, sc = t.stride()
+    else:
+        if t.strides[0] % 8 or t.strides[1] % 8:
+            raise ValueError(f"{what}: strides must be multiples of 8 bytes")
+        sn, sc = t.strides[0] // 8, t.strides[1] // 8
+    if t.shape[0] <= 1:
+        sn = max(sn, 1)
+    if sn <= 0 or sc <= 0:
+        raise ValueError(f"{what}: negative or zero strides are not supported")
+    return int(sn), int(sc)
+
+
+def _ptr(t):
+    if isinstance(t, torch.Tensor):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def _particles_struct(position, momentum):
+    psn, psc = _n3_strides(position, "position")
+    msn, msc = _n3_strides(momentum, "momentum")
+    if position.shape[0] != momentum.shape[0]:
+        raise ValueError("position and momentum must have the same number of particles")
+    return _lib.Particles(_ptr(position), psn, psc, _ptr(momentum), msn, msc, int(position.shape[0]))
+
+
+def _push_consts(charge, mass, dt, c2):
+    # mass ** 2 exactly as turbopy/computetools.py:430 evaluates it (Python /
+    # numpy scalar power), so the kernel starts from the reference's own value.
+    return _lib.PushConsts(float(charge), float(mass ** 2), float(dt), float(c2))
+
+
+class _FieldArg:
+    """E or B of ``push`` lowered to (pointer, mode, strides) + keep-alives."""
+
+    def __init__(self, F, name, n, device):
+        self.keep = None
+        self.sn = self.sc = 0
+        if _is_cuda(F):
+            _require_f64(F, name)
+            if F.ndim == 2 and F.shape == (n, 3) and n != 1:
+                self.mode = _lib.TP_FIELD_PER_PARTICLE
+                self.sn, self.sc = (int(s) for s in F.stride())
+                if self.sn <= 0 or self.sc <= 0:
+                    raise ValueError(f"{name}: unsupported strides")
+                self.keep = F
+            elif F.shape in ((3,), (1, 3)):
+                self.mode = _lib.TP_FIELD_UNIFORM_DEV
+                self.keep = F.reshape(3).contiguous()
+            else:
+                raise ValueError(f"{name} must have shape (3,), (1,3) or (n,3); got {tuple(F.shape)}")
+            self.ptr = self.keep.data_ptr()
+            return
+        A = np.asarray(F.cpu() if isinstance(F, torch.Tensor) else F, dtype=np.float64)
+        if A.ndim == 0:
+            if name == "B":
+                # np.cross(vminus, t) with a scalar t (computetools.py:436)
+                raise ValueError("incompatible dimensions for cross product\n(dimension must be 2 or 3)")
+            A = np.full(3, float(A))        # dt*E*charge/2 broadcasts a scalar E
+        if A.shape in ((3,), (1, 3)):
+            self.mode = _lib.TP_FIELD_UNIFORM_HOST
+            self.keep = (C.c_double * 3)(*A.reshape(3))
+            self.ptr = C.addressof(self.keep)
+        elif A.shape == (n, 3):
+            self.mode = _lib.TP_FIELD_PER_PARTICLE
+            if device is None:              # host path: C-order per-particle array
+                self.keep = np.ascontiguousarray(A)
+                self.ptr = self.keep.ctypes.data
+            else:
+                self.keep = torch.from_numpy(np.ascontiguousarray(A)).to(device)
+                self.ptr = self.keep.data_ptr()
+            self.sn, self.sc = 3, 1
+        else:
+            raise ValueError(f"{name} must have shape (3,), (1,3) or (n,3); got {A.shape}")
+
+
+class GridOnDevice:
+    """Device copies of the ``Grid`` attributes the kernels read (uploaded once
+    per grid and device): ``r`` (turbopy/core.py:666-667), ``cell_widths`` (:670),
+    and the host scalars ``dr``, ``r[0]``, ``r[-1]``."""
+
+    _cache = {}
+
+    def __init__(self, r_host, dr, device):
+        r_host = np.ascontiguousarray(np.asarray(r_host, dtype=np.float64))
+        self.ng = int(r_host.shape[0])
+        self.dr = float(dr)
+        self.r_first = float(r_host[0])
+        self.r_last = float(r_host[-1])
+        self.r = torch.from_numpy(r_host).to(device)
+        self._widths = None
+        self._r_host = r_host
+
+    @property
+    def cell_widths(self):
+        if self._widths is None:
+            self._widths = torch.from_numpy(self._r_host[1:] - self._r_host[:-1]).to(self.r.device)
+        return self._widths
+
+    @classmethod
+    def of(cls, grid, device):
+        device = torch.device(device)
+        key = (id(grid), device.type, device.index if device.index is not None else torch.cuda.current_device())
+        hit = cls._cache.get(key)
+        if hit is None or hit[0] is not grid:
+            hit = (grid, cls(grid.r, grid.dr, device))
+            cls._cache[key] = hit
+        return hit[1]
+
+
+class GatherStatus:
+    """The 4-word device status block of the gather kernels, polled lazily."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            self.words = torch.zeros(4, dtype=torch.int64, device=self.device)
+            self.reset()
+
+    def reset(self):
+        _lib.check(_lib.lib().tp_status_reset(C.c_void_p(self.words.data_ptr()), _stream_ptr(self.device)))
+
+    def read(self):
+        w = self.words.cpu().numpy().view(np.uint64)
+        return int(w[0]), int(w[1]), int(w[2])
+
+    @staticmethod
+    def message(count, first, bits):
+        why = []
+        if bits & _lib.TP_ST_BELOW:
+            why.append("below the interpolation range's minimum value")
+        if bits & _lib.TP_ST_ABOVE:
+            why.append("above the interpolation range's maximum value")
+        if bits & _lib.TP_ST_BAD_WINDOW:
+            why.append("Error finding requested point in the grid")
+        return (f"{count} particle coordinate(s) outside the grid (first index {first}): "
+                + "; ".join(why) + " -- those particles were left unchanged")
+
+    def check(self):
+        """Raise like the reference would have: ValueError for the interp1d
+        bounds check (formulas B, C), AssertionError for create_interpolator's
+        asserts (formula A, turbopy/core.py:726-729)."""
+        count, first, bits = self.read()
+        if count:
+            self.reset()
+            exc = AssertionError if bits & _lib.TP_ST_BAD_WINDOW else ValueError
+            raise exc(self.message(count, first, bits))
+
+
+def _grid_components(F, name, ng):
+    """Lower a grid field to three (tensor-or-None, node stride) pairs."""
+    if F is None or (np.isscalar(F) and F == 0):
+        return [(None, 1)] * 3
+    if isinstance(F, (tuple, list)):
+        if len(F) != 3:
+            raise ValueError(f"{name}: a component tuple needs 3 entries (None = zero component)")
+        out = []
+        for c, comp in enumerate(F):
+            if comp is None:
+                out.append((None, 1))
+                continue
+            if comp.ndim != 1 or comp.shape[0] != ng:
+                raise ValueError(f"{name}[{c}] must have shape ({ng},), got {tuple(comp.shape)}")
+            _require_f64(comp, f"{name}[{c}]")
+            st = comp.stride(0) if isinstance(comp, torch.Tensor) else comp.strides[0] // 8
+            out.append((comp, int(st)))
+        return out
+    if getattr(F, "ndim", None) == 2 and tuple(F.shape) == (ng, 3):
+        # Grid.generate_field(3) layout (turbopy/core.py:675-698)
+        _require_f64(F, name)
+        return [(F[:, c], int(F[:, c].stride(0) if isinstance(F, torch.Tensor) else F[:, c].strides[0] // 8))
+                for c in range(3)]
+    raise ValueError(f"{name} must be None, an ({ng},3) array, or a 3-tuple of ({ng},) arrays / None; "
+                     "a bare (ng,) array is ambiguous (which component?)")
+
+
+# --------------------------------------------------------------------------- BorisPush
+class BorisPush(ComputeTool):
+    """Calculate charged particle motion in electric and magnetic fields
+    (relativistic Boris push) on a B200.
+
+    Replaces ``turbopy.computetools.BorisPush`` (computetools.py:384-441) under
+    the same name; ``input_data`` takes no options the stock tool does not have.
+    As in the reference, the constructor touches neither the clock, the grid
+    nor the device; ``owner.clock.dt`` is read at call time (:427).
+    """
+
+    def __init__(self, owner, input_data):
+        super().__init__(owner, input_data)
+        self.c2 = 2.9979e8 ** 2             # computetools.py:405 (pinned by tests/test_computetools.py:12)
+        self._status = {}
+
+    # -- the reference method ------------------------------------------------
+    def push(self, position, momentum, charge, mass, E, B):
+        """Update position and momentum in place (computetools.py:407-441).
+
+        ``position``/``momentum``: (n,3) float64, CUDA tensors (resident path)
+        or numpy arrays (end-to-end host path).  ``E``/``B``: anything the
+        reference broadcasts against (n,3): (3,), (1,3) or (n,3).
+        """
+        k = _push_consts(charge, mass, self.owner.clock.dt, self.c2)
+        lib = _lib.lib()
+        if _is_cuda(position):
+            if not _is_cuda(momentum) or momentum.device != position.device:
+                raise TypeError("position and momentum must live on the same CUDA device")
+            p = _particles_struct(position, momentum)
+            dev = position.device
+            e = _FieldArg(E, "E", p.n, dev)
+            b = _FieldArg(B, "B", p.n, dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.tp_boris_push_f64(C.byref(p), C.byref(k),
+                                                 C.c_void_p(e.ptr), e.mode, e.sn, e.sc,
+                                                 C.c_void_p(b.ptr), b.mode, b.sn, b.sc, _stream_ptr(dev)))
+            return None
+        if isinstance(position, np.ndarray) and isinstance(momentum, np.ndarray):
+            p = _particles_struct(position, momentum)
+            e = _FieldArg(E, "E", p.n, None)
+            b = _FieldArg(B, "B", p.n, None)
+            _lib.check(lib.tp_boris_push_host_f64(C.byref(p), C.byref(k),
+                                                  C.c_void_p(e.ptr), int(e.mode == _lib.TP_FIELD_PER_PARTICLE),
+                                                  C.c_void_p(b.ptr), int(b.mode == _lib.TP_FIELD_PER_PARTICLE)))
+            return None
+        raise TypeError("position/momentum must both be CUDA float64 tensors or both numpy float64 arrays")
+
+    # -- the fused path --------------------------------------------------------
+    def gather_push(self, position, momentum, charge, mass, E_grid=None, B_grid=None,
+                    axis=0, formula="interp", grid=None):
+        """Gather E and B at ``position[:, axis]`` by linear interpolation of the
+        grid fields and push, in one kernel.
+
+        ``E_grid`` / ``B_grid``: ``None`` (zero field), an ``(ng,3)`` array
+        (``Grid.generate_field(3)``), or a 3-tuple of ``(ng,)`` arrays / ``None``
+        per component.  ``formula`` selects the reference's rounding: ``"interp"``
+        (``Interpolators.interpolate1D`` -> numpy.interp, the default),
+        ``"create_interpolator"`` (``Grid.create_interpolator``) or
+        ``"interp1d_nd"`` (scipy's N-D linear path).  ``grid``: the owner's
+        ``Grid`` by default.  Particles whose coordinate is outside the grid are
+        left unchanged and reported by :meth:`check_status` (the reference
+        raises before pushing anyone; a kernel cannot).
+        """
+        grid = self.owner.grid if grid is None else grid
+        k = _push_consts(charge, mass, self.owner.clock.dt, self.c2)
+        code = _FORMULAS[formula]
+        if axis not in (0, 1, 2):
+            raise ValueError("axis must be 0, 1 or 2")
+        lib = _lib.lib()
+        p = _particles_struct(position, momentum)
+        ng = int(grid.num_points) if hasattr(grid, "num_points") else int(len(grid.r))
+        comps = _grid_components(E_grid, "E_grid", ng) + _grid_components(B_grid, "B_grid", ng)
+        g = _lib.GridFields()
+        g.ng, g.dr = ng, float(grid.dr)
+        if _is_cuda(position):
+            dev = position.device
+            gd = GridOnDevice.of(grid, dev)
+            g.r, g.r_first, g.r_last = gd.r.data_ptr(), gd.r_first, gd.r_last
+            for c, (t, st) in enumerate(comps):
+                if t is not None and not (_is_cuda(t) and t.device == dev):
+                    raise TypeError("grid fields must be CUDA tensors on the particles' device")
+                g.comp[c] = t.data_ptr() if t is not None else None
+                g.comp_stride[c] = st
+            status = self._status.get(dev)
+            if status is None:
+                status = self._status[dev] = GatherStatus(dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.tp_gather_push_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
+                                                  C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
+            return None
+        if isinstance(position, np.ndarray):
+            r = np.ascontiguousarray(grid.r, dtype=np.float64)
+            g.r, g.r_first, g.r_last = r.ctypes.data, float(r[0]), float(r[-1])
+            for c, (t, st) in enumerate(comps):
+                if t is not None and not isinstance(t, np.ndarray):
+                    raise TypeError("host path: grid fields must be numpy arrays")
+                g.comp[c] = t.ctypes.data if t is not None else None
+                g.comp_stride[c] = st
+            words = (C.c_uint64 * 4)()
+            _lib.check(lib.tp_gather_push_host_f64(C.byref(p), C.byref(k), C.byref(g), axis, code, words))
+            if words[0]:
+                exc = AssertionError if words[2] & _lib.TP_ST_BAD_WINDOW else ValueError
+                raise exc(GatherStatus.message(int(words[0]), int(words[1]), int(words[2])))
+            return None
+        raise TypeError("position/momentum must both be CUDA float64 tensors or both numpy float64 arrays")
+
+    def check_status(self):
+        """Poll the device error flags of :meth:`gather_push` (one small D2H
+        copy + sync per device): raises ValueError / AssertionError if any
+        particle left the grid since the last check."""
+        for status in self._status.values():
+            status.check()
+
+
+# --------------------------------------------------------------------------- Interpolators
+class _Interp1D:
+    """The callable ``interpolate1D`` returns: ``f(x_new)`` evaluates the
+    piecewise-linear interpolant on the GPU with scipy's rounding --
+    numpy.interp's for 1-D ``y`` (formula B), ``interp1d._call_linear``'s for
+    N-D ``y`` (formula C; interpolation along the last axis, interp1d's
+    default axis=-1).  Out-of-range points raise ValueError like
+    ``interp1d(bounds_error=True)``."""
+
+    def __init__(self, x, y):
+        self._numpy = not isinstance(x, torch.Tensor)
+        if self._numpy:
+            if not torch.cuda.is_available():
+                _lib.check(_lib.TP_E_NODEVICE)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(dev)
+            y = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.float64))).to(dev)
+        if not (_is_cuda(x) and _is_cuda(y)) or x.device != y.device:
+            raise TypeError("x and y must be CUDA float64 tensors on one device (or numpy arrays)")
+        _require_f64(x, "x"); _require_f64(y, "y")
+        if x.ndim != 1:
+            raise ValueError("the x array must have exactly one dimension.")
+        if y.ndim == 0:
+            raise ValueError("the y array must have at least one dimension.")
+        if y.shape[-1] != x.shape[0]:
+            raise ValueError("x and y arrays must be equal in length along interpolation axis.")
+        if x.shape[0] < 2:
+            raise ValueError("x and y arrays must have at least 2 entries")
+        self.x = x.contiguous()
+        self.y = y
+        self._y2 = y.reshape(-1, y.shape[-1]).contiguous()
+        ends = self.x[[0, -1]].cpu()
+        self.r_first, self.r_last = float(ends[0]), float(ends[1])
+        self.dr = (self.r_last - self.r_first) / (x.shape[0] - 1)      # index guess only
+        self.formula = _lib.TP_INTERP_B if y.ndim == 1 else _lib.TP_INTERP_C
+        self._status = GatherStatus(x.device)
+
+    def __call__(self, x_new):
+        dev = self.x.device
+        as_numpy = not isinstance(x_new, torch.Tensor)
+        xq = torch.as_tensor(np.asarray(x_new, dtype=np.float64)).to(dev) if as_numpy else x_new
+        if not _is_cuda(xq):
+            xq = xq.to(dev)
+        _require_f64(xq, "x_new")
+        shape = tuple(xq.shape)
+        xq = xq.reshape(-1).contiguous()
+        n = xq.shape[0]
+        k = self._y2.shape[0]
+        out = torch.empty((k, n), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().tp_interp1d_f64(
+                C.c_void_p(self.x.data_ptr()), self.x.shape[0], self.dr, self.r_first, self.r_last,
+                C.c_void_p(self._y2.data_ptr()), k, self._y2.stride(0), self._y2.stride(1),
+                C.c_void_p(xq.data_ptr()), 1, n,
+                C.c_void_p(out.data_ptr()), n, self.formula,
+                C.c_void_p(self._status.words.data_ptr()), _stream_ptr(dev)))
+        count, first, bits = self._status.read()
+        if count:
+            self._status.reset()
+            bad = float(xq[first])
+            side = "below" if bits & _lib.TP_ST_BELOW and bad < self.r_first else "above"
+            bound = self.r_first if side == "below" else self.r_last
+            raise ValueError(f"A value ({bad}) in x_new is {side} the interpolation range's "
+                             f"{'minimum' if side == 'below' else 'maximum'} value ({bound}).")
+        out = out.reshape(self.y.shape[:-1] + shape)
+        return out.cpu().numpy() if (as_numpy and self._numpy) else out
+
+
+class Interpolators(ComputeTool):
+    """Interpolate a function y(x) given y at grid points in x -- replaces
+    ``turbopy.computetools.Interpolators`` (computetools.py:444-481)."""
+
+    def __init__(self, owner, input_data):
+        super().__init__(owner, input_data)
+
+    def interpolate1D(self, x, y, kind='linear'):
+        """Return an interpolating function ``f(x_new)`` (computetools.py:459-481).
+        Only ``kind='linear'`` is on the particle hot path and implemented here;
+        spline kinds raise (they are scipy/LAPACK code, not a B200 kernel)."""
+        if kind != 'linear':
+            raise NotImplementedError(
+                f"interpolate1D(kind={kind!r}): only 'linear' is implemented by turbopy_b200 "
+                "(the field gather of the particle hot path); use the stock turboPy tool for splines")
+        return _Interp1D(x, y)
+
+
+# --------------------------------------------------------------------------- FiniteDifference
+class BandedOperator:
+    """What the ``FiniteDifference`` matrix builders return in place of a
+    ``scipy.sparse.dia_matrix``: supports ``D @ f`` / ``D.dot(f)`` on CUDA
+    tensors (and numpy arrays, staged through the GPU), ``shape``, ``offsets``,
+    ``data`` and ``toarray()`` -- the surface tests/test_computetools.py:141-291
+    uses.  ``apply`` is the kernel launch; the entries are only materialised on
+    request (by applying the operator to unit vectors)."""
+
+    def __init__(self, n, offsets, apply_fn, device):
+        self.shape = (n, n)
+        self.offsets = np.asarray(offsets, dtype=np.int32)
+        self._apply = apply_fn
+        self._device = device
+        self._dense = None
+
+    def dot(self, f):
+        if isinstance(f, torch.Tensor):
+            if not _is_cuda(f):
+                raise TypeError("operand must be a CUDA tensor (or a numpy array)")
+            _require_f64(f, "operand")
+            if f.ndim != 1 or f.shape[0] != self.shape[0]:
+                raise ValueError("dimension mismatch")
+            return self._apply(f.contiguous())
+        a = np.asarray(f, dtype=np.float64)
+        if a.ndim != 1 or a.shape[0] != self.shape[0]:
+            raise ValueError("dimension mismatch")
+        out = self._apply(torch.from_numpy(np.ascontiguousarray(a)).to(self._device))
+        return out.cpu().numpy()
+
+    __matmul__ = dot
+
+    def toarray(self):
+        if self._dense is None:
+            n = self.shape[0]
+            eye = torch.eye(n, dtype=torch.float64, device=self._device)
+            self._dense = torch.stack([self._apply(eye[j].contiguous()) for j in range(n)], dim=1).cpu().numpy()
+        return self._dense
+
+    @property
+    def data(self):
+        """scipy's dia layout: ``data[k, j] = A[j - offsets[k], j]``."""
+        A = self.toarray()
+        n = self.shape[0]
+        out = np.zeros((len(self.offsets), n))
+        for k, off in enumerate(self.offsets):
+            j = np.arange(max(0, off), min(n, n + off))
+            out[k, j] = A[j - off, j]
+        return out
+
+
+class FiniteDifference(ComputeTool):
+    """Finite-difference stencils on the 1-D grid -- replaces
+    ``turbopy.computetools.FiniteDifference`` (computetools.py:62-381) for the
+    operators on the hot path.  ``input_data["method"]`` selects
+    ``"centered"`` / ``"upwind_left"`` for :meth:`setup_ddx`."""
+
+    def __init__(self, owner, input_data):
+        super().__init__(owner, input_data)
+        self.dr = self.owner.grid.dr            # cached like the reference (:85)
+
+    def setup_ddx(self):
+        assert (self.input_data["method"] in ["centered", "upwind_left"])
+        if self.input_data["method"] == "centered":
+            return self.centered_difference
+        if self.input_data["method"] == "upwind_left":
+            return self.upwind_left
+
+    def _device_in(self, y):
+        """(device tensor, was_numpy)"""
+        if isinstance(y, torch.Tensor):
+            if not _is_cuda(y):
+                raise TypeError("y must be a CUDA tensor (or a numpy array)")
+            t = y
+        else:
+            if not torch.cuda.is_available():
+                _lib.check(_lib.TP_E_NODEVICE)
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.float64))).cuda()
+        _require_f64(t, "y")
+        n = int(self.owner.grid.num_points)
+        if t.ndim != 1 or t.shape[0] != n:
+            raise ValueError(f"could not broadcast input array from shape {tuple(t.shape)} into shape ({n},)")
+        return t.contiguous(), not isinstance(y, torch.Tensor)
+
+    def centered_difference(self, y):
+        """Centered estimate of dy/dx; a fresh array (computetools.py:104-120)."""
+        t, was_numpy = self._device_in(y)
+        d = torch.empty_like(t)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.lib().tp_fd_centered_f64(C.c_void_p(t.data_ptr()), C.c_void_p(d.data_ptr()),
+                                                     t.shape[0], 2 * self.dr, _stream_ptr(t.device)))
+        return d.cpu().numpy() if was_numpy else d
+
+    def upwind_left(self, y):
+        """Left upwind estimate of dy/dx; a fresh array (computetools.py:122-138)."""
+        t, was_numpy = self._device_in(y)
+        w = GridOnDevice.of(self.owner.grid, t.device).cell_widths
+        d = torch.empty_like(t)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.lib().tp_fd_upwind_left_f64(C.c_void_p(t.data_ptr()), C.c_void_p(w.data_ptr()),
+                                                        C.c_void_p(d.data_ptr()), t.shape[0],
+                                                        _stream_ptr(t.device)))
+        return d.cpu().numpy() if was_numpy else d
+
+    def del2_radial(self, device=None):
+        """Operator for (1/r)(d/dr)(r df/dr) (computetools.py:189-223): apply it
+        with ``D @ f``.  The tridiagonal rows are rebuilt inside the kernel
+        from ``Grid.r`` and ``dr``; no diagonals are stored."""
+        if not torch.cuda.is_available():
+            _lib.check(_lib.TP_E_NODEVICE)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        gd = GridOnDevice.of(self.owner.grid, dev)
+        g1 = 1 / (2.0 * self.dr)                # :197
+        g2 = 1 / (self.dr ** 2)                 # :211
+        n = gd.ng
+
+        def apply(f):
+            out = torch.empty_like(f)
+            with torch.cuda.device(f.device):
+                _lib.check(_lib.lib().tp_fd_del2_radial_apply_f64(
+                    C.c_void_p(f.data_ptr()), C.c_void_p(gd.r.data_ptr()), C.c_void_p(out.data_ptr()),
+                    n, g1, g2, _stream_ptr(f.device)))
+            return out
+
+        return BandedOperator(n, [-1, 0, 1], apply, dev)
