@@ -193,9 +193,13 @@ int tp_graph_destroy(void* graph_exec);
 /* ---- launch accounting and self tests -------------------------------------- */
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t tp_launch_count(void);
-/* device self-test of the shared-reciprocal division against IEEE a/b on n
- * pseudo-random pairs; *mismatches must come back 0 */
-int tp_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches, tp_stream_t stream);
+/* device self-test of the shared-reciprocal division ("Arithmetic
+ * contract") against IEEE a/b on n pseudo-random pairs, including zeros,
+ * infinities and operands outside the fast path's domain: *mismatches = pairs
+ * the fast path accepted but got wrong (must be 0), *fast_taken = pairs it
+ * accepted (may be NULL) */
+int tp_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches, int64_t* fast_taken,
+                         tp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -36,9 +36,11 @@ def to_layout(tp, arr, layout):
 
 def test_division_selftest(tp):
     from turbopy_b200 import _lib
-    bad = C.c_int64(-1)
-    _lib.check(_lib.lib().tp_selftest_division(200_000_000, 12345, C.byref(bad), None))
+    bad, taken = C.c_int64(-1), C.c_int64(-1)
+    n = 200_000_000
+    _lib.check(_lib.lib().tp_selftest_division(n, 12345, C.byref(bad), C.byref(taken), None))
     assert bad.value == 0
+    assert taken.value > n // 2          # the fast path is the common case, not a dead branch
 
 
 def test_known_answer_crossed_fields(tp, golden):

@@ -156,6 +156,7 @@ def test_fused_vs_oracle(tp, formula, ng, layout):
     pos0, mom0 = thermal_ensemble(n, seed=ng)
     pos0[:, 0] = np.random.default_rng(ng + 1).uniform(0.02, 0.98, n)
     pos0[:5, 0] = grid.r[[0, 1, ng // 2, ng - 2, ng - 1]]         # exactly on nodes, both ends
+    mom0[0, 0], mom0[4, 0] = abs(mom0[0, 0]), -abs(mom0[4, 0])      # the two end particles drift inward
     comps = smooth_fields(grid)
     E = torch.from_numpy(np.stack(comps[:3], axis=1)).cuda()        # (ng,3) generate_field(3) layout
     Bt = tuple(torch.from_numpy(c).cuda() for c in comps[3:])       # three separate (ng,) arrays

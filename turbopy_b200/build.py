@@ -30,6 +30,8 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "-I", INCLUDE,
 ]
+# tuning experiments only (e.g. TURBOPY_B200_NVCC_FLAGS="-DTP_MIN_BLOCKS=3")
+NVCC_FLAGS += os.environ.get("TURBOPY_B200_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

@@ -8,7 +8,8 @@ namespace tp {
 
 struct PushK {            // kernel-side constants of one push call
     double dt, q, mm;     // clock.dt, charge, mass**2
-    ConstRecip c2;        // BorisPush.c2 and RN(1/c2)
+    double c2, rc2;       // BorisPush.c2 and RN(1/c2) (host-rounded)
+    int    fast_ok;       // c2 is usable by the FAST division policy
 };
 
 struct Vec3 { double x, y, z; };
@@ -24,29 +25,32 @@ __device__ __forceinline__ Vec3 dt_field_q(const PushK& k, const Vec3& F) {
 }
 
 // One Boris step.  eq = (dt*E)*q, bq = (dt*B)*q (see dt_field_q); x and p are
-// updated in place.  Divisions by 2 are exact multiplications by 0.5; the three
-// quotients that share a denominator (m1, 1+|t|^2, m2) use one correctly
-// rounded reciprocal plus a Markstein correction each (common.cuh) and are
-// bit-identical to IEEE division.
+// updated in place.  Divisions by 2 are exact multiplications by 0.5.  FAST:
+// the quotients that share a denominator (m1, 1+|t|^2, m2, c2) use one
+// correctly rounded reciprocal each and record their validity in `g`
+// (common.cuh); the caller must test guard_ok(g) && finite3(x) and recompute
+// with FAST = false otherwise.  FAST = false is plain IEEE arithmetic.
+template <bool FAST>
 __device__ __forceinline__ void boris_step(const PushK& k, const Vec3& eq, const Vec3& bq,
-                                           Vec3& x, Vec3& p) {
+                                           Vec3& x, Vec3& p, Guard& g) {
+    const Recip<FAST> rc2 = const_recip<FAST>(k.c2, k.rc2);
     // :429  vminus = momentum + dt*E*charge/2
     const double hx = eq.x * 0.5, hy = eq.y * 0.5, hz = eq.z * 0.5;
     const double vmx = p.x + hx, vmy = p.y + hy, vmz = p.z + hz;
     // :430-431  m1 = sqrt(mass**2 + sum(p*p)/c2)   (old momentum)
     const double pp = (p.x * p.x + p.y * p.y) + p.z * p.z;
-    const double m1 = sqrt(k.mm + div_const(pp, k.c2));
+    const double m1 = sqrt(k.mm + quot<FAST>(pp, rc2, g));
     // :433  t = dt*B*charge/m1/2
-    const Recip r1 = make_recip(m1);
-    const double tx = div_shared(bq.x, r1) * 0.5;
-    const double ty = div_shared(bq.y, r1) * 0.5;
-    const double tz = div_shared(bq.z, r1) * 0.5;
+    const Recip<FAST> r1 = make_recip<FAST>(m1, g);
+    const double tx = quot<FAST>(bq.x, r1, g) * 0.5;
+    const double ty = quot<FAST>(bq.y, r1, g) * 0.5;
+    const double tz = quot<FAST>(bq.z, r1, g) * 0.5;
     // :434  s = 2*t/(1 + sum(t*t))
     const double den = 1.0 + ((tx * tx + ty * ty) + tz * tz);
-    const Recip rd = make_recip(den);
-    const double sx = div_shared(2.0 * tx, rd);
-    const double sy = div_shared(2.0 * ty, rd);
-    const double sz = div_shared(2.0 * tz, rd);
+    const Recip<FAST> rd = make_recip<FAST>(den, g);
+    const double sx = quot<FAST>(2.0 * tx, rd, g);
+    const double sy = quot<FAST>(2.0 * ty, rd, g);
+    const double sz = quot<FAST>(2.0 * tz, rd, g);
     // :436  vprime = vminus + cross(vminus, t)
     const double vpx = vmx + (vmy * tz - vmz * ty);
     const double vpy = vmy + (vmz * tx - vmx * tz);
@@ -61,12 +65,12 @@ __device__ __forceinline__ void boris_step(const PushK& k, const Vec3& eq, const
     p.z = plz + hz;
     // :439-440  m2 from the new momentum
     const double qq = (p.x * p.x + p.y * p.y) + p.z * p.z;
-    const double m2 = sqrt(k.mm + div_const(qq, k.c2));
+    const double m2 = sqrt(k.mm + quot<FAST>(qq, rc2, g));
     // :441  position = position + dt*momentum/m2
-    const Recip r2 = make_recip(m2);
-    x.x = x.x + div_shared(k.dt * p.x, r2);
-    x.y = x.y + div_shared(k.dt * p.y, r2);
-    x.z = x.z + div_shared(k.dt * p.z, r2);
+    const Recip<FAST> r2 = make_recip<FAST>(m2, g);
+    x.x = x.x + quot<FAST>(k.dt * p.x, r2, g);
+    x.y = x.y + quot<FAST>(k.dt * p.y, r2, g);
+    x.z = x.z + quot<FAST>(k.dt * p.z, r2, g);
 }
 
 }  // namespace tp

@@ -36,7 +36,7 @@ const DeviceProps& device_props() {
 __global__ void selftest_division_kernel(int64_t n, uint64_t seed, unsigned long long* mismatches) {
     const int64_t gtid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    unsigned long long bad = 0;
+    unsigned long long bad = 0, taken = 0;
     for (int64_t i = gtid; i < n; i += gstride) {
         // splitmix64 stream per pair
         uint64_t z = seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(2 * i + 1);
@@ -67,13 +67,20 @@ __global__ void selftest_division_kernel(int64_t n, uint64_t seed, unsigned long
         if (mode == 9) a = __longlong_as_double(0x7ff0000000000000ll);   // inf numerator
         if (mode == 10) b = __longlong_as_double(0x7ff0000000000000ll);  // inf denominator
         if (mode == 11) b = 0.0;
-        const Recip r = make_recip(b);
-        const double q = div_shared(a, r);
+        // The contract of the FAST policy: whenever the guard and the finiteness
+        // test pass (b > 0 as for every denominator of the hot path), the quotient
+        // has the bits of IEEE a/b; otherwise the caller recomputes with a/b.
+        b = fabs(b);
+        Guard g;
+        const Recip<true> r = make_recip<true>(b, g);
+        const double q = quot<true>(a, r, g);
         const double t = a / b;
-        const bool same = (__double_as_longlong(q) == __double_as_longlong(t)) || (q != q && t != t);
-        if (!same) ++bad;
+        const bool accepted = guard_ok(g) && finite3(q, q, q);
+        if (accepted && __double_as_longlong(q) != __double_as_longlong(t)) ++bad;
+        if (accepted) ++taken;
     }
     if (bad) atomicAdd(mismatches, bad);
+    atomicAdd(mismatches + 1, taken);
 }
 
 }  // namespace tp
@@ -111,21 +118,23 @@ extern "C" int tp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64
 
 extern "C" int64_t tp_launch_count(void) { return g_launch_count; }
 
-extern "C" int tp_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches, tp_stream_t stream) {
+extern "C" int tp_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches, int64_t* fast_taken,
+                                    tp_stream_t stream) {
     const DeviceProps& d = device_props();
     if (d.status != TP_OK) return d.status;
     if (!mismatches || n < 0) return TP_E_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     unsigned long long* dev = nullptr;
-    TP_CUDA_TRY(cudaMalloc(&dev, sizeof(unsigned long long)));
-    cudaMemsetAsync(dev, 0, sizeof(unsigned long long), s);
+    TP_CUDA_TRY(cudaMalloc(&dev, 2 * sizeof(unsigned long long)));
+    cudaMemsetAsync(dev, 0, 2 * sizeof(unsigned long long), s);
     selftest_division_kernel<<<d.sm_count * 4, 256, 0, s>>>(n, seed, dev);
     count_launch();
-    unsigned long long host = 0;
-    cudaError_t e = cudaMemcpyAsync(&host, dev, sizeof(host), cudaMemcpyDeviceToHost, s);
+    unsigned long long host[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     cudaFree(dev);
-    *mismatches = static_cast<int64_t>(host);
+    *mismatches = static_cast<int64_t>(host[0]);
+    if (fast_taken) *fast_taken = static_cast<int64_t>(host[1]);
     return static_cast<int>(e);
 }
 

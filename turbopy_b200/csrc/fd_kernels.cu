@@ -25,9 +25,19 @@ static int fd_blocks(int64_t n_pairs) {
 }
 
 // d[i] = (y[i+1] - y[i-1]) / two_dr for 0 < i < n-1; d[0] = d[n-1] = 0.
+// Quotient by the constant 2*dr: FAST policy with a per-value check, IEEE otherwise.
+struct ConstDiv { double b, rb; int fast_ok; };
+
+__device__ __forceinline__ double div_const(double a, const ConstDiv& c) {
+    Guard g;
+    const double q = quot<true>(a, const_recip<true>(c.b, c.rb), g);
+    if (__builtin_expect(c.fast_ok && guard_ok(g) && finite3(q, q, q), 1)) return q;
+    return a / c.b;
+}
+
 __global__ void __launch_bounds__(kFdThreads) fd_centered_kernel(const double* __restrict__ y,
                                                                  double* __restrict__ d, int64_t n,
-                                                                 ConstRecip two_dr, bool vec) {
+                                                                 ConstDiv two_dr, bool vec) {
     const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kFdThreads + threadIdx.x;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * kFdThreads;
     const int64_t npairs = (n + 1) >> 1;
@@ -81,11 +91,15 @@ __global__ void __launch_bounds__(kFdThreads) fd_upwind_kernel(const double* __r
 __device__ __forceinline__ double del2_row(int64_t i, int64_t n, double fm, double fc, double fp, double ri,
                                            double g1, double g2, double diag, double above0) {
     double acc = 0.0;
-    const Recip rr = make_recip(ri);
-    if (i > 0) acc = acc + (div_shared(-g1, rr) + g2) * fm;
+    // g1/r[i] and (-g1)/r[i] = -(g1/r[i]) exactly: one quotient, FAST with a local check
+    Guard g;
+    const Recip<true> rr = make_recip<true>(ri, g);
+    double qa = quot<true>(g1, rr, g);
+    if (__builtin_expect(!(guard_ok(g) && finite3(qa, qa, qa) && ri > 0.0), 0)) qa = g1 / ri;
+    if (i > 0) acc = acc + ((-qa) + g2) * fm;
     acc = acc + diag * fc;
     if (i < n - 1) {
-        const double above = (i == 0) ? above0 : (div_shared(g1, rr) + g2);
+        const double above = (i == 0) ? above0 : (qa + g2);
         acc = acc + above * fp;
     }
     return acc;
@@ -137,11 +151,11 @@ __global__ void __launch_bounds__(kFdThreads) fd_dia_kernel(const __grid_constan
     }
 }
 
-static ConstRecip host_recip(double b) {
-    ConstRecip c;
+static ConstDiv host_recip(double b) {
+    ConstDiv c;
     c.b = b;
     c.rb = 1.0 / b;
-    c.ok = std::isfinite(c.rb) && std::fabs(c.rb) >= 0x1p-960 && std::fabs(c.rb) <= 0x1p960;
+    c.fast_ok = const_divisor_ok(b) ? 1 : 0;
     return c;
 }
 

@@ -3,6 +3,17 @@
 //   A  Grid.create_interpolator           turbopy/core.py:711-755
 //   B  interp1d (1-D y) -> numpy.interp   turbopy/computetools.py:480
 //   C  interp1d (N-D y) -> scipy _call_linear
+//
+// Two evaluators per formula:
+//   gather6_fast  straight-line code for the generic particle: strictly inside a
+//                 cell found by the uniform-grid guess (x0 < x < x1), FAST
+//                 divisions recorded in a Guard.  Returns false when the
+//                 particle is not generic (on a node, guess off by one,
+//                 outside the grid, NaN, formula A window not the plain two
+//                 nodes); the caller then uses
+//   gather6_exact the complete semantics (search, on-node shortcuts, NaN
+//                 fallbacks, status codes) with IEEE divisions.
+// Both produce bit-identical values where both apply (tests/test_gpu_gather.py).
 #pragma once
 #include "common.cuh"
 
@@ -19,22 +30,84 @@ struct GridView {
     double        dr;         // Grid.dr, formula A's window half-width
 };
 
-// j with r[j] <= x < r[j+1], clamped to [0, ng-2]; numpy.interp's binary search
-// result for in-range x (x == r[ng-1] is handled by the callers).  A uniform
-// grid guess is verified against the actual node coordinates (Grid.r comes
-// from np.linspace, not r_min + j*dr, so the guess can be off by one); a grid
-// that is not uniform falls through to a binary search.
-__device__ __forceinline__ int find_cell(const GridView& g, double x) {
+// ---------------------------------------------------------------------------
+// fast path
+// ---------------------------------------------------------------------------
+template <int FORMULA>
+__device__ __forceinline__ bool gather6_fast(const GridView& g, double x, double (&F)[6], Guard& gd) {
     const int last = g.ng - 2;
-    double t = (x - g.r_first) * g.inv_dr;
+    // uniform-grid guess; F2I saturates and maps NaN to 0, the clamp keeps the
+    // loads in bounds for any x
+    int j = __double2int_rz((x - g.r_first) * g.inv_dr);
+    j = max(0, min(j, last));
+    const double x0 = g.r[j], x1 = g.r[j + 1];
+    bool ok = (x0 < x) && (x < x1);                 // strictly inside cell j (false for NaN)
+    if (FORMULA == TP_INTERP_B) {
+        // numpy.interp: slope = (y1-y0)/(x1-x0); out = slope*(x-x0) + y0
+        const Recip<true> rdx = make_recip<true>(x1 - x0, gd);
+        const double dx0 = x - x0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            F[k] = 0.0;
+            if (g.comp[k] != nullptr) {
+                const double* y = g.comp[k] + static_cast<int64_t>(j) * g.stride[k];
+                const double y0 = y[0], y1 = y[g.stride[k]];
+                F[k] = quot<true>(y1 - y0, rdx, gd) * dx0 + y0;
+            }
+        }
+    } else if (FORMULA == TP_INTERP_C) {
+        // ((x-x_lo)/(x_hi-x_lo))*y_hi + ((x_hi-x)/(x_hi-x_lo))*y_lo
+        const Recip<true> rw = make_recip<true>(x1 - x0, gd);
+        const double w_hi = quot<true>(x - x0, rw, gd);
+        const double w_lo = quot<true>(x1 - x, rw, gd);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            F[k] = 0.0;
+            if (g.comp[k] != nullptr) {
+                const double* y = g.comp[k] + static_cast<int64_t>(j) * g.stride[k];
+                F[k] = w_hi * y[g.stride[k]] + w_lo * y[0];
+            }
+        }
+    } else {
+        // create_interpolator: the window (x-dr, x+dr) must hold exactly nodes j, j+1
+        const double lo_edge = x - g.dr, hi_edge = x + g.dr;
+        const double xm = g.r[max(j - 1, 0)], xp = g.r[min(j + 2, g.ng - 1)];
+        ok = ok && (lo_edge < x0) && (x1 < hi_edge) && (j == 0 || !(lo_edge < xm)) &&
+             (j == last || !(xp < hi_edge));
+        const Recip<true> rdx = make_recip<true>(x1 - x0, gd);
+        const double dx0 = x - x0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            F[k] = 0.0;
+            if (g.comp[k] != nullptr) {
+                const double* y = g.comp[k] + static_cast<int64_t>(j) * g.stride[k];
+                const double y0 = y[0], y1 = y[g.stride[k]];
+                F[k] = y0 + quot<true>(dx0 * (y1 - y0), rdx, gd);
+            }
+        }
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------
+// exact path (complete semantics, IEEE divisions)
+// ---------------------------------------------------------------------------
+
+// j with r[j] <= x < r[j+1], clamped to [0, ng-2]: numpy.interp's binary
+// search result for in-range x.  Grid.r comes from np.linspace, not
+// r_min + j*dr, so the uniform guess can be off by one; a grid that is not
+// uniform at all falls through to a binary search.
+static __device__ __noinline__ int find_cell(const GridView& g, double x) {
+    const int last = g.ng - 2;
+    const double t = (x - g.r_first) * g.inv_dr;
     int j = (t >= 0.0) ? ((t < static_cast<double>(last)) ? static_cast<int>(t) : last) : 0;
     if (x < g.r[j]) {
         if (j > 0) --j;
     } else if (j < last && x >= g.r[j + 1]) {
         ++j;
     }
-    if (__builtin_expect((x < g.r[j] && j > 0) || (j < last && x >= g.r[j + 1]), 0)) {
-        int lo = 0, hi = last;                 // invariant: r[lo] <= x (or lo == 0)
+    if ((x < g.r[j] && j > 0) || (j < last && x >= g.r[j + 1])) {
+        int lo = 0, hi = last;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
             if (g.r[mid] <= x) lo = mid; else hi = mid - 1;
@@ -44,130 +117,75 @@ __device__ __forceinline__ int find_cell(const GridView& g, double x) {
     return j;
 }
 
-// Range status shared by all formulas (interp1d's bounds check raises for
-// x < r[0] or x > r[-1]; create_interpolator asserts the same, core.py:726-727).
-__device__ __forceinline__ unsigned range_status(const GridView& g, double x) {
-    return (x < g.r_first ? TP_ST_BELOW : 0u) | (x > g.r_last ? TP_ST_ABOVE : 0u);
+__device__ __forceinline__ double node_value(const GridView& g, int k, int j) {
+    return g.comp[k][static_cast<int64_t>(j) * g.stride[k]];
 }
 
-// ---- formula B -------------------------------------------------------------
-// numpy.interp:  slope = (y1-y0)/(x1-x0);  out = slope*(x-x0) + y0, with the
-// exact-node shortcuts and the NaN fallbacks of the C implementation.
-struct CellB {
-    int j; bool exact; double dx0; Recip rdx; int jn;
-};
-
-__device__ __forceinline__ CellB locate_b(const GridView& g, double x) {
-    CellB c;
-    c.j = find_cell(g, x);
-    if (x >= g.r_last) c.j = g.ng - 1;            // x == r[-1] -> y[-1]
-    const double x0 = g.r[c.j];
-    c.exact = (c.j == g.ng - 1) || (x0 == x);
-    c.jn = (c.j < g.ng - 1) ? c.j + 1 : c.j;
-    c.dx0 = x - x0;
-    c.rdx = make_recip(g.r[c.jn] - x0);
-    return c;
-}
-
-__device__ __forceinline__ double eval_b(const GridView& g, const CellB& c, int k, double x) {
-    const double* y = g.comp[k];
-    if (y == nullptr) return 0.0;
-    const double y0 = y[static_cast<int64_t>(c.j) * g.stride[k]];
-    if (c.exact) return y0;
-    const double y1 = y[static_cast<int64_t>(c.jn) * g.stride[k]];
-    const double slope = div_shared(y1 - y0, c.rdx);
-    double out = slope * c.dx0 + y0;
-    if (__builtin_expect(out != out, 0)) {        // numpy: "try the other direction"
-        if (x != x) return x;                     // numpy.interp passes a NaN abscissa through
-        out = slope * (x - g.r[c.jn]) + y1;
-        if (out != out && y0 == y1) out = y0;
-    }
-    return out;
-}
-
-// ---- formula C -------------------------------------------------------------
-// hi = clip(searchsorted(r, x, 'left'), 1, ng-1), lo = hi-1;
-// out = ((x-x_lo)/(x_hi-x_lo))*y_hi + ((x_hi-x)/(x_hi-x_lo))*y_lo
-struct CellC { int lo; double w_hi, w_lo; };
-
-__device__ __forceinline__ CellC locate_c(const GridView& g, double x) {
-    CellC c;
-    int j = find_cell(g, x);                      // r[j] <= x < r[j+1], j <= ng-2
-    // 'left' insertion index: first i with r[i] >= x
-    int hi = (x == g.r[j]) ? j : j + 1;
-    hi = hi < 1 ? 1 : hi;
-    c.lo = hi - 1;
-    const double x_lo = g.r[c.lo], x_hi = g.r[hi];
-    const Recip rw = make_recip(x_hi - x_lo);
-    c.w_hi = div_shared(x - x_lo, rw);
-    c.w_lo = div_shared(x_hi - x, rw);
-    return c;
-}
-
-__device__ __forceinline__ double eval_c(const GridView& g, const CellC& c, int k) {
-    const double* y = g.comp[k];
-    if (y == nullptr) return 0.0;
-    const double y_lo = y[static_cast<int64_t>(c.lo) * g.stride[k]];
-    const double y_hi = y[static_cast<int64_t>(c.lo + 1) * g.stride[k]];
-    return c.w_hi * y_hi + c.w_lo * y_lo;
-}
-
-// ---- formula A -------------------------------------------------------------
-// nodes with  x - dr < r[i] < x + dr  (core.py:728); one node -> y[i];
-// two -> y0 + ((x - r_lo)*(y1 - y0))/(r_hi - r_lo); else the :729 assert.
-struct CellA { int first; int count; double dx0; Recip rdx; };
-
-__device__ __forceinline__ CellA locate_a(const GridView& g, double x) {
-    CellA c;
-    const int j = find_cell(g, x);
-    const double lo_edge = x - g.dr, hi_edge = x + g.dr;
-    int first = -1, count = 0;
-    const int i0 = j - 2 < 0 ? 0 : j - 2;
-    const int i1 = j + 3 > g.ng - 1 ? g.ng - 1 : j + 3;
-    for (int i = i0; i <= i1; ++i) {
-        const double ri = g.r[i];
-        if (lo_edge < ri && ri < hi_edge) {
-            if (first < 0) first = i;
-            ++count;
-        }
-    }
-    c.first = first < 0 ? 0 : first;
-    c.count = count;
-    const int nxt = c.first + 1 < g.ng ? c.first + 1 : c.first;
-    c.dx0 = x - g.r[c.first];
-    c.rdx = make_recip(g.r[nxt] - g.r[c.first]);
-    return c;
-}
-
-__device__ __forceinline__ double eval_a(const GridView& g, const CellA& c, int k) {
-    const double* y = g.comp[k];
-    if (y == nullptr) return 0.0;
-    const double y0 = y[static_cast<int64_t>(c.first) * g.stride[k]];
-    if (c.count == 1) return y0;
-    const int nxt = c.first + 1 < g.ng ? c.first + 1 : c.first;
-    const double y1 = y[static_cast<int64_t>(nxt) * g.stride[k]];
-    return y0 + div_shared(c.dx0 * (y1 - y0), c.rdx);
-}
-
-// Gather all six components with one formula.  Returns the TP_ST_* status;
-// F is only meaningful when the status is 0.
+// Returns the TP_ST_* status; F is only meaningful when it is 0.
 template <int FORMULA>
-__device__ __forceinline__ unsigned gather6(const GridView& g, double x, double (&F)[6]) {
-    unsigned st = range_status(g, x);
+__device__ __noinline__ unsigned gather6_exact(const GridView& g, double x, double (&F)[6]) {
+    // interp1d's bounds check raises for x < r[0] or x > r[-1]; create_interpolator
+    // asserts the same (core.py:726-727)
+    const unsigned st = (x < g.r_first ? TP_ST_BELOW : 0u) | (x > g.r_last ? TP_ST_ABOVE : 0u);
     if (st) return st;
+    const int ng = g.ng;
     if (FORMULA == TP_INTERP_B) {
-        const CellB c = locate_b(g, x);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) F[k] = eval_b(g, c, k, x);
+        int j = find_cell(g, x);
+        if (x >= g.r_last) j = ng - 1;                       // x == r[-1] -> y[-1]
+        const double x0 = g.r[j];
+        const bool exact = (j == ng - 1) || (x0 == x);
+        const int jn = (j < ng - 1) ? j + 1 : j;
+        const double dx = g.r[jn] - x0;
+        for (int k = 0; k < 6; ++k) {
+            if (g.comp[k] == nullptr) { F[k] = 0.0; continue; }
+            const double y0 = node_value(g, k, j);
+            if (exact) { F[k] = y0; continue; }
+            const double y1 = node_value(g, k, jn);
+            const double slope = (y1 - y0) / dx;
+            double out = slope * (x - x0) + y0;
+            if (out != out) {                                // numpy: "try the other direction"
+                if (x != x) out = x;                         // a NaN abscissa passes through
+                else {
+                    out = slope * (x - g.r[jn]) + y1;
+                    if (out != out && y0 == y1) out = y0;
+                }
+            }
+            F[k] = out;
+        }
     } else if (FORMULA == TP_INTERP_C) {
-        const CellC c = locate_c(g, x);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) F[k] = eval_c(g, c, k);
+        const int j = find_cell(g, x);
+        int hi = (x == g.r[j]) ? j : j + 1;                  // 'left' insertion index
+        hi = hi < 1 ? 1 : hi;
+        const int lo = hi - 1;
+        const double x_lo = g.r[lo], x_hi = g.r[hi];
+        const double w_hi = (x - x_lo) / (x_hi - x_lo);
+        const double w_lo = (x_hi - x) / (x_hi - x_lo);
+        for (int k = 0; k < 6; ++k) {
+            if (g.comp[k] == nullptr) { F[k] = 0.0; continue; }
+            F[k] = w_hi * node_value(g, k, hi) + w_lo * node_value(g, k, lo);
+        }
     } else {
-        const CellA c = locate_a(g, x);
-        if (c.count != 1 && c.count != 2) return TP_ST_BAD_WINDOW;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) F[k] = eval_a(g, c, k);
+        const int j = find_cell(g, x);
+        const double lo_edge = x - g.dr, hi_edge = x + g.dr;
+        int first = -1, count = 0;
+        const int i0 = j - 2 < 0 ? 0 : j - 2;
+        const int i1 = j + 3 > ng - 1 ? ng - 1 : j + 3;
+        for (int i = i0; i <= i1; ++i) {
+            const double ri = g.r[i];
+            if (lo_edge < ri && ri < hi_edge) {
+                if (first < 0) first = i;
+                ++count;
+            }
+        }
+        if (count != 1 && count != 2) return TP_ST_BAD_WINDOW;    // core.py:729
+        const int nxt = first + 1 < ng ? first + 1 : first;
+        for (int k = 0; k < 6; ++k) {
+            if (g.comp[k] == nullptr) { F[k] = 0.0; continue; }
+            const double y0 = node_value(g, k, first);
+            if (count == 1) { F[k] = y0; continue; }              // core.py:731-732
+            const double y1 = node_value(g, k, nxt);
+            F[k] = y0 + ((x - g.r[first]) * (y1 - y0)) / (g.r[nxt] - g.r[first]);   // :752-753
+        }
     }
     return 0u;
 }

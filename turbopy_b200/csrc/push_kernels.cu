@@ -22,6 +22,9 @@
 
 namespace tp {
 
+#ifndef TP_MIN_BLOCKS
+#define TP_MIN_BLOCKS 2
+#endif
 constexpr int kThreads = 256;
 
 // ---------------------------------------------------------------------------
@@ -126,11 +129,26 @@ __device__ __forceinline__ Vec3 uniform_of(const FieldArg& f) {
 // ---------------------------------------------------------------------------
 // push (E, B given per call)
 // ---------------------------------------------------------------------------
+// Recovery path of one particle: reload it from global memory (nothing has been
+// stored yet) and redo the step with IEEE divisions.
+__device__ __noinline__ void push_one_exact(const PushArgs& a, const Vec3& Eu, const Vec3& Bu, int64_t i) {
+    Vec3 x, p;
+    load_one(a.p, i, x, p);
+    Guard g;
+    boris_step<false>(a.k, dt_field_q(a.k, field_at(a.E, Eu, i)), dt_field_q(a.k, field_at(a.B, Bu, i)), x, p, g);
+    store_one(a.p, i, x, p);
+}
+
+__device__ __forceinline__ bool push_one_fast(const PushArgs& a, const Vec3& Eu, const Vec3& Bu, int64_t i,
+                                              Vec3& x, Vec3& p) {
+    Guard g;
+    boris_step<true>(a.k, dt_field_q(a.k, field_at(a.E, Eu, i)), dt_field_q(a.k, field_at(a.B, Bu, i)), x, p, g);
+    return guard_ok(g) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+}
+
 template <bool VEC2>
-__global__ void __launch_bounds__(kThreads, 2) push_kernel(const __grid_constant__ PushArgs a) {
+__global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) push_kernel(const __grid_constant__ PushArgs a) {
     const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
-    const bool all_uniform = a.E.mode != TP_FIELD_PER_PARTICLE && a.B.mode != TP_FIELD_PER_PARTICLE;
-    const Vec3 equ = dt_field_q(a.k, Eu), bqu = dt_field_q(a.k, Bu);
     const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * kThreads;
     if (VEC2) {
@@ -139,35 +157,22 @@ __global__ void __launch_bounds__(kThreads, 2) push_kernel(const __grid_constant
             const int64_t i = pr * 2;
             Vec3 x[2], p[2];
             load_pair(a.p, i, x, p);
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                if (all_uniform) {
-                    boris_step(a.k, equ, bqu, x[v], p[v]);
-                } else {
-                    const Vec3 eq = dt_field_q(a.k, field_at(a.E, Eu, i + v));
-                    const Vec3 bq = dt_field_q(a.k, field_at(a.B, Bu, i + v));
-                    boris_step(a.k, eq, bq, x[v], p[v]);
-                }
+            const bool ok0 = push_one_fast(a, Eu, Bu, i, x[0], p[0]);
+            const bool ok1 = push_one_fast(a, Eu, Bu, i + 1, x[1], p[1]);
+            if (__builtin_expect(ok0 && ok1, 1)) {
+                store_pair(a.p, i, x, p);
+            } else {
+                if (ok0) store_one(a.p, i, x[0], p[0]); else push_one_exact(a, Eu, Bu, i);
+                if (ok1) store_one(a.p, i + 1, x[1], p[1]); else push_one_exact(a, Eu, Bu, i + 1);
             }
-            store_pair(a.p, i, x, p);
         }
-        if ((a.p.n & 1) && gtid == 0) {               // odd tail
-            const int64_t i = a.p.n - 1;
-            Vec3 x, p;
-            load_one(a.p, i, x, p);
-            const Vec3 eq = dt_field_q(a.k, field_at(a.E, Eu, i));
-            const Vec3 bq = dt_field_q(a.k, field_at(a.B, Bu, i));
-            boris_step(a.k, eq, bq, x, p);
-            store_one(a.p, i, x, p);
-        }
+        if ((a.p.n & 1) && gtid == 0) push_one_exact(a, Eu, Bu, a.p.n - 1);     // odd tail
     } else {
         for (int64_t i = gtid; i < a.p.n; i += gstride) {
             Vec3 x, p;
             load_one(a.p, i, x, p);
-            const Vec3 eq = dt_field_q(a.k, field_at(a.E, Eu, i));
-            const Vec3 bq = dt_field_q(a.k, field_at(a.B, Bu, i));
-            boris_step(a.k, eq, bq, x, p);
-            store_one(a.p, i, x, p);
+            if (__builtin_expect(push_one_fast(a, Eu, Bu, i, x, p), 1)) store_one(a.p, i, x, p);
+            else push_one_exact(a, Eu, Bu, i);
         }
     }
 }
@@ -269,25 +274,43 @@ __device__ __forceinline__ double axis_of(const Vec3& x, int axis) {
     return axis == 0 ? x.x : (axis == 1 ? x.y : x.z);
 }
 
+// Generic particle: straight-line gather + push, validity in the return value.
 template <int FORMULA>
-__device__ __forceinline__ bool gather_and_step(const GatherArgs& a, const GridView& g, int64_t i, Vec3& x, Vec3& p) {
+__device__ __forceinline__ bool gather_step_fast(const GatherArgs& a, const GridView& g, Vec3& x, Vec3& p) {
     double F[6];
-    const unsigned st = gather6<FORMULA>(g, axis_of(x, a.axis), F);
-    if (__builtin_expect(st != 0u, 0)) {
+    Guard gd;
+    bool ok = gather6_fast<FORMULA>(g, axis_of(x, a.axis), F, gd);
+    Vec3 E, B;
+    E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
+    boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
+    return ok && guard_ok(gd) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+}
+
+// Recovery path: reload the particle (nothing has been stored yet), complete
+// gather semantics, IEEE divisions; out-of-grid particles are flagged and left
+// untouched.
+template <int FORMULA>
+__device__ __noinline__ void gather_step_exact(const GatherArgs& a, const GridView& g, int64_t i) {
+    Vec3 x, p;
+    load_one(a.p, i, x, p);
+    double F[6];
+    const unsigned st = gather6_exact<FORMULA>(g, axis_of(x, a.axis), F);
+    if (st != 0u) {
         flag_particle(a.status, i, st);
-        return false;                // flagged particles are left untouched
+        return;
     }
     Vec3 E, B;
     E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
-    boris_step(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p);
-    return true;
+    Guard gd;
+    boris_step<false>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
+    store_one(a.p, i, x, p);
 }
 
 // ---------------------------------------------------------------------------
 // fused gather + push
 // ---------------------------------------------------------------------------
 template <bool VEC2, int FORMULA, bool STAGED>
-__global__ void __launch_bounds__(kThreads, 2) gather_push_kernel(const __grid_constant__ GatherArgs a) {
+__global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) gather_push_kernel(const __grid_constant__ GatherArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (STAGED) stage_issue(a, smem);
     const GridView g = make_view<STAGED>(a, smem);
@@ -303,30 +326,26 @@ __global__ void __launch_bounds__(kThreads, 2) gather_push_kernel(const __grid_c
         if (STAGED) stage_wait(smem);
         while (pr < npairs) {
             const int64_t i = pr * 2;
-            const bool w0 = gather_and_step<FORMULA>(a, g, i, x[0], p[0]);
-            const bool w1 = gather_and_step<FORMULA>(a, g, i + 1, x[1], p[1]);
-            if (__builtin_expect(w0 && w1, 1)) {
+            const bool ok0 = gather_step_fast<FORMULA>(a, g, x[0], p[0]);
+            const bool ok1 = gather_step_fast<FORMULA>(a, g, x[1], p[1]);
+            if (__builtin_expect(ok0 && ok1, 1)) {
                 store_pair(a.p, i, x, p);
             } else {
-                if (w0) store_one(a.p, i, x[0], p[0]);
-                if (w1) store_one(a.p, i + 1, x[1], p[1]);
+                if (ok0) store_one(a.p, i, x[0], p[0]); else gather_step_exact<FORMULA>(a, g, i);
+                if (ok1) store_one(a.p, i + 1, x[1], p[1]); else gather_step_exact<FORMULA>(a, g, i + 1);
             }
             pr += gstride;
             if (pr < npairs) load_pair(a.p, pr * 2, x, p);
         }
-        if ((a.p.n & 1) && gtid == 0) {
-            const int64_t i = a.p.n - 1;
-            Vec3 x1, p1;
-            load_one(a.p, i, x1, p1);
-            if (gather_and_step<FORMULA>(a, g, i, x1, p1)) store_one(a.p, i, x1, p1);
-        }
+        if ((a.p.n & 1) && gtid == 0) gather_step_exact<FORMULA>(a, g, a.p.n - 1);
     } else {
         int64_t i = gtid;
         Vec3 x, p;
         if (i < a.p.n) load_one(a.p, i, x, p);
         if (STAGED) stage_wait(smem);
         while (i < a.p.n) {
-            if (gather_and_step<FORMULA>(a, g, i, x, p)) store_one(a.p, i, x, p);
+            if (__builtin_expect(gather_step_fast<FORMULA>(a, g, x, p), 1)) store_one(a.p, i, x, p);
+            else gather_step_exact<FORMULA>(a, g, i);
             i += gstride;
             if (i < a.p.n) load_one(a.p, i, x, p);
         }
@@ -362,7 +381,12 @@ __global__ void __launch_bounds__(kThreads, 2) interp_kernel(const __grid_consta
                 gv.stride[c] = g.stride[0];
             }
             double F[6];
-            const unsigned st = gather6<FORMULA>(gv, x, F);
+            Guard gd;
+            unsigned st = 0u;
+            bool ok = gather6_fast<FORMULA>(gv, x, F, gd) && guard_ok(gd);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) ok = ok && (F[c] == F[c]);      // NaN -> numpy's fallbacks
+            if (!ok) st = gather6_exact<FORMULA>(gv, x, F);
             if (st != 0u && c0 == 0) flag_particle(a.g.status, i, st);
 #pragma unroll
             for (int c = 0; c < 6; ++c)
@@ -390,9 +414,9 @@ static int fill_particles(const tp_particles* p, ParticleArgs& a, bool& vec2) {
 static int fill_consts(const tp_push_consts* k, PushK& o) {
     if (!k) return TP_E_ARG;
     o.dt = k->dt; o.q = k->charge; o.mm = k->mass_sq;
-    o.c2.b = k->c2;
-    o.c2.rb = 1.0 / k->c2;                      // IEEE on the host: RN(1/c2)
-    o.c2.ok = std::isfinite(o.c2.rb) && std::fabs(o.c2.rb) >= 0x1p-960 && std::fabs(o.c2.rb) <= 0x1p960;
+    o.c2 = k->c2;
+    o.rc2 = 1.0 / k->c2;                        // IEEE on the host: RN(1/c2)
+    o.fast_ok = const_divisor_ok(k->c2) ? 1 : 0;
     return TP_OK;
 }
 

@@ -43,16 +43,16 @@ __device__ __forceinline__ void block_sum(double (&v)[kRedVals], double* out) {
 }
 
 __device__ __forceinline__ void accumulate(double px, double py, double pz, double mass, double mm,
-                                           const ConstRecip& c2, double (&acc)[kRedVals]) {
+                                           double c2, double (&acc)[kRedVals]) {
     const double p2 = (px * px + py * py) + pz * pz;
-    const double m1 = sqrt(mm + div_const(p2, c2));
+    const double m1 = sqrt(mm + p2 / c2);
     acc[0] += p2 / (m1 + mass);
     acc[1] += px; acc[2] += py; acc[3] += pz; acc[4] += p2;
 }
 
 __global__ void __launch_bounds__(kRedThreads) moments_partial_kernel(const double* __restrict__ mom, int64_t sn,
                                                                       int64_t sc, int64_t n, double mass, double mm,
-                                                                      ConstRecip c2, bool vec, double* scratch) {
+                                                                      double c2, bool vec, double* scratch) {
     double acc[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kRedThreads + threadIdx.x;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * kRedThreads;
@@ -101,9 +101,6 @@ extern "C" int tp_reduce_moments_f64(const double* mom, int64_t stride_n, int64_
     if (n < 0 || !out8 || !scratch || (n > 0 && !mom)) return TP_E_ARG;
     if (stride_n <= 0 || stride_c <= 0) return TP_E_LAYOUT;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    ConstRecip c;
-    c.b = c2; c.rb = 1.0 / c2;
-    c.ok = std::isfinite(c.rb) && std::fabs(c.rb) >= 0x1p-960 && std::fabs(c.rb) <= 0x1p960;
     const bool vec = layout_of(stride_n, stride_c, n) == kLayoutSoA && aligned16(mom) && (stride_c % 2 == 0) && n >= 2;
     const int64_t items = vec ? (n + 1) / 2 : n;
     int64_t blocks = (items + kRedThreads - 1) / kRedThreads;
@@ -111,7 +108,7 @@ extern "C" int tp_reduce_moments_f64(const double* mom, int64_t stride_n, int64_
     if (blocks > full) blocks = full;
     if (blocks > kRedMaxBlocks) blocks = kRedMaxBlocks;
     if (blocks < 1) blocks = 1;
-    moments_partial_kernel<<<static_cast<int>(blocks), kRedThreads, 0, s>>>(mom, stride_n, stride_c, n, mass, mass_sq, c,
+    moments_partial_kernel<<<static_cast<int>(blocks), kRedThreads, 0, s>>>(mom, stride_n, stride_c, n, mass, mass_sq, c2,
                                                                           vec, scratch);
     moments_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, static_cast<int>(blocks), n, out8);
     count_launch(2);
