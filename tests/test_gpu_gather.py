@@ -171,6 +171,36 @@ def test_fused_vs_oracle(tp, formula, ng, layout):
     assert_bits_equal(mom.cpu().numpy(), rm, "momentum")
 
 
+@pytest.mark.parametrize("formula", ["A", "B", "C"])
+@pytest.mark.parametrize("ng", [513, (1 << 18) + 1])
+def test_fused_tma_pipeline_vs_oracle(tp, formula, ng):
+    """Enough particles (> one 1024-particle tile per SM) for the TMA-pipelined
+    kernel: several ring wrap-arounds per CTA, a ragged scalar tail, on-node and
+    out-of-grid particles inside full tiles (exact path through shared memory)."""
+    grid = make_grid(ng)
+    dt = 1e-12
+    tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+    n = 148 * 1024 * 5 + 777
+    pos0, mom0 = thermal_ensemble(n, seed=ng + 5)
+    pos0[:, 0] = np.random.default_rng(ng).uniform(0.02, 0.98, n)
+    on_node = np.arange(0, n, 9973)
+    pos0[on_node, 0] = grid.r[(on_node * 7) % (ng - 2) + 1]
+    outside = np.array([5, 100_003, n - 3])
+    pos0[outside, 0] = [-0.25, 1.5, 1.0 + 1e-15]
+    comps = smooth_fields(grid)
+    E = torch.from_numpy(np.stack(comps[:3], axis=1)).cuda()
+    B = torch.from_numpy(np.stack(comps[3:], axis=1)).cuda()
+    pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, axis=0, formula=formula)
+    with pytest.raises((ValueError, AssertionError), match="3 particle"):
+        tool.check_status()
+    keep = np.ones(n, dtype=bool); keep[outside] = False
+    rp, rm = fused_reference(formula, pos0[keep], mom0[keep], grid, comps, 0, dt, 1)
+    gp, gm = pos.cpu().numpy(), mom.cpu().numpy()
+    assert_bits_equal(gp[keep], rp, "position"); assert_bits_equal(gm[keep], rm, "momentum")
+    assert_bits_equal(gp[outside], pos0[outside]); assert_bits_equal(gm[outside], mom0[outside])
+
+
 @pytest.mark.parametrize("axis", [0, 1, 2])
 def test_fused_partial_components_and_axis(tp, axis):
     """The pif shape: only E_y on the grid, B absent (None), any gather axis."""

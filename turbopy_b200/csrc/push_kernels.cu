@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace tp {
@@ -99,6 +100,29 @@ __device__ __forceinline__ void store_pair(const ParticleArgs& a, int64_t i, con
     st2(a.mom + 2 * a.mom_sc + i, make_double2(p[0].z, p[1].z));
 }
 
+// One thread per CTA asks the TMA to pull the six 4 KB component slices of the
+// CTA's tile `first .. first + 2*kThreads` (a later loop iteration) into L2, so
+// that the loads of that iteration hit L2 instead of paying the DRAM latency
+// with only 16 resident warps per SM.  SoA fast path only (16-byte aligned).
+#ifndef TP_PF_DIST
+#define TP_PF_DIST 1
+#endif
+__device__ __forceinline__ void prefetch_tile(const ParticleArgs& a, int64_t first, int64_t n_even) {
+#if TP_PF_DIST > 0
+    if (threadIdx.x == 0 && first < n_even) {
+        const int64_t rest = n_even - first;
+        const uint32_t bytes = static_cast<uint32_t>((rest < 2 * kThreads ? rest : 2 * kThreads) * sizeof(double));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pos + c * a.pos_sc + first), "r"(bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.mom + c * a.mom_sc + first), "r"(bytes)
+                         : "memory");
+        }
+    }
+#endif
+}
+
 __device__ __forceinline__ void load_one(const ParticleArgs& a, int64_t i, Vec3& x, Vec3& p) {
     const double* xs = a.pos + i * a.pos_sn;
     const double* ps = a.mom + i * a.mom_sn;
@@ -131,7 +155,8 @@ __device__ __forceinline__ Vec3 uniform_of(const FieldArg& f) {
 // ---------------------------------------------------------------------------
 // Recovery path of one particle: reload it from global memory (nothing has been
 // stored yet) and redo the step with IEEE divisions.
-__device__ __noinline__ void push_one_exact(const PushArgs& a, const Vec3& Eu, const Vec3& Bu, int64_t i) {
+__device__ __noinline__ void push_one_exact(const PushArgs& a, int64_t i) {
+    const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);     // rebuilt here: no references into the hot loop
     Vec3 x, p;
     load_one(a.p, i, x, p);
     Guard g;
@@ -162,17 +187,17 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) push_kernel(const __g
             if (__builtin_expect(ok0 && ok1, 1)) {
                 store_pair(a.p, i, x, p);
             } else {
-                if (ok0) store_one(a.p, i, x[0], p[0]); else push_one_exact(a, Eu, Bu, i);
-                if (ok1) store_one(a.p, i + 1, x[1], p[1]); else push_one_exact(a, Eu, Bu, i + 1);
+                if (ok0) store_one(a.p, i, x[0], p[0]); else push_one_exact(a,i);
+                if (ok1) store_one(a.p, i + 1, x[1], p[1]); else push_one_exact(a,i + 1);
             }
         }
-        if ((a.p.n & 1) && gtid == 0) push_one_exact(a, Eu, Bu, a.p.n - 1);     // odd tail
+        if ((a.p.n & 1) && gtid == 0) push_one_exact(a,a.p.n - 1);     // odd tail
     } else {
         for (int64_t i = gtid; i < a.p.n; i += gstride) {
             Vec3 x, p;
             load_one(a.p, i, x, p);
             if (__builtin_expect(push_one_fast(a, Eu, Bu, i, x, p), 1)) store_one(a.p, i, x, p);
-            else push_one_exact(a, Eu, Bu, i);
+            else push_one_exact(a,i);
         }
     }
 }
@@ -236,7 +261,7 @@ __device__ __forceinline__ void stage_issue(const GatherArgs& a, unsigned char* 
     for (int s = 0; s < a.nseg; ++s) {
         const uint32_t first = a.seg[s].tma_bytes >> 3;
         double* dst = reinterpret_cast<double*>(smem + a.seg[s].smem_off);
-        for (uint32_t e = first + threadIdx.x; e < a.seg[s].n_doubles; e += kThreads) dst[e] = a.seg[s].src[e];
+        for (uint32_t e = first + threadIdx.x; e < a.seg[s].n_doubles; e += blockDim.x) dst[e] = a.seg[s].src[e];
     }
 }
 
@@ -288,22 +313,31 @@ __device__ __forceinline__ bool gather_step_fast(const GatherArgs& a, const Grid
 
 // Recovery path: reload the particle (nothing has been stored yet), complete
 // gather semantics, IEEE divisions; out-of-grid particles are flagged and left
-// untouched.
+// untouched.  The out-of-line entry points below take only the grid-constant
+// argument block and the shared-memory base and rebuild their own GridView:
+// passing the hot loop's view or particle registers by reference would force
+// them into local memory (LDL/STL in the hot loop, profiles/r1_v3).
 template <int FORMULA>
-__device__ __noinline__ void gather_step_exact(const GatherArgs& a, const GridView& g, int64_t i) {
-    Vec3 x, p;
+__device__ __forceinline__ bool exact_core(const GatherArgs& a, const GridView& g, int64_t i, Vec3& x, Vec3& p) {
     load_one(a.p, i, x, p);
     double F[6];
     const unsigned st = gather6_exact<FORMULA>(g, axis_of(x, a.axis), F);
     if (st != 0u) {
         flag_particle(a.status, i, st);
-        return;
+        return false;
     }
     Vec3 E, B;
     E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
     Guard gd;
     boris_step<false>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
-    store_one(a.p, i, x, p);
+    return true;
+}
+
+template <int FORMULA, bool STAGED>
+__device__ __noinline__ void gather_step_exact(const GatherArgs& a, unsigned char* smem, int64_t i) {
+    const GridView g = make_view<STAGED>(a, smem);
+    Vec3 x, p;
+    if (exact_core<FORMULA>(a, g, i, x, p)) store_one(a.p, i, x, p);
 }
 
 // ---------------------------------------------------------------------------
@@ -326,18 +360,19 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) gather_push_kernel(co
         if (STAGED) stage_wait(smem);
         while (pr < npairs) {
             const int64_t i = pr * 2;
+            prefetch_tile(a.p, (pr - threadIdx.x + TP_PF_DIST * gstride) * 2, npairs * 2);
             const bool ok0 = gather_step_fast<FORMULA>(a, g, x[0], p[0]);
             const bool ok1 = gather_step_fast<FORMULA>(a, g, x[1], p[1]);
             if (__builtin_expect(ok0 && ok1, 1)) {
                 store_pair(a.p, i, x, p);
             } else {
-                if (ok0) store_one(a.p, i, x[0], p[0]); else gather_step_exact<FORMULA>(a, g, i);
-                if (ok1) store_one(a.p, i + 1, x[1], p[1]); else gather_step_exact<FORMULA>(a, g, i + 1);
+                if (ok0) store_one(a.p, i, x[0], p[0]); else gather_step_exact<FORMULA, STAGED>(a, smem, i);
+                if (ok1) store_one(a.p, i + 1, x[1], p[1]); else gather_step_exact<FORMULA, STAGED>(a, smem, i + 1);
             }
             pr += gstride;
             if (pr < npairs) load_pair(a.p, pr * 2, x, p);
         }
-        if ((a.p.n & 1) && gtid == 0) gather_step_exact<FORMULA>(a, g, a.p.n - 1);
+        if ((a.p.n & 1) && gtid == 0) gather_step_exact<FORMULA, STAGED>(a, smem, a.p.n - 1);
     } else {
         int64_t i = gtid;
         Vec3 x, p;
@@ -345,9 +380,155 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) gather_push_kernel(co
         if (STAGED) stage_wait(smem);
         while (i < a.p.n) {
             if (__builtin_expect(gather_step_fast<FORMULA>(a, g, x, p), 1)) store_one(a.p, i, x, p);
-            else gather_step_exact<FORMULA>(a, g, i);
+            else gather_step_exact<FORMULA, STAGED>(a, smem, i);
             i += gstride;
             if (i < a.p.n) load_one(a.p, i, x, p);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fused gather + push, particles streamed by the TMA
+// ---------------------------------------------------------------------------
+// The register-path kernel above keeps only 16 warps per SM resident (128
+// registers per thread) and its loads sit at the end of each iteration, so the
+// HBM latency is exposed (profiles/r1_v2: long_scoreboard is the top stall).
+// Here the particle arrays themselves go through the TMA: one persistent CTA
+// per SM owns a ring of NST shared-memory stages; each stage holds one tile of
+// kTile particles as six contiguous 8 KB component slices.  One elected thread
+//   - fills a stage with six cp.async.bulk loads that complete on the stage's
+//     mbarrier (expect_tx = 48 KB),
+//   - after the CTA has updated the tile in place in shared memory, drains it
+//     with six cp.async.bulk stores (bulk async-group),
+//   - re-fills the stage of the PREVIOUS tile once that tile's stores have
+//     finished reading shared memory (wait_group.read 1),
+// so two tiles of loads are always in flight behind the tile being computed and
+// no thread ever waits on a global load.  The 512 threads read their two
+// particles from the stage with 128-bit LDS, run the same fast / exact
+// arithmetic as the register path, and write the result back with 128-bit STS.
+constexpr int kTmaThreads = 512;
+constexpr int kTile = 2 * kTmaThreads;                         // particles per tile
+constexpr uint32_t kSliceBytes = kTile * sizeof(double);       // 8 KB per component
+constexpr uint32_t kTileBytes = 6 * kSliceBytes;               // 48 KB per stage
+constexpr int kMaxStages = 4;
+
+struct TmaArgs {
+    GatherArgs g;
+    int nstages;
+    uint32_t tiles_off;        // byte offset of stage 0 in dynamic shared memory (128-B aligned)
+    int64_t ntiles;            // full tiles; the remaining n - ntiles*kTile particles use the scalar path
+};
+
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tile_load(const ParticleArgs& p, int64_t tile, unsigned char* stage, uint64_t* bar) {
+    const int64_t first = tile * kTile;
+    mbar_expect_tx(bar, kTileBytes);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        tma_bulk_g2s(stage + c * kSliceBytes, p.pos + c * p.pos_sc + first, kSliceBytes, bar);
+        tma_bulk_g2s(stage + (3 + c) * kSliceBytes, p.mom + c * p.mom_sc + first, kSliceBytes, bar);
+    }
+}
+
+__device__ __forceinline__ void tile_store(const ParticleArgs& p, int64_t tile, const unsigned char* stage) {
+    const int64_t first = tile * kTile;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        tma_bulk_s2g(p.pos + c * p.pos_sc + first, stage + c * kSliceBytes, kSliceBytes);
+        tma_bulk_s2g(p.mom + c * p.mom_sc + first, stage + (3 + c) * kSliceBytes, kSliceBytes);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// Recovery path for the TMA kernel: the tile has not been stored yet, so global
+// memory still holds the particle's input; the result (or, for a flagged
+// particle, the untouched input) goes back through the shared-memory stage.
+// `slot` addresses the particle's x component inside the stage; the other five
+// components follow at multiples of `pitch` doubles.
+template <int FORMULA, bool STAGED>
+__device__ __noinline__ void gather_step_exact_slot(const GatherArgs& a, unsigned char* smem, int64_t i,
+                                                    double* slot, int pitch) {
+    const GridView g = make_view<STAGED>(a, smem);
+    Vec3 x, p;
+    exact_core<FORMULA>(a, g, i, x, p);          // flagged: x, p hold the untouched input
+    slot[0] = x.x; slot[pitch] = x.y; slot[2 * pitch] = x.z;
+    slot[3 * pitch] = p.x; slot[4 * pitch] = p.y; slot[5 * pitch] = p.z;
+}
+
+template <int FORMULA, bool STAGED>
+__global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const __grid_constant__ TmaArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const GatherArgs& a = ta.g;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);       // one mbarrier per stage
+    unsigned char* tiles = smem + ta.tiles_off;
+    const int nst = ta.nstages;
+    if (threadIdx.x == 0)
+        for (int s = 0; s < nst; ++s) mbar_init(&full[s], 1);
+    if (STAGED) stage_issue(a, smem); else __syncthreads();       // (stage_issue syncs after its own init)
+    const int64_t t0 = blockIdx.x, tstep = gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nst; ++s) {
+            const int64_t t = t0 + s * tstep;
+            if (t < ta.ntiles) tile_load(a.p, t, tiles + s * kTileBytes, &full[s]);
+        }
+    }
+    const GridView g = make_view<STAGED>(a, smem);
+    if (STAGED) stage_wait(smem);
+
+    int s = 0, prev = 0;
+    uint32_t parity = 0;
+    for (int64_t t = t0; t < ta.ntiles; t += tstep) {
+        mbar_wait(&full[s], parity);
+        double* buf = reinterpret_cast<double*>(tiles + s * kTileBytes) + 2 * threadIdx.x;
+        Vec3 x[2], p[2];
+        {
+            const double2 x0 = ld2(buf), x1 = ld2(buf + kTile), x2 = ld2(buf + 2 * kTile);
+            const double2 p0 = ld2(buf + 3 * kTile), p1 = ld2(buf + 4 * kTile), p2 = ld2(buf + 5 * kTile);
+            x[0].x = x0.x; x[1].x = x0.y; x[0].y = x1.x; x[1].y = x1.y; x[0].z = x2.x; x[1].z = x2.y;
+            p[0].x = p0.x; p[1].x = p0.y; p[0].y = p1.x; p[1].y = p1.y; p[0].z = p2.x; p[1].z = p2.y;
+        }
+        const int64_t i = t * kTile + 2 * threadIdx.x;
+        const bool ok0 = gather_step_fast<FORMULA>(a, g, x[0], p[0]);
+        const bool ok1 = gather_step_fast<FORMULA>(a, g, x[1], p[1]);
+        st2(buf, make_double2(x[0].x, x[1].x));
+        st2(buf + kTile, make_double2(x[0].y, x[1].y));
+        st2(buf + 2 * kTile, make_double2(x[0].z, x[1].z));
+        st2(buf + 3 * kTile, make_double2(p[0].x, p[1].x));
+        st2(buf + 4 * kTile, make_double2(p[0].y, p[1].y));
+        st2(buf + 5 * kTile, make_double2(p[0].z, p[1].z));
+        if (__builtin_expect(!(ok0 && ok1), 0)) {       // recovery overwrites the particle's slot
+            if (!ok0) gather_step_exact_slot<FORMULA, STAGED>(a, smem, i, buf, kTile);
+            if (!ok1) gather_step_exact_slot<FORMULA, STAGED>(a, smem, i + 1, buf + 1, kTile);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tile_store(a.p, t, tiles + s * kTileBytes);
+            // refill the previous tile's stage: its stores were committed one
+            // iteration ago; wait until they have finished READING shared memory
+            const int64_t tn = t + (nst - 1) * tstep;
+            if (t != t0 && tn < ta.ntiles) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                tile_load(a.p, tn, tiles + prev * kTileBytes, &full[prev]);
+            }
+        }
+        prev = s;
+        if (++s == nst) { s = 0; parity ^= 1u; }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+
+    // ragged tail (< kTile particles) on the last CTA, scalar path
+    if (blockIdx.x == gridDim.x - 1) {
+        for (int64_t i = ta.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
+            Vec3 x, p;
+            load_one(a.p, i, x, p);
+            if (gather_step_fast<FORMULA>(a, g, x, p)) store_one(a.p, i, x, p);
+            else gather_step_exact<FORMULA, STAGED>(a, smem, i);
         }
     }
 }
@@ -534,6 +715,60 @@ static int launch_gather_push_f(const GatherArgs& a, int formula, size_t smem, b
     }
 }
 
+// TMA-pipelined variant: SoA, 16-byte aligned arrays, at least one full tile per SM.
+template <int FORMULA, bool STAGED>
+static int launch_gather_push_tma(const TmaArgs& ta, size_t smem, int blocks, cudaStream_t s) {
+    auto kern = gather_push_tma_kernel<FORMULA, STAGED>;
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    kern<<<blocks, kTmaThreads, smem, s>>>(ta);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+static bool tma_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("TURBOPY_B200_TMA");          // tuning / A-B switch, default on
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+// Returns TP_OK and sets `launched` when the TMA kernel took the call.
+static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_smem, bool staged, cudaStream_t s,
+                               bool& launched) {
+    launched = false;
+    const DeviceProps& d = device_props();
+    TmaArgs ta;
+    ta.g = a;
+    ta.ntiles = a.p.n / kTile;
+    if (!tma_enabled() || ta.ntiles < d.sm_count) return TP_OK;
+    ta.tiles_off = static_cast<uint32_t>(((staged ? grid_smem : kSmemHeader) + 127) & ~size_t(127));
+    const int64_t room = d.smem_optin - 1024 - static_cast<int64_t>(ta.tiles_off);
+    ta.nstages = static_cast<int>(std::min<int64_t>(kMaxStages, room / kTileBytes));
+    if (ta.nstages < 2) return TP_OK;
+    const size_t smem = ta.tiles_off + static_cast<size_t>(ta.nstages) * kTileBytes;
+    const int blocks = static_cast<int>(std::min<int64_t>(d.sm_count, ta.ntiles));
+    int rc;
+    switch (formula) {
+        case TP_INTERP_A:
+            rc = staged ? launch_gather_push_tma<TP_INTERP_A, true>(ta, smem, blocks, s)
+                        : launch_gather_push_tma<TP_INTERP_A, false>(ta, smem, blocks, s);
+            break;
+        case TP_INTERP_B:
+            rc = staged ? launch_gather_push_tma<TP_INTERP_B, true>(ta, smem, blocks, s)
+                        : launch_gather_push_tma<TP_INTERP_B, false>(ta, smem, blocks, s);
+            break;
+        case TP_INTERP_C:
+            rc = staged ? launch_gather_push_tma<TP_INTERP_C, true>(ta, smem, blocks, s)
+                        : launch_gather_push_tma<TP_INTERP_C, false>(ta, smem, blocks, s);
+            break;
+        default: return TP_E_MODE;
+    }
+    launched = (rc == TP_OK);
+    return rc;
+}
+
 template <int FORMULA, bool STAGED>
 static int launch_interp(const InterpArgs& a, size_t smem, cudaStream_t s) {
     auto kern = interp_kernel<FORMULA, STAGED>;
@@ -563,6 +798,12 @@ int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_
     a.axis = axis;
     a.status = reinterpret_cast<unsigned long long*>(status);
     if (a.p.n == 0) return TP_OK;
+    if (formula < TP_INTERP_A || formula > TP_INTERP_C) return TP_E_MODE;
+    if (vec2) {
+        bool launched = false;
+        if ((rc = try_gather_push_tma(a, formula, smem, staged, s, launched))) return rc;
+        if (launched) return TP_OK;
+    }
     return vec2 ? launch_gather_push_f<true>(a, formula, smem, staged, s)
                 : launch_gather_push_f<false>(a, formula, smem, staged, s);
 }
