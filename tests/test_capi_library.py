@@ -1,0 +1,84 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol the header
+declares, and refuses to compute without a B200 (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from turbopy_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    return _lib
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "turbopy_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree(lib):
+    declared = header_functions()
+    assert len(declared) >= 20
+    assert sorted(lib.SIGNATURES) == declared
+
+
+def test_every_declared_symbol_is_exported(lib):
+    handle = C.CDLL(lib.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(handle, name), f"{name} declared in include/turbopy_b200.h but not exported"
+
+
+def test_version_and_error_strings(lib):
+    l = lib.lib()
+    assert l.tp_version() == 100
+    assert lib.error_string(0) == "ok"
+    assert "no CPU fallback" in lib.error_string(lib.TP_E_NODEVICE)
+    assert lib.error_string(-2).startswith("turbopy_b200")
+
+
+def test_struct_layouts_match_header(lib):
+    assert C.sizeof(lib.Particles) == 7 * 8
+    assert C.sizeof(lib.PushConsts) == 4 * 8
+    assert C.sizeof(lib.GridFields) == 5 * 8 + 6 * 8 + 6 * 8
+
+
+def test_sass_is_sm100_with_tma(lib):
+    """The shipped cubin is sm_100a and the staging / particle pipeline really
+    use the TMA (UBLKCP = cp.async.bulk) and mbarrier (SYNCS) instructions."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out and "SYNCS" in out
+    assert "DFMA" in out                      # fp64 pipe, not tensor cores
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import numpy as np
+    import turbopy_b200 as tp
+    from helpers import make_owner
+    l = lib.lib()
+    assert l.tp_device_info(None, None, None, None, None) == lib.TP_E_NODEVICE
+    tool = tp.BorisPush(make_owner(), {"type": "BorisPush"})
+    pos = np.zeros((4, 3)); mom = np.zeros((4, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tool.push(pos, mom, 1.0, 1.0, np.zeros(3), np.zeros(3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tool.gather_push(pos, mom, 1.0, 1.0, E_grid=None, B_grid=None)
+    fdt = tp.FiniteDifference(make_owner(), {"type": "FiniteDifference", "method": "centered"})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fdt.centered_difference(np.zeros(10))
+    assert np.array_equal(pos, np.zeros((4, 3)))

@@ -1,0 +1,135 @@
+"""CPU: host-side logic of the drop-in tools (no kernel launches)."""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+from helpers import make_grid, make_owner
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_registry_semantics():
+    """turbopy/core.py:302-327: duplicate -> ValueError unless override,
+    non-subclass -> TypeError, unknown lookup -> KeyError."""
+    import turbopy_b200 as tp
+    assert tp.ComputeTool.lookup("BorisPush") is tp.BorisPush
+    assert tp.ComputeTool.lookup("Interpolators") is tp.Interpolators
+    assert tp.ComputeTool.lookup("FiniteDifference") is tp.FiniteDifference
+    assert tp.Diagnostic.lookup("kinetic_energy") is tp.KineticEnergyDiagnostic
+    with pytest.raises(ValueError, match="already registered"):
+        tp.ComputeTool.register("BorisPush", tp.BorisPush)
+    tp.ComputeTool.register("BorisPush", tp.BorisPush, override=True)
+    with pytest.raises(TypeError):
+        tp.ComputeTool.register("NotATool", dict)
+    with pytest.raises(KeyError):
+        tp.ComputeTool.lookup("nope")
+    assert tp.ComputeTool.is_valid_name("FiniteDifference") and not tp.ComputeTool.is_valid_name("nope")
+
+
+def test_constructors_touch_nothing():
+    """Reference tests build tools from a bare Simulation with no grid/clock
+    (tests/test_computetools.py:9-10); the clock does not exist yet when tools
+    are constructed (turbopy/core.py:166-178)."""
+    import turbopy_b200 as tp
+    from types import SimpleNamespace
+    owner = SimpleNamespace(clock=None, grid=None)
+    t = tp.BorisPush(owner, {"type": "BorisPush"})
+    assert t.c2 == 2.9979e8 ** 2 and t.name == "BorisPush" and t.owner is owner
+    assert callable(t.push) and callable(t.gather_push)          # bound methods exist before initialize()
+    i = tp.Interpolators(owner, {"type": "Interpolators"})
+    assert callable(i.interpolate1D)
+    f = tp.FiniteDifference(make_owner(grid=make_grid(10, 0.0, 10.0)), {"type": "FiniteDifference", "method": "centered"})
+    assert f.dr == make_grid(10, 0.0, 10.0).dr
+    assert f.setup_ddx() == f.centered_difference
+    t.initialize(); i.initialize(); f.initialize()
+
+
+def test_field_argument_lowering():
+    from turbopy_b200 import _lib
+    from turbopy_b200.tools import _FieldArg
+    e = _FieldArg(np.array([1.0, 2.0, 3.0]), "E", 5, None)
+    assert e.mode == _lib.TP_FIELD_UNIFORM_HOST and list(e.keep) == [1.0, 2.0, 3.0]
+    e = _FieldArg(np.array([[1.0, 2.0, 3.0]]), "E", 5, None)
+    assert e.mode == _lib.TP_FIELD_UNIFORM_HOST
+    e = _FieldArg(0, "E", 5, None)                      # scalar E broadcasts (dt*E*charge/2)
+    assert list(e.keep) == [0.0, 0.0, 0.0]
+    with pytest.raises(ValueError, match="cross product"):
+        _FieldArg(0, "B", 5, None)                      # np.cross with a scalar
+    pp = _FieldArg(np.ones((5, 3)), "B", 5, None)
+    assert pp.mode == _lib.TP_FIELD_PER_PARTICLE and (pp.sn, pp.sc) == (3, 1)
+    with pytest.raises(ValueError):
+        _FieldArg(np.ones((4, 3)), "B", 5, None)
+
+
+def test_particle_layout_checks():
+    from turbopy_b200.tools import _n3_strides
+    a = np.zeros((7, 3))
+    assert _n3_strides(a, "position") == (3, 1)                       # numpy C order = AoS
+    assert _n3_strides(np.asfortranarray(a), "position") == (1, 7)    # Fortran order = SoA
+    with pytest.raises(IndexError):
+        _n3_strides(np.zeros(3), "position")                          # reference: IndexError on (3,) particles
+    with pytest.raises(ValueError):
+        _n3_strides(np.zeros((3, 7)), "position")
+    with pytest.raises(TypeError):
+        _n3_strides(np.zeros((7, 3), dtype=np.float32), "position")
+
+
+def test_grid_component_lowering():
+    from turbopy_b200.tools import _grid_components
+    ng = 12
+    E = np.zeros((ng, 3))
+    comps = _grid_components(E, "E_grid", ng)
+    assert [st for _, st in comps] == [3, 3, 3]
+    assert comps[1][0].ctypes.data == E.ctypes.data + 8
+    comps = _grid_components((None, np.zeros(ng), None), "E_grid", ng)
+    assert comps[0][0] is None and comps[1][1] == 1
+    assert _grid_components(None, "B_grid", ng) == [(None, 1)] * 3
+    with pytest.raises(ValueError, match="ambiguous"):
+        _grid_components(np.zeros(ng), "E_grid", ng)
+    with pytest.raises(ValueError):
+        _grid_components((None, np.zeros(ng + 1), None), "E_grid", ng)
+
+
+def test_soa_particles_layout():
+    import turbopy_b200 as tp
+    v = tp.soa_particles(7, device="cpu", fill=0.0)
+    assert tuple(v.shape) == (7, 3) and v.stride() == (1, 8)
+    v[3, 1] = 5.0
+    assert v[:, 1][3] == 5.0 and v[:, 1].is_contiguous()
+    assert v[0, :].shape == (3,)                                     # diagnostics index data[0, :]
+
+
+def test_shard_ranges_cover_everything():
+    from turbopy_b200.sharding import shard_range
+    for n in (0, 1, 7, 1000, 10 ** 9):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under turbopy_b200/ may import it."""
+    pkg = os.path.join(ROOT, "turbopy_b200")
+    for name in os.listdir(pkg):
+        if not name.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, name)).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.module:
+                mods = [node.module]
+            assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), (name, mods)
+
+
+def test_interpolate1d_rejects_splines_without_device():
+    import turbopy_b200 as tp
+    tool = tp.Interpolators(make_owner(), {"type": "Interpolators"})
+    with pytest.raises(NotImplementedError):
+        tool.interpolate1D(np.arange(4.0), np.arange(4.0), "cubic")
