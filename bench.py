@@ -291,9 +291,12 @@ def run_b200(args):
     achieved = BYTES_PER_PUSH * n / (ms / K * 1e-3) / 1e9
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic["bytes_per_launch"] if traffic else None, "peak_source": peak_src,
-                "kernel": "gather_push_kernel<VEC2, interp(B), staged>",
-                "algorithmic_bytes_per_launch": BYTES_PER_PUSH * n}
+                "traffic": (traffic["bytes_per_launch"] if traffic and traffic.get("particles") == n else None),
+                "traffic_source": (traffic.get("source") if traffic and traffic.get("particles") == n else None),
+                "peak_source": peak_src,
+                "kernel": "gather_push_tma_kernel<interp(B), staged> (TMA-pipelined fused gather + Boris push)",
+                "algorithmic_bytes_per_launch": BYTES_PER_PUSH * n,
+                "timing": "CUDA events on the launch stream around K launches, / K"}
 
     # ---- end to end through the public API on HOST (pinned) arrays
     e2e = None

@@ -200,6 +200,10 @@ int64_t tp_launch_count(void);
  * accepted (may be NULL) */
 int tp_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches, int64_t* fast_taken,
                          tp_stream_t stream);
+/* same for the branch-free in-range reciprocal / square root of the fast path
+ * against IEEE 1.0/b and sqrt(a) */
+int tp_selftest_roots(int64_t n, uint64_t seed, int64_t* mismatches, int64_t* fast_taken,
+                      tp_stream_t stream);
 
 #ifdef __cplusplus
 }

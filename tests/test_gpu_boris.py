@@ -43,6 +43,17 @@ def test_division_selftest(tp):
     assert taken.value > n // 2          # the fast path is the common case, not a dead branch
 
 
+def test_roots_selftest(tp):
+    """The branch-free in-range reciprocal / sqrt of the fast path equal IEEE
+    1.0/b and sqrt(a) wherever the guard accepts the operand."""
+    from turbopy_b200 import _lib
+    bad, taken = C.c_int64(-1), C.c_int64(-1)
+    n = 200_000_000
+    _lib.check(_lib.lib().tp_selftest_roots(n, 777, C.byref(bad), C.byref(taken), None))
+    assert bad.value == 0
+    assert taken.value > n
+
+
 def test_known_answer_crossed_fields(tp, golden):
     """The reference's own known-answer test, tests/test_computetools.py:40-62."""
     tool = pusher(tp, 1e-9)

@@ -75,6 +75,7 @@ SIGNATURES = {
     "tp_graph_destroy": (C.c_int, [C.c_void_p]),
     "tp_launch_count": (C.c_int64, []),
     "tp_selftest_division": (C.c_int, [C.c_int64, C.c_uint64, c_i64_p, c_i64_p, C.c_void_p]),
+    "tp_selftest_roots": (C.c_int, [C.c_int64, C.c_uint64, c_i64_p, c_i64_p, C.c_void_p]),
 }
 
 _lib = None

@@ -39,7 +39,7 @@ __device__ __forceinline__ void boris_step(const PushK& k, const Vec3& eq, const
     const double vmx = p.x + hx, vmy = p.y + hy, vmz = p.z + hz;
     // :430-431  m1 = sqrt(mass**2 + sum(p*p)/c2)   (old momentum)
     const double pp = (p.x * p.x + p.y * p.y) + p.z * p.z;
-    const double m1 = sqrt(k.mm + quot<FAST>(pp, rc2, g));
+    const double m1 = root<FAST>(k.mm + quot<FAST>(pp, rc2, g), g);
     // :433  t = dt*B*charge/m1/2
     const Recip<FAST> r1 = make_recip<FAST>(m1, g);
     const double tx = quot<FAST>(bq.x, r1, g) * 0.5;
@@ -65,7 +65,7 @@ __device__ __forceinline__ void boris_step(const PushK& k, const Vec3& eq, const
     p.z = plz + hz;
     // :439-440  m2 from the new momentum
     const double qq = (p.x * p.x + p.y * p.y) + p.z * p.z;
-    const double m2 = sqrt(k.mm + quot<FAST>(qq, rc2, g));
+    const double m2 = root<FAST>(k.mm + quot<FAST>(qq, rc2, g), g);
     // :441  position = position + dt*momentum/m2
     const Recip<FAST> r2 = make_recip<FAST>(m2, g);
     x.x = x.x + quot<FAST>(k.dt * p.x, r2, g);

@@ -83,9 +83,76 @@ __global__ void selftest_division_kernel(int64_t n, uint64_t seed, unsigned long
     atomicAdd(mismatches + 1, taken);
 }
 
+// rcp_inrange / sqrt_inrange against the IEEE library results (1.0/b, sqrt(a)).
+__global__ void selftest_roots_kernel(int64_t n, uint64_t seed, unsigned long long* out) {
+    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    unsigned long long bad = 0, taken = 0;
+    for (int64_t i = gtid; i < n; i += gstride) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(2 * i + 1);
+        auto next = [&z]() {
+            z += 0x9E3779B97F4A7C15ull;
+            uint64_t x = z;
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+            x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+            return x ^ (x >> 31);
+        };
+        uint64_t m = next() & 0xFFFFFFFFFFFFFull;
+        const uint64_t sel = next();
+        const int mode = static_cast<int>(sel & 15);
+        if (mode == 1) m = 0xFFFFFFFFFFFFFull - (m & 0xff);     // mantissa ~ all ones
+        if (mode == 2) m &= 0xfff;                              // ~ power of two
+        if (mode == 3) m = (m & 0xff) | 0x6A09E667F3BCDull;     // ~ sqrt(2) pattern
+        int e = static_cast<int>((sel >> 8) % 1200) - 600;      // spans inside and outside [2^-500, 2^500]
+        if (mode == 4) e = static_cast<int>((sel >> 8) % 2046) - 1022;
+        double v = __longlong_as_double(static_cast<long long>((static_cast<uint64_t>(1023 + e) << 52) | m));
+        if (mode == 5) v = 0.0;
+        if (mode == 6) v = __longlong_as_double(0x7ff0000000000000ll);
+        if (mode == 7) v = -v;
+        Guard g;
+        guard_range(g, v);
+        const double s = sqrt_inrange(v);
+        const double rcp = rcp_inrange(v);
+        Guard gr;
+        guard_range(gr, rcp);
+        if (guard_ok(g)) {                                      // sqrt argument accepted
+            ++taken;
+            const double ref = sqrt(v);                         // negative argument: both NaN (payload may differ;
+            const bool same = __double_as_longlong(s) == __double_as_longlong(ref) || (s != s && ref != ref);
+            if (!same) ++bad;                                   //  the kernels treat any NaN as "recompute")
+        }
+        if (guard_ok(gr) && v > 0.0) {                          // reciprocal accepted
+            ++taken;
+            if (__double_as_longlong(rcp) != __double_as_longlong(1.0 / v)) ++bad;
+        }
+    }
+    if (bad) atomicAdd(out, bad);
+    atomicAdd(out + 1, taken);
+}
+
 }  // namespace tp
 
 using namespace tp;
+
+extern "C" int tp_selftest_roots(int64_t n, uint64_t seed, int64_t* mismatches, int64_t* fast_taken,
+                                 tp_stream_t stream) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    if (!mismatches || n < 0) return TP_E_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned long long* dev = nullptr;
+    TP_CUDA_TRY(cudaMalloc(&dev, 2 * sizeof(unsigned long long)));
+    cudaMemsetAsync(dev, 0, 2 * sizeof(unsigned long long), s);
+    selftest_roots_kernel<<<d.sm_count * 4, 256, 0, s>>>(n, seed, dev);
+    count_launch();
+    unsigned long long host[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(dev);
+    *mismatches = static_cast<int64_t>(host[0]);
+    if (fast_taken) *fast_taken = static_cast<int64_t>(host[1]);
+    return static_cast<int>(e);
+}
 
 extern "C" int tp_version(void) { return TP_VERSION; }
 
