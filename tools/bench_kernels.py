@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""Roofline numbers for every kernel of the hot path (the driver's headline
+bench is ../bench.py; this script feeds DESIGN.md / profiles/).
+
+    python tools/bench_kernels.py [--quick] [--json out.json]
+
+Each row: algorithmic bytes per unit x units / CUDA-event time, against the
+measured HBM copy peak.  Inputs are larger than L2 unless the row says so.
+"""
+import argparse
+import json
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import turbopy_b200 as tp  # noqa: E402
+from oracle import grid as ogrid  # noqa: E402  (Grid.r restatement, setup only)
+
+Q_E, M_E = -1.6022e-19, 9.1094e-31
+
+
+def peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timed(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / iters
+
+
+def owner_for(ng, dt=1e-12, rmax=1.0):
+    r = ogrid.grid_points(0.0, rmax, ng)
+    grid = SimpleNamespace(r=r, dr=ogrid.grid_dr(0.0, rmax, ng), num_points=ng, r_min=0.0, r_max=rmax,
+                           cell_widths=ogrid.cell_widths(r))
+    return SimpleNamespace(clock=SimpleNamespace(dt=dt, num_steps=10), grid=grid)
+
+
+def particles(n, seed=0, lo=0.05, hi=0.95, sigma=0.1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pos, mom = tp.soa_particles(n), tp.soa_particles(n)
+    pos.copy_(lo + (hi - lo) * torch.rand((n, 3), dtype=torch.float64, device="cuda", generator=g))
+    mom.copy_(torch.randn((n, 3), dtype=torch.float64, device="cuda", generator=g) * (M_E * 2.9979e8 * sigma))
+    return pos, mom
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    pk = peak()
+    rows = []
+
+    def add(name, units, bytes_per_unit, seconds, note=""):
+        gbs = units * bytes_per_unit / seconds / 1e9
+        rows.append({"kernel": name, "units": units, "bytes_per_unit": bytes_per_unit, "ms": seconds * 1e3,
+                     "units_per_s": units / seconds, "GBps": gbs, "frac_of_measured_peak": gbs / pk, "note": note})
+        print(f"{name:58s} {units:>11d} units  {seconds*1e3:9.4f} ms  {units/seconds/1e9:8.2f} G/s  "
+              f"{gbs:8.1f} GB/s  {100*gbs/pk:5.1f}%  {note}", flush=True)
+
+    it = 5 if args.quick else 30
+    n16 = 16 << 20
+
+    # ---- kernel 1a: BorisPush.push, uniform E x B
+    for n, note in ((1_000_000, "config 1 size: 48 MB of state, L2-resident"), (n16, ""), (64 << 20, "")):
+        if args.quick and n > n16:
+            continue
+        tool = tp.BorisPush(owner_for(10), {"type": "BorisPush"})
+        pos, mom = particles(n)
+        E, B = np.array([0.0, 1e5, 0.0]), np.array([0.0, 0.0, 1.0])
+        add("push uniform ExB (SoA)", n, 96, timed(lambda: tool.push(pos, mom, Q_E, M_E, E, B), it), note)
+        if n == 1_000_000:
+            with tp.StepGraph() as g:
+                for _ in range(100):
+                    tool.push(pos, mom, Q_E, M_E, E, B)
+            add("push uniform ExB (SoA), CUDA graph of 100 steps", n, 96, timed(g.replay, 5) / 100, note)
+            g.close()
+        del pos, mom
+    # AoS (numpy's layout) and per-particle fields (the un-fused path: 144 B/particle)
+    tool = tp.BorisPush(owner_for(10), {"type": "BorisPush"})
+    pos, mom = particles(n16)
+    pa, ma = pos.contiguous(), mom.contiguous()
+    add("push uniform ExB (AoS (n,3) C-order)", n16, 96,
+        timed(lambda: tool.push(pa, ma, Q_E, M_E, np.array([0.0, 1e5, 0.0]), np.array([0.0, 0.0, 1.0])), it))
+    Ep, Bp = tp.soa_particles(n16, fill=1e4), tp.soa_particles(n16, fill=0.5)
+    add("push per-particle E,B (SoA, un-fused)", n16, 144, timed(lambda: tool.push(pos, mom, Q_E, M_E, Ep, Bp), it))
+    del pa, ma, Ep, Bp
+
+    # ---- kernel 1b: fused gather + push
+    for ng, ncomp, formula in ((30, 1, "interp"), (4097, 1, "interp"), (1025, 6, "interp"), (1025, 6, "create_interpolator"),
+                               (1025, 6, "interp1d_nd"), ((1 << 20) + 1, 6, "interp")):
+        ow = owner_for(ng, dt=1e-13)
+        tool = tp.BorisPush(ow, {"type": "BorisPush"})
+        r = torch.from_numpy(ow.grid.r).cuda()
+        if ncomp == 1:
+            E = (None, torch.cos(6.28 * r), None); B = None
+        else:
+            E = torch.stack([1e3 * torch.cos(6.28 * (k + 1) * r) for k in range(3)], dim=1).contiguous()
+            B = torch.stack([torch.sin(6.28 * (k + 1) * r) for k in range(3)], dim=1).contiguous()
+        pos.copy_(0.05 + 0.9 * torch.rand((n16, 3), dtype=torch.float64, device="cuda"))
+        mom.zero_()
+        t = timed(lambda: tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, formula=formula), it)
+        tool.check_status()
+        add(f"gather+push ng={ng} comps={ncomp} formula={formula}", n16, 96, t,
+            "grid in L2 (not staged)" if ng > 5000 else "grid staged in smem by TMA")
+    # sorted particles on the big grid (cell-coherent gathers)
+    ow = owner_for((1 << 20) + 1, dt=1e-13)
+    tool = tp.BorisPush(ow, {"type": "BorisPush"})
+    r = torch.from_numpy(ow.grid.r).cuda()
+    E = torch.stack([1e3 * torch.cos(6.28 * (k + 1) * r) for k in range(3)], dim=1).contiguous()
+    B = torch.stack([torch.sin(6.28 * (k + 1) * r) for k in range(3)], dim=1).contiguous()
+    xs = torch.sort(0.05 + 0.9 * torch.rand(n16, dtype=torch.float64, device="cuda")).values
+    pos[:, 0].copy_(xs); mom.zero_()
+    t = timed(lambda: tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B), it)
+    add("gather+push ng=1048577 comps=6, particles sorted by x", n16, 96, t, "grid in L2")
+    del pos, mom
+
+    # ---- kernel 2: FiniteDifference stencils
+    for n in ((1 << 24) + 1, (1 << 28)):
+        if args.quick and n > (1 << 25):
+            continue
+        ow = owner_for(n)
+        fdt = tp.FiniteDifference(ow, {"type": "FiniteDifference", "method": "centered"})
+        y = torch.sin(torch.linspace(0, 6.28, n, dtype=torch.float64, device="cuda"))
+        add("fd centered_difference", n, 16, timed(lambda: fdt.centered_difference(y), it), "incl. torch.empty_like")
+        add("fd upwind_left", n, 24, timed(lambda: fdt.upwind_left(y), it))
+        D = fdt.del2_radial()
+        add("fd del2_radial @ f", n, 24, timed(lambda: D @ y, it))
+        del y, fdt, D, ow
+        tp.GridOnDevice._cache.clear()
+        torch.cuda.empty_cache()
+
+    # ---- kernel 3: moment reduction
+    for n in (n16, 128 << 20):
+        if args.quick and n > n16:
+            continue
+        _, mom = particles(n)
+        out = torch.empty(8, dtype=torch.float64, device="cuda")
+        scratch = torch.empty(16384, dtype=torch.float64, device="cuda")
+        add("moments reduction (KE, P, |p|^2)", n, 24,
+            timed(lambda: tp.reduce_moments(mom, M_E, 2.9979e8 ** 2, out=out, scratch=scratch), it))
+        del mom
+
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump({"peak_gbs": pk, "rows": rows}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,7 +105,7 @@ __device__ __forceinline__ void store_pair(const ParticleArgs& a, int64_t i, con
 // that the loads of that iteration hit L2 instead of paying the DRAM latency
 // with only 16 resident warps per SM.  SoA fast path only (16-byte aligned).
 #ifndef TP_PF_DIST
-#define TP_PF_DIST 1
+#define TP_PF_DIST 2      /* iterations ahead; 0/1/2/3 measured: 46.3 / 51.0 / 51.3 / 50.6 G pushes/s */
 #endif
 __device__ __forceinline__ void prefetch_tile(const ParticleArgs& a, int64_t first, int64_t n_even) {
 #if TP_PF_DIST > 0
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) push_kernel(const __g
             const int64_t i = pr * 2;
             Vec3 x[2], p[2];
             load_pair(a.p, i, x, p);
+            prefetch_tile(a.p, (pr - threadIdx.x + TP_PF_DIST * gstride) * 2, npairs * 2);
             const bool ok0 = push_one_fast(a, Eu, Bu, i, x[0], p[0]);
             const bool ok1 = push_one_fast(a, Eu, Bu, i + 1, x[1], p[1]);
             if (__builtin_expect(ok0 && ok1, 1)) {
@@ -534,6 +535,97 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const _
 }
 
 // ---------------------------------------------------------------------------
+// BorisPush.push with uniform E, B, particles streamed by the TMA (same ring as
+// above; configs 1 and 4 of BASELINE.json call push() directly)
+// ---------------------------------------------------------------------------
+struct PushTmaArgs {
+    PushArgs a;
+    int nstages;
+    uint32_t tiles_off;
+    int64_t ntiles;
+};
+
+__device__ __noinline__ void push_one_exact_slot(const PushArgs& a, int64_t i, double* slot, int pitch) {
+    const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
+    Vec3 x, p;
+    load_one(a.p, i, x, p);                    // the tile has not been stored yet: global memory holds the input
+    Guard g;
+    boris_step<false>(a.k, dt_field_q(a.k, Eu), dt_field_q(a.k, Bu), x, p, g);
+    slot[0] = x.x; slot[pitch] = x.y; slot[2 * pitch] = x.z;
+    slot[3 * pitch] = p.x; slot[4 * pitch] = p.y; slot[5 * pitch] = p.z;
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1) push_tma_kernel(const __grid_constant__ PushTmaArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const PushArgs& a = ta.a;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);
+    unsigned char* tiles = smem + ta.tiles_off;
+    const int nst = ta.nstages;
+    if (threadIdx.x == 0)
+        for (int s = 0; s < nst; ++s) mbar_init(&full[s], 1);
+    __syncthreads();
+    const int64_t t0 = blockIdx.x, tstep = gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nst; ++s) {
+            const int64_t t = t0 + s * tstep;
+            if (t < ta.ntiles) tile_load(a.p, t, tiles + s * kTileBytes, &full[s]);
+        }
+    }
+    const Vec3 equ = dt_field_q(a.k, uniform_of(a.E)), bqu = dt_field_q(a.k, uniform_of(a.B));
+    int s = 0, prev = 0;
+    uint32_t parity = 0;
+    for (int64_t t = t0; t < ta.ntiles; t += tstep) {
+        mbar_wait(&full[s], parity);
+        double* buf = reinterpret_cast<double*>(tiles + s * kTileBytes) + 2 * threadIdx.x;
+        Vec3 x[2], p[2];
+        {
+            const double2 x0 = ld2(buf), x1 = ld2(buf + kTile), x2 = ld2(buf + 2 * kTile);
+            const double2 p0 = ld2(buf + 3 * kTile), p1 = ld2(buf + 4 * kTile), p2 = ld2(buf + 5 * kTile);
+            x[0].x = x0.x; x[1].x = x0.y; x[0].y = x1.x; x[1].y = x1.y; x[0].z = x2.x; x[1].z = x2.y;
+            p[0].x = p0.x; p[1].x = p0.y; p[0].y = p1.x; p[1].y = p1.y; p[0].z = p2.x; p[1].z = p2.y;
+        }
+        const int64_t i = t * kTile + 2 * threadIdx.x;
+        Guard g0, g1;
+        boris_step<true>(a.k, equ, bqu, x[0], p[0], g0);
+        boris_step<true>(a.k, equ, bqu, x[1], p[1], g1);
+        const bool ok0 = guard_ok(g0) && finite3(x[0].x, x[0].y, x[0].z) && a.k.fast_ok;
+        const bool ok1 = guard_ok(g1) && finite3(x[1].x, x[1].y, x[1].z) && a.k.fast_ok;
+        st2(buf, make_double2(x[0].x, x[1].x));
+        st2(buf + kTile, make_double2(x[0].y, x[1].y));
+        st2(buf + 2 * kTile, make_double2(x[0].z, x[1].z));
+        st2(buf + 3 * kTile, make_double2(p[0].x, p[1].x));
+        st2(buf + 4 * kTile, make_double2(p[0].y, p[1].y));
+        st2(buf + 5 * kTile, make_double2(p[0].z, p[1].z));
+        if (__builtin_expect(!(ok0 && ok1), 0)) {
+            if (!ok0) push_one_exact_slot(a, i, buf, kTile);
+            if (!ok1) push_one_exact_slot(a, i + 1, buf + 1, kTile);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tile_store(a.p, t, tiles + s * kTileBytes);
+            const int64_t tn = t + (nst - 1) * tstep;
+            if (t != t0 && tn < ta.ntiles) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                tile_load(a.p, tn, tiles + prev * kTileBytes, &full[prev]);
+            }
+        }
+        prev = s;
+        if (++s == nst) { s = 0; parity ^= 1u; }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (blockIdx.x == gridDim.x - 1) {                       // ragged tail, scalar path
+        const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
+        for (int64_t i = ta.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
+            Vec3 x, p;
+            load_one(a.p, i, x, p);
+            if (push_one_fast(a, Eu, Bu, i, x, p)) store_one(a.p, i, x, p);
+            else push_one_exact(a, i);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // gather only (Interpolators.interpolate1D(x, y)(x_new))
 // ---------------------------------------------------------------------------
 struct InterpArgs {
@@ -827,6 +919,22 @@ extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
     if ((rc = fill_field(B, b_mode, b_sn, b_sc, a.B))) return rc;
     if (a.p.n == 0) return TP_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool uniform = a.E.mode != TP_FIELD_PER_PARTICLE && a.B.mode != TP_FIELD_PER_PARTICLE;
+    if (vec2 && uniform && tma_enabled() && a.p.n / kTile >= d.sm_count) {
+        PushTmaArgs ta;
+        ta.a = a;
+        ta.ntiles = a.p.n / kTile;
+        ta.tiles_off = kSmemHeader;
+        ta.nstages = static_cast<int>(std::min<int64_t>(kMaxStages, (d.smem_optin - 1024 - kSmemHeader) / kTileBytes));
+        if (ta.nstages >= 2) {
+            const size_t smem = ta.tiles_off + static_cast<size_t>(ta.nstages) * kTileBytes;
+            if ((rc = set_smem(push_tma_kernel, smem))) return rc;
+            const int blocks = static_cast<int>(std::min<int64_t>(d.sm_count, ta.ntiles));
+            push_tma_kernel<<<blocks, kTmaThreads, smem, s>>>(ta);
+            count_launch();
+            return static_cast<int>(cudaGetLastError());
+        }
+    }
     if (vec2) {
         const int blocks = grid_blocks(reinterpret_cast<const void*>(push_kernel<true>), 0, (a.p.n + 1) / 2);
         push_kernel<true><<<blocks, kThreads, 0, s>>>(a);
