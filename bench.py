@@ -37,6 +37,8 @@ OMEGA, C_WAVE, E0 = 2e8, 2.998e8, 1.0          # particle_in_field.toml:15-17, p
 DT = 1e-8 / 20                                 # particle_in_field.toml:7-10
 BYTES_PER_PUSH = 96                            # 6 fp64 read + 6 fp64 written per particle-step
 METRIC = "Boris particle-pushes/sec (fp64, gather+push)"
+WORKLOAD = ("configs[1]: pif electron ensemble in 1D EM plane wave, linear field gather "
+            "(E_y on grid, B=0) + Boris push")
 UNIT = "pushes/s"
 
 
@@ -211,8 +213,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "pif plane wave: interp1d gather of E_y + BorisPush.push (CPU numpy)",
-                   "particles_per_step": per_worker * cores, "grid_nodes": args.ng},
+        "config": {"workload": WORKLOAD, "particles_per_gpu": args.particles, "grid_nodes": args.ng, "dt": DT,
+                   "layout": "numpy (n,3) fp64 on the host", "parallelism": f"{cores} forked host workers",
+                   "sample_particles_per_step": per_worker * cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -333,8 +336,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: pif electron ensemble in 1D EM plane wave, linear field gather "
-                                   "(E_y on grid, B=0) + Boris push",
+            "config": {"workload": WORKLOAD,
                        "particles_per_gpu": n, "grid_nodes": args.ng, "dt": DT, "layout": "SoA fp64 resident",
                        "parallelism": f"particle shards x{world}, grid replicated",
                        "l2": "inputs larger than L2 (1.6 GB of particle state per step vs 126 MB)",
