@@ -173,7 +173,8 @@ def test_fused_vs_oracle(tp, formula, ng, layout):
 
 @pytest.mark.parametrize("formula", ["A", "B", "C"])
 @pytest.mark.parametrize("ng", [513, (1 << 18) + 1])
-def test_fused_tma_pipeline_vs_oracle(tp, formula, ng):
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_fused_tma_pipeline_vs_oracle(tp, formula, ng, layout):
     """Enough particles (> one 1024-particle tile per SM) for the TMA-pipelined
     kernel: several ring wrap-arounds per CTA, a ragged scalar tail, on-node and
     out-of-grid particles inside full tiles (exact path through shared memory)."""
@@ -190,7 +191,10 @@ def test_fused_tma_pipeline_vs_oracle(tp, formula, ng):
     comps = smooth_fields(grid)
     E = torch.from_numpy(np.stack(comps[:3], axis=1)).cuda()
     B = torch.from_numpy(np.stack(comps[3:], axis=1)).cuda()
-    pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    if layout == "soa":
+        pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    else:                                            # numpy's (n,3) C order: the AoS tile mode of the ring
+        pos, mom = torch.from_numpy(pos0).cuda(), torch.from_numpy(mom0).cuda()
     tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, axis=0, formula=formula)
     with pytest.raises((ValueError, AssertionError), match="3 particle"):
         tool.check_status()

@@ -389,32 +389,34 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) gather_push_kernel(co
 }
 
 // ---------------------------------------------------------------------------
-// fused gather + push, particles streamed by the TMA
+// particles streamed by the TMA: the shared-memory ring
 // ---------------------------------------------------------------------------
-// The register-path kernel above keeps only 16 warps per SM resident (128
-// registers per thread) and its loads sit at the end of each iteration, so the
+// The register-path kernels above keep only 16 warps per SM resident (128
+// registers per thread) and their loads sit at the end of each iteration, so the
 // HBM latency is exposed (profiles/r1_v2: long_scoreboard is the top stall).
 // Here the particle arrays themselves go through the TMA: one persistent CTA
-// per SM owns a ring of NST shared-memory stages; each stage holds one tile of
-// kTile particles as six contiguous 8 KB component slices.  One elected thread
-//   - fills a stage with six cp.async.bulk loads that complete on the stage's
+// per SM owns a ring of NST shared-memory stages of 48 KB; a stage holds one
+// tile of kTile = 1024 particles, either as six contiguous 8 KB component slices
+// (SoA) or as two contiguous 24 KB (n,3) C-order blocks (AoS, numpy's layout).
+// One elected thread
+//   - fills a stage with cp.async.bulk loads that complete on the stage's
 //     mbarrier (expect_tx = 48 KB),
 //   - after the CTA has updated the tile in place in shared memory, drains it
-//     with six cp.async.bulk stores (bulk async-group),
+//     with cp.async.bulk stores (bulk async-group),
 //   - re-fills the stage of the PREVIOUS tile once that tile's stores have
 //     finished reading shared memory (wait_group.read 1),
 // so two tiles of loads are always in flight behind the tile being computed and
 // no thread ever waits on a global load.  The 512 threads read their two
-// particles from the stage with 128-bit LDS, run the same fast / exact
-// arithmetic as the register path, and write the result back with 128-bit STS.
+// particles from the stage with 128-bit LDS (conflict-free in both layouts),
+// run the same fast / exact arithmetic as the register path, and write the
+// result back with 128-bit STS.
 constexpr int kTmaThreads = 512;
 constexpr int kTile = 2 * kTmaThreads;                         // particles per tile
 constexpr uint32_t kSliceBytes = kTile * sizeof(double);       // 8 KB per component
 constexpr uint32_t kTileBytes = 6 * kSliceBytes;               // 48 KB per stage
 constexpr int kMaxStages = 4;
 
-struct TmaArgs {
-    GatherArgs g;
+struct RingArgs {
     int nstages;
     uint32_t tiles_off;        // byte offset of stage 0 in dynamic shared memory (128-B aligned)
     int64_t ntiles;            // full tiles; the remaining n - ntiles*kTile particles use the scalar path
@@ -426,106 +428,180 @@ __device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_sme
                  : "memory");
 }
 
+template <bool AOS>
 __device__ __forceinline__ void tile_load(const ParticleArgs& p, int64_t tile, unsigned char* stage, uint64_t* bar) {
     const int64_t first = tile * kTile;
     mbar_expect_tx(bar, kTileBytes);
+    if (AOS) {
+        tma_bulk_g2s(stage, p.pos + 3 * first, 3 * kSliceBytes, bar);
+        tma_bulk_g2s(stage + 3 * kSliceBytes, p.mom + 3 * first, 3 * kSliceBytes, bar);
+    } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        tma_bulk_g2s(stage + c * kSliceBytes, p.pos + c * p.pos_sc + first, kSliceBytes, bar);
-        tma_bulk_g2s(stage + (3 + c) * kSliceBytes, p.mom + c * p.mom_sc + first, kSliceBytes, bar);
+        for (int c = 0; c < 3; ++c) {
+            tma_bulk_g2s(stage + c * kSliceBytes, p.pos + c * p.pos_sc + first, kSliceBytes, bar);
+            tma_bulk_g2s(stage + (3 + c) * kSliceBytes, p.mom + c * p.mom_sc + first, kSliceBytes, bar);
+        }
     }
 }
 
+template <bool AOS>
 __device__ __forceinline__ void tile_store(const ParticleArgs& p, int64_t tile, const unsigned char* stage) {
     const int64_t first = tile * kTile;
+    if (AOS) {
+        tma_bulk_s2g(p.pos + 3 * first, stage, 3 * kSliceBytes);
+        tma_bulk_s2g(p.mom + 3 * first, stage + 3 * kSliceBytes, 3 * kSliceBytes);
+    } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        tma_bulk_s2g(p.pos + c * p.pos_sc + first, stage + c * kSliceBytes, kSliceBytes);
-        tma_bulk_s2g(p.mom + c * p.mom_sc + first, stage + (3 + c) * kSliceBytes, kSliceBytes);
+        for (int c = 0; c < 3; ++c) {
+            tma_bulk_s2g(p.pos + c * p.pos_sc + first, stage + c * kSliceBytes, kSliceBytes);
+            tma_bulk_s2g(p.mom + c * p.mom_sc + first, stage + (3 + c) * kSliceBytes, kSliceBytes);
+        }
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-// Recovery path for the TMA kernel: the tile has not been stored yet, so global
-// memory still holds the particle's input; the result (or, for a flagged
-// particle, the untouched input) goes back through the shared-memory stage.
-// `slot` addresses the particle's x component inside the stage; the other five
-// components follow at multiples of `pitch` doubles.
-template <int FORMULA, bool STAGED>
-__device__ __noinline__ void gather_step_exact_slot(const GatherArgs& a, unsigned char* smem, int64_t i,
-                                                    double* slot, int pitch) {
-    const GridView g = make_view<STAGED>(a, smem);
-    Vec3 x, p;
-    exact_core<FORMULA>(a, g, i, x, p);          // flagged: x, p hold the untouched input
-    slot[0] = x.x; slot[pitch] = x.y; slot[2 * pitch] = x.z;
-    slot[3 * pitch] = p.x; slot[4 * pitch] = p.y; slot[5 * pitch] = p.z;
+// Where the calling thread's particle v (0 or 1) lives inside a stage: pointers
+// to its x and px components; y/z (py/pz) follow at multiples of pitch doubles.
+template <bool AOS>
+struct Slot {
+    static constexpr int pitch = AOS ? 1 : kTile;
+    __device__ static double* x(double* stage, int v) { return AOS ? stage + 6 * threadIdx.x + 3 * v : stage + 2 * threadIdx.x + v; }
+    __device__ static double* p(double* stage, int v) { return x(stage, v) + 3 * kTile; }
+};
+
+template <bool AOS>
+__device__ __forceinline__ void stage_read(const double* stage, Vec3 (&x)[2], Vec3 (&p)[2]) {
+    if (AOS) {          // six contiguous doubles per array: x0 y0 z0 x1 y1 z1
+        const double* b = stage + 6 * threadIdx.x;
+        const double2 a0 = ld2(b), a1 = ld2(b + 2), a2 = ld2(b + 4);
+        const double2 m0 = ld2(b + 3 * kTile), m1 = ld2(b + 3 * kTile + 2), m2 = ld2(b + 3 * kTile + 4);
+        x[0].x = a0.x; x[0].y = a0.y; x[0].z = a1.x; x[1].x = a1.y; x[1].y = a2.x; x[1].z = a2.y;
+        p[0].x = m0.x; p[0].y = m0.y; p[0].z = m1.x; p[1].x = m1.y; p[1].y = m2.x; p[1].z = m2.y;
+    } else {
+        const double* b = stage + 2 * threadIdx.x;
+        const double2 x0 = ld2(b), x1 = ld2(b + kTile), x2 = ld2(b + 2 * kTile);
+        const double2 p0 = ld2(b + 3 * kTile), p1 = ld2(b + 4 * kTile), p2 = ld2(b + 5 * kTile);
+        x[0].x = x0.x; x[1].x = x0.y; x[0].y = x1.x; x[1].y = x1.y; x[0].z = x2.x; x[1].z = x2.y;
+        p[0].x = p0.x; p[1].x = p0.y; p[0].y = p1.x; p[1].y = p1.y; p[0].z = p2.x; p[1].z = p2.y;
+    }
 }
 
-template <int FORMULA, bool STAGED>
-__global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const __grid_constant__ TmaArgs ta) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const GatherArgs& a = ta.g;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);       // one mbarrier per stage
-    unsigned char* tiles = smem + ta.tiles_off;
-    const int nst = ta.nstages;
-    if (threadIdx.x == 0)
-        for (int s = 0; s < nst; ++s) mbar_init(&full[s], 1);
-    if (STAGED) stage_issue(a, smem); else __syncthreads();       // (stage_issue syncs after its own init)
-    const int64_t t0 = blockIdx.x, tstep = gridDim.x;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < nst; ++s) {
-            const int64_t t = t0 + s * tstep;
-            if (t < ta.ntiles) tile_load(a.p, t, tiles + s * kTileBytes, &full[s]);
-        }
+template <bool AOS>
+__device__ __forceinline__ void stage_write(double* stage, const Vec3 (&x)[2], const Vec3 (&p)[2]) {
+    if (AOS) {
+        double* b = stage + 6 * threadIdx.x;
+        st2(b, make_double2(x[0].x, x[0].y)); st2(b + 2, make_double2(x[0].z, x[1].x)); st2(b + 4, make_double2(x[1].y, x[1].z));
+        b += 3 * kTile;
+        st2(b, make_double2(p[0].x, p[0].y)); st2(b + 2, make_double2(p[0].z, p[1].x)); st2(b + 4, make_double2(p[1].y, p[1].z));
+    } else {
+        double* b = stage + 2 * threadIdx.x;
+        st2(b, make_double2(x[0].x, x[1].x));
+        st2(b + kTile, make_double2(x[0].y, x[1].y));
+        st2(b + 2 * kTile, make_double2(x[0].z, x[1].z));
+        st2(b + 3 * kTile, make_double2(p[0].x, p[1].x));
+        st2(b + 4 * kTile, make_double2(p[0].y, p[1].y));
+        st2(b + 5 * kTile, make_double2(p[0].z, p[1].z));
     }
-    const GridView g = make_view<STAGED>(a, smem);
-    if (STAGED) stage_wait(smem);
+}
 
+__device__ __forceinline__ void slot_write(double* xs, double* ps, int pitch, const Vec3& x, const Vec3& p) {
+    xs[0] = x.x; xs[pitch] = x.y; xs[2 * pitch] = x.z;
+    ps[0] = p.x; ps[pitch] = p.y; ps[2 * pitch] = p.z;
+}
+
+// The ring driver.  fast(x, p) -> bool updates one particle in registers;
+// recover(i, xs, ps, pitch) recomputes particle i from global memory (the tile
+// has not been stored yet) and writes it into its stage slot.
+template <bool AOS, typename Fast, typename Recover>
+__device__ __forceinline__ void tma_ring(const ParticleArgs& P, const RingArgs& ra, unsigned char* smem, Fast fast,
+                                         Recover recover) {
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);       // one mbarrier per stage (header bytes 16..47)
+    unsigned char* tiles = smem + ra.tiles_off;
+    const int nst = ra.nstages;
+    const int64_t t0 = blockIdx.x, tstep = gridDim.x;
     int s = 0, prev = 0;
     uint32_t parity = 0;
-    for (int64_t t = t0; t < ta.ntiles; t += tstep) {
+    for (int64_t t = t0; t < ra.ntiles; t += tstep) {
         mbar_wait(&full[s], parity);
-        double* buf = reinterpret_cast<double*>(tiles + s * kTileBytes) + 2 * threadIdx.x;
+        double* stage = reinterpret_cast<double*>(tiles + s * kTileBytes);
         Vec3 x[2], p[2];
-        {
-            const double2 x0 = ld2(buf), x1 = ld2(buf + kTile), x2 = ld2(buf + 2 * kTile);
-            const double2 p0 = ld2(buf + 3 * kTile), p1 = ld2(buf + 4 * kTile), p2 = ld2(buf + 5 * kTile);
-            x[0].x = x0.x; x[1].x = x0.y; x[0].y = x1.x; x[1].y = x1.y; x[0].z = x2.x; x[1].z = x2.y;
-            p[0].x = p0.x; p[1].x = p0.y; p[0].y = p1.x; p[1].y = p1.y; p[0].z = p2.x; p[1].z = p2.y;
-        }
-        const int64_t i = t * kTile + 2 * threadIdx.x;
-        const bool ok0 = gather_step_fast<FORMULA>(a, g, x[0], p[0]);
-        const bool ok1 = gather_step_fast<FORMULA>(a, g, x[1], p[1]);
-        st2(buf, make_double2(x[0].x, x[1].x));
-        st2(buf + kTile, make_double2(x[0].y, x[1].y));
-        st2(buf + 2 * kTile, make_double2(x[0].z, x[1].z));
-        st2(buf + 3 * kTile, make_double2(p[0].x, p[1].x));
-        st2(buf + 4 * kTile, make_double2(p[0].y, p[1].y));
-        st2(buf + 5 * kTile, make_double2(p[0].z, p[1].z));
-        if (__builtin_expect(!(ok0 && ok1), 0)) {       // recovery overwrites the particle's slot
-            if (!ok0) gather_step_exact_slot<FORMULA, STAGED>(a, smem, i, buf, kTile);
-            if (!ok1) gather_step_exact_slot<FORMULA, STAGED>(a, smem, i + 1, buf + 1, kTile);
+        stage_read<AOS>(stage, x, p);
+        const bool ok0 = fast(x[0], p[0]);
+        const bool ok1 = fast(x[1], p[1]);
+        stage_write<AOS>(stage, x, p);
+        if (__builtin_expect(!(ok0 && ok1), 0)) {               // recovery overwrites the particle's slot
+            const int64_t i = t * kTile + 2 * threadIdx.x;
+            if (!ok0) recover(i, Slot<AOS>::x(stage, 0), Slot<AOS>::p(stage, 0), Slot<AOS>::pitch);
+            if (!ok1) recover(i + 1, Slot<AOS>::x(stage, 1), Slot<AOS>::p(stage, 1), Slot<AOS>::pitch);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
         __syncthreads();
         if (threadIdx.x == 0) {
-            tile_store(a.p, t, tiles + s * kTileBytes);
+            tile_store<AOS>(P, t, tiles + s * kTileBytes);
             // refill the previous tile's stage: its stores were committed one
             // iteration ago; wait until they have finished READING shared memory
             const int64_t tn = t + (nst - 1) * tstep;
-            if (t != t0 && tn < ta.ntiles) {
+            if (t != t0 && tn < ra.ntiles) {
                 asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                tile_load(a.p, tn, tiles + prev * kTileBytes, &full[prev]);
+                tile_load<AOS>(P, tn, tiles + prev * kTileBytes, &full[prev]);
             }
         }
         prev = s;
         if (++s == nst) { s = 0; parity ^= 1u; }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 
+// barrier init (before the CTA-wide sync) and the prologue fills (after it)
+__device__ __forceinline__ void ring_init(const RingArgs& ra, unsigned char* smem) {
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);
+    if (threadIdx.x == 0)
+        for (int s = 0; s < ra.nstages; ++s) mbar_init(&full[s], 1);
+}
+
+template <bool AOS>
+__device__ __forceinline__ void ring_prologue(const ParticleArgs& P, const RingArgs& ra, unsigned char* smem) {
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ra.nstages; ++s) {
+            const int64_t t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(s) * gridDim.x;
+            if (t < ra.ntiles) tile_load<AOS>(P, t, smem + ra.tiles_off + s * kTileBytes, &full[s]);
+        }
+    }
+}
+
+// ---- fused gather + push ---------------------------------------------------
+struct TmaArgs {
+    GatherArgs g;
+    RingArgs ring;
+};
+
+template <int FORMULA, bool STAGED>
+__device__ __noinline__ void gather_step_exact_slot(const GatherArgs& a, unsigned char* smem, int64_t i, double* xs,
+                                                    double* ps, int pitch) {
+    const GridView g = make_view<STAGED>(a, smem);
+    Vec3 x, p;
+    exact_core<FORMULA>(a, g, i, x, p);          // flagged: x, p hold the untouched input
+    slot_write(xs, ps, pitch, x, p);
+}
+
+template <int FORMULA, bool STAGED, bool AOS>
+__global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const __grid_constant__ TmaArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const GatherArgs& a = ta.g;
+    ring_init(ta.ring, smem);
+    if (STAGED) stage_issue(a, smem); else __syncthreads();       // (stage_issue syncs after its own init)
+    ring_prologue<AOS>(a.p, ta.ring, smem);
+    const GridView g = make_view<STAGED>(a, smem);
+    if (STAGED) stage_wait(smem);
+    tma_ring<AOS>(
+        a.p, ta.ring, smem, [&](Vec3& x, Vec3& p) { return gather_step_fast<FORMULA>(a, g, x, p); },
+        [&](int64_t i, double* xs, double* ps, int pitch) {
+            gather_step_exact_slot<FORMULA, STAGED>(a, smem, i, xs, ps, pitch);
+        });
     // ragged tail (< kTile particles) on the last CTA, scalar path
     if (blockIdx.x == gridDim.x - 1) {
-        for (int64_t i = ta.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
+        for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
             Vec3 x, p;
             load_one(a.p, i, x, p);
             if (gather_step_fast<FORMULA>(a, g, x, p)) store_one(a.p, i, x, p);
@@ -534,89 +610,40 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const _
     }
 }
 
-// ---------------------------------------------------------------------------
-// BorisPush.push with uniform E, B, particles streamed by the TMA (same ring as
-// above; configs 1 and 4 of BASELINE.json call push() directly)
-// ---------------------------------------------------------------------------
+// ---- BorisPush.push with uniform E, B (configs 1 and 4 call push() directly) --
 struct PushTmaArgs {
     PushArgs a;
-    int nstages;
-    uint32_t tiles_off;
-    int64_t ntiles;
+    RingArgs ring;
 };
 
-__device__ __noinline__ void push_one_exact_slot(const PushArgs& a, int64_t i, double* slot, int pitch) {
+__device__ __noinline__ void push_one_exact_slot(const PushArgs& a, int64_t i, double* xs, double* ps, int pitch) {
     const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
     Vec3 x, p;
     load_one(a.p, i, x, p);                    // the tile has not been stored yet: global memory holds the input
     Guard g;
     boris_step<false>(a.k, dt_field_q(a.k, Eu), dt_field_q(a.k, Bu), x, p, g);
-    slot[0] = x.x; slot[pitch] = x.y; slot[2 * pitch] = x.z;
-    slot[3 * pitch] = p.x; slot[4 * pitch] = p.y; slot[5 * pitch] = p.z;
+    slot_write(xs, ps, pitch, x, p);
 }
 
+template <bool AOS>
 __global__ void __launch_bounds__(kTmaThreads, 1) push_tma_kernel(const __grid_constant__ PushTmaArgs ta) {
     extern __shared__ __align__(128) unsigned char smem[];
     const PushArgs& a = ta.a;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);
-    unsigned char* tiles = smem + ta.tiles_off;
-    const int nst = ta.nstages;
-    if (threadIdx.x == 0)
-        for (int s = 0; s < nst; ++s) mbar_init(&full[s], 1);
+    ring_init(ta.ring, smem);
     __syncthreads();
-    const int64_t t0 = blockIdx.x, tstep = gridDim.x;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < nst; ++s) {
-            const int64_t t = t0 + s * tstep;
-            if (t < ta.ntiles) tile_load(a.p, t, tiles + s * kTileBytes, &full[s]);
-        }
-    }
+    ring_prologue<AOS>(a.p, ta.ring, smem);
     const Vec3 equ = dt_field_q(a.k, uniform_of(a.E)), bqu = dt_field_q(a.k, uniform_of(a.B));
-    int s = 0, prev = 0;
-    uint32_t parity = 0;
-    for (int64_t t = t0; t < ta.ntiles; t += tstep) {
-        mbar_wait(&full[s], parity);
-        double* buf = reinterpret_cast<double*>(tiles + s * kTileBytes) + 2 * threadIdx.x;
-        Vec3 x[2], p[2];
-        {
-            const double2 x0 = ld2(buf), x1 = ld2(buf + kTile), x2 = ld2(buf + 2 * kTile);
-            const double2 p0 = ld2(buf + 3 * kTile), p1 = ld2(buf + 4 * kTile), p2 = ld2(buf + 5 * kTile);
-            x[0].x = x0.x; x[1].x = x0.y; x[0].y = x1.x; x[1].y = x1.y; x[0].z = x2.x; x[1].z = x2.y;
-            p[0].x = p0.x; p[1].x = p0.y; p[0].y = p1.x; p[1].y = p1.y; p[0].z = p2.x; p[1].z = p2.y;
-        }
-        const int64_t i = t * kTile + 2 * threadIdx.x;
-        Guard g0, g1;
-        boris_step<true>(a.k, equ, bqu, x[0], p[0], g0);
-        boris_step<true>(a.k, equ, bqu, x[1], p[1], g1);
-        const bool ok0 = guard_ok(g0) && finite3(x[0].x, x[0].y, x[0].z) && a.k.fast_ok;
-        const bool ok1 = guard_ok(g1) && finite3(x[1].x, x[1].y, x[1].z) && a.k.fast_ok;
-        st2(buf, make_double2(x[0].x, x[1].x));
-        st2(buf + kTile, make_double2(x[0].y, x[1].y));
-        st2(buf + 2 * kTile, make_double2(x[0].z, x[1].z));
-        st2(buf + 3 * kTile, make_double2(p[0].x, p[1].x));
-        st2(buf + 4 * kTile, make_double2(p[0].y, p[1].y));
-        st2(buf + 5 * kTile, make_double2(p[0].z, p[1].z));
-        if (__builtin_expect(!(ok0 && ok1), 0)) {
-            if (!ok0) push_one_exact_slot(a, i, buf, kTile);
-            if (!ok1) push_one_exact_slot(a, i + 1, buf + 1, kTile);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tile_store(a.p, t, tiles + s * kTileBytes);
-            const int64_t tn = t + (nst - 1) * tstep;
-            if (t != t0 && tn < ta.ntiles) {
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                tile_load(a.p, tn, tiles + prev * kTileBytes, &full[prev]);
-            }
-        }
-        prev = s;
-        if (++s == nst) { s = 0; parity ^= 1u; }
-    }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tma_ring<AOS>(
+        a.p, ta.ring, smem,
+        [&](Vec3& x, Vec3& p) {
+            Guard g;
+            boris_step<true>(a.k, equ, bqu, x, p, g);
+            return guard_ok(g) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+        },
+        [&](int64_t i, double* xs, double* ps, int pitch) { push_one_exact_slot(a, i, xs, ps, pitch); });
     if (blockIdx.x == gridDim.x - 1) {                       // ragged tail, scalar path
         const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
-        for (int64_t i = ta.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
+        for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
             Vec3 x, p;
             load_one(a.p, i, x, p);
             if (push_one_fast(a, Eu, Bu, i, x, p)) store_one(a.p, i, x, p);
@@ -671,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, 2) interp_kernel(const __grid_consta
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-static int fill_particles(const tp_particles* p, ParticleArgs& a, bool& vec2) {
+static int fill_particles(const tp_particles* p, ParticleArgs& a, bool& vec2, bool* aos16 = nullptr) {
     if (!p || p->n < 0) return TP_E_ARG;
     if (p->n > 0 && (!p->pos || !p->mom)) return TP_E_ARG;
     if (p->pos_stride_n <= 0 || p->pos_stride_c <= 0 || p->mom_stride_n <= 0 || p->mom_stride_c <= 0)
@@ -681,6 +708,9 @@ static int fill_particles(const tp_particles* p, ParticleArgs& a, bool& vec2) {
     a.n = p->n;
     vec2 = layout_of(a.pos_sn, a.pos_sc, a.n) == kLayoutSoA && layout_of(a.mom_sn, a.mom_sc, a.n) == kLayoutSoA &&
            aligned16(a.pos) && aligned16(a.mom) && (a.pos_sc % 2 == 0) && (a.mom_sc % 2 == 0) && a.n >= 2;
+    if (aos16)
+        *aos16 = layout_of(a.pos_sn, a.pos_sc, a.n) == kLayoutAoS && layout_of(a.mom_sn, a.mom_sc, a.n) == kLayoutAoS &&
+                 aligned16(a.pos) && aligned16(a.mom);
     return TP_OK;
 }
 
@@ -807,15 +837,23 @@ static int launch_gather_push_f(const GatherArgs& a, int formula, size_t smem, b
     }
 }
 
-// TMA-pipelined variant: SoA, 16-byte aligned arrays, at least one full tile per SM.
-template <int FORMULA, bool STAGED>
+// TMA-pipelined variant: SoA or AoS, 16-byte aligned arrays, at least one full tile per SM.
+template <int FORMULA, bool STAGED, bool AOS>
 static int launch_gather_push_tma(const TmaArgs& ta, size_t smem, int blocks, cudaStream_t s) {
-    auto kern = gather_push_tma_kernel<FORMULA, STAGED>;
+    auto kern = gather_push_tma_kernel<FORMULA, STAGED, AOS>;
     int rc = set_smem(kern, smem);
     if (rc) return rc;
     kern<<<blocks, kTmaThreads, smem, s>>>(ta);
     count_launch();
     return static_cast<int>(cudaGetLastError());
+}
+
+template <int FORMULA>
+static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, bool staged, bool aos, cudaStream_t s) {
+    if (staged) return aos ? launch_gather_push_tma<FORMULA, true, true>(ta, smem, blocks, s)
+                           : launch_gather_push_tma<FORMULA, true, false>(ta, smem, blocks, s);
+    return aos ? launch_gather_push_tma<FORMULA, false, true>(ta, smem, blocks, s)
+               : launch_gather_push_tma<FORMULA, false, false>(ta, smem, blocks, s);
 }
 
 static bool tma_enabled() {
@@ -826,35 +864,33 @@ static bool tma_enabled() {
     return on;
 }
 
-// Returns TP_OK and sets `launched` when the TMA kernel took the call.
-static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_smem, bool staged, cudaStream_t s,
-                               bool& launched) {
-    launched = false;
+// Ring geometry for `n` particles behind `front` bytes of other shared memory; false if the ring is not worth it.
+static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int& blocks) {
     const DeviceProps& d = device_props();
+    ring.ntiles = n / kTile;
+    if (!tma_enabled() || ring.ntiles < d.sm_count) return false;
+    ring.tiles_off = static_cast<uint32_t>((front + 127) & ~size_t(127));
+    const int64_t room = d.smem_optin - 1024 - static_cast<int64_t>(ring.tiles_off);
+    ring.nstages = static_cast<int>(std::min<int64_t>(kMaxStages, room / kTileBytes));
+    if (ring.nstages < 2) return false;
+    smem = ring.tiles_off + static_cast<size_t>(ring.nstages) * kTileBytes;
+    blocks = static_cast<int>(std::min<int64_t>(d.sm_count, ring.ntiles));
+    return true;
+}
+
+// Returns TP_OK and sets `launched` when the TMA kernel took the call.
+static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_smem, bool staged, bool aos,
+                               cudaStream_t s, bool& launched) {
+    launched = false;
     TmaArgs ta;
     ta.g = a;
-    ta.ntiles = a.p.n / kTile;
-    if (!tma_enabled() || ta.ntiles < d.sm_count) return TP_OK;
-    ta.tiles_off = static_cast<uint32_t>(((staged ? grid_smem : kSmemHeader) + 127) & ~size_t(127));
-    const int64_t room = d.smem_optin - 1024 - static_cast<int64_t>(ta.tiles_off);
-    ta.nstages = static_cast<int>(std::min<int64_t>(kMaxStages, room / kTileBytes));
-    if (ta.nstages < 2) return TP_OK;
-    const size_t smem = ta.tiles_off + static_cast<size_t>(ta.nstages) * kTileBytes;
-    const int blocks = static_cast<int>(std::min<int64_t>(d.sm_count, ta.ntiles));
+    size_t smem = 0; int blocks = 0;
+    if (!plan_ring(a.p.n, staged ? grid_smem : kSmemHeader, ta.ring, smem, blocks)) return TP_OK;
     int rc;
     switch (formula) {
-        case TP_INTERP_A:
-            rc = staged ? launch_gather_push_tma<TP_INTERP_A, true>(ta, smem, blocks, s)
-                        : launch_gather_push_tma<TP_INTERP_A, false>(ta, smem, blocks, s);
-            break;
-        case TP_INTERP_B:
-            rc = staged ? launch_gather_push_tma<TP_INTERP_B, true>(ta, smem, blocks, s)
-                        : launch_gather_push_tma<TP_INTERP_B, false>(ta, smem, blocks, s);
-            break;
-        case TP_INTERP_C:
-            rc = staged ? launch_gather_push_tma<TP_INTERP_C, true>(ta, smem, blocks, s)
-                        : launch_gather_push_tma<TP_INTERP_C, false>(ta, smem, blocks, s);
-            break;
+        case TP_INTERP_A: rc = launch_gather_push_tma_v<TP_INTERP_A>(ta, smem, blocks, staged, aos, s); break;
+        case TP_INTERP_B: rc = launch_gather_push_tma_v<TP_INTERP_B>(ta, smem, blocks, staged, aos, s); break;
+        case TP_INTERP_C: rc = launch_gather_push_tma_v<TP_INTERP_C>(ta, smem, blocks, staged, aos, s); break;
         default: return TP_E_MODE;
     }
     launched = (rc == TP_OK);
@@ -879,8 +915,8 @@ int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_
     if (d.status != TP_OK) return d.status;
     GatherArgs a;
     std::memset(&a, 0, sizeof(a));
-    bool vec2 = false;
-    int rc = fill_particles(p, a.p, vec2);
+    bool vec2 = false, aos16 = false;
+    int rc = fill_particles(p, a.p, vec2, &aos16);
     if (rc) return rc;
     if ((rc = fill_consts(k, a.k))) return rc;
     if (axis < 0 || axis > 2) return TP_E_MODE;
@@ -891,9 +927,9 @@ int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_
     a.status = reinterpret_cast<unsigned long long*>(status);
     if (a.p.n == 0) return TP_OK;
     if (formula < TP_INTERP_A || formula > TP_INTERP_C) return TP_E_MODE;
-    if (vec2) {
+    if (vec2 || aos16) {
         bool launched = false;
-        if ((rc = try_gather_push_tma(a, formula, smem, staged, s, launched))) return rc;
+        if ((rc = try_gather_push_tma(a, formula, smem, staged, aos16, s, launched))) return rc;
         if (launched) return TP_OK;
     }
     return vec2 ? launch_gather_push_f<true>(a, formula, smem, staged, s)
@@ -911,8 +947,8 @@ extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
     if (d.status != TP_OK) return d.status;
     PushArgs a;
     std::memset(&a, 0, sizeof(a));
-    bool vec2 = false;
-    int rc = fill_particles(p, a.p, vec2);
+    bool vec2 = false, aos16 = false;
+    int rc = fill_particles(p, a.p, vec2, &aos16);
     if (rc) return rc;
     if ((rc = fill_consts(k, a.k))) return rc;
     if ((rc = fill_field(E, e_mode, e_sn, e_sc, a.E))) return rc;
@@ -920,17 +956,18 @@ extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
     if (a.p.n == 0) return TP_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool uniform = a.E.mode != TP_FIELD_PER_PARTICLE && a.B.mode != TP_FIELD_PER_PARTICLE;
-    if (vec2 && uniform && tma_enabled() && a.p.n / kTile >= d.sm_count) {
+    if ((vec2 || aos16) && uniform) {
         PushTmaArgs ta;
         ta.a = a;
-        ta.ntiles = a.p.n / kTile;
-        ta.tiles_off = kSmemHeader;
-        ta.nstages = static_cast<int>(std::min<int64_t>(kMaxStages, (d.smem_optin - 1024 - kSmemHeader) / kTileBytes));
-        if (ta.nstages >= 2) {
-            const size_t smem = ta.tiles_off + static_cast<size_t>(ta.nstages) * kTileBytes;
-            if ((rc = set_smem(push_tma_kernel, smem))) return rc;
-            const int blocks = static_cast<int>(std::min<int64_t>(d.sm_count, ta.ntiles));
-            push_tma_kernel<<<blocks, kTmaThreads, smem, s>>>(ta);
+        size_t smem = 0; int blocks = 0;
+        if (plan_ring(a.p.n, kSmemHeader, ta.ring, smem, blocks)) {
+            if (aos16) {
+                if ((rc = set_smem(push_tma_kernel<true>, smem))) return rc;
+                push_tma_kernel<true><<<blocks, kTmaThreads, smem, s>>>(ta);
+            } else {
+                if ((rc = set_smem(push_tma_kernel<false>, smem))) return rc;
+                push_tma_kernel<false><<<blocks, kTmaThreads, smem, s>>>(ta);
+            }
             count_launch();
             return static_cast<int>(cudaGetLastError());
         }
