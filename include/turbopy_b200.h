@@ -156,6 +156,14 @@ int tp_fd_del2_radial_apply_f64(const double* f, const double* r, double* out, i
  * offsets ndiag HOST ints (|off| <= 2, ndiag <= 5). */
 int tp_fd_dia_apply_f64(const double* data, const int* offsets, int ndiag,
                         const double* x, double* out, int64_t n, tp_stream_t stream);
+/* the same for operators whose diagonals are constant apart from <= 8 entries
+ * within 4 columns of either boundary (ddx :140-155, ddr :246-263, del2
+ * :225-244, BC_left_* :265-357, BC_right_extrap :359-381): coef[k] is the
+ * constant of diagonal k (HOST), (ov_diag[o], ov_col[o], ov_val[o]) the
+ * exceptions data[ov_diag][ov_col] = ov_val (HOST).  Reads only x: 16 B/point. */
+int tp_fd_dia_const_apply_f64(const double* coef, const int* offsets, int ndiag,
+                              const int* ov_diag, const int64_t* ov_col, const double* ov_val, int nov,
+                              const double* x, double* out, int64_t n, tp_stream_t stream);
 
 /* ---- kernel 3: energy / moment reduction (new; no reference function) ----
  * out8 (device) = {KE, Px, Py, Pz, sum|p|^2, n, 0, 0} with

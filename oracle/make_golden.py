@@ -282,6 +282,37 @@ def golden_fd(tp):
     print("fd.npz:", len(out), "arrays; oracle == reference bit-for-bit")
 
 
+def golden_fd_operators(tp):
+    """Every remaining FiniteDifference matrix builder: stored
+    diagonals, dense form and D @ y from the reference; oracle asserted identical."""
+    out = {}
+    for tag, n, rmax in (("n10", 10, 10.0), ("n1025", 1025, 1.0)):
+        sim = refload.make_owner(tp, grid={"N": n, "r_min": 0.0, "r_max": rmax,
+                                           "coordinate_system": "cylindrical"})
+        g = sim.grid
+        tool = tp.computetools.FiniteDifference(sim, {"type": "FiniteDifference", "method": "centered"})
+        rng = np.random.default_rng(n)
+        y = rng.normal(size=n)
+        out[f"{tag}_y"] = y
+        for name in fd.BANDED_NAMES:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                D = getattr(tool, name)()
+            data, offsets = fd.banded_operator(name, g.r, g.dr)
+            assert list(D.offsets) == list(offsets), name
+            assert bits_equal(np.nan_to_num(D.data, nan=-7.0), np.nan_to_num(data, nan=-7.0)), name
+            Dy = D @ y
+            assert bits_equal(np.nan_to_num(Dy, nan=-7.0), np.nan_to_num(fd.dia_apply(data, offsets, y), nan=-7.0)), name
+            # dense form: value equality (scipy builds it through COO and loses the sign of -0.0)
+            assert np.array_equal(np.nan_to_num(D.toarray(), nan=-7.0),
+                                  np.nan_to_num(fd.dia_toarray(data, offsets, n), nan=-7.0)), name
+            out[f"{tag}_{name}_data"], out[f"{tag}_{name}_offsets"] = D.data, np.array(D.offsets)
+            out[f"{tag}_{name}_apply"] = Dy
+            if n == 10:
+                out[f"{tag}_{name}_dense"] = D.toarray()
+    np.savez_compressed(os.path.join(GOLDEN, "fd_operators.npz"), **out)
+    print("fd_operators.npz:", len(out), "arrays; oracle == reference bit-for-bit")
+
+
 def main():
     if not refload.available():
         raise SystemExit("needs /root/reference (build container only)")
@@ -291,6 +322,7 @@ def main():
     golden_gather(tp)
     golden_pif(tp)
     golden_fd(tp)
+    golden_fd_operators(tp)
 
 
 if __name__ == "__main__":

@@ -138,3 +138,44 @@ def test_kinetic_energy_diagnostic(tp, tmp_path):
     ref = omom.moments(mom0[:, 0], mom0[:, 1], mom0[:, 2], M_E, C_LIGHT ** 2)
     assert abs(rows[0, 0] - ref[0]) <= 1e-12 * ref[0]
     assert rows[0, 5] == n
+
+
+# ---------------------------------------------------------------- remaining banded operators (8f-1)
+@pytest.mark.parametrize("name", ofd.BANDED_NAMES)
+def test_banded_operator_goldens(tp, golden_dir, name):
+    """Every other FiniteDifference matrix builder against the reference-generated
+    goldens (stored diagonals, dense form, D @ y) and the oracle."""
+    g = np.load(f"{golden_dir}/fd_operators.npz")
+    for tag, n, rmax in (("n10", 10, 10.0), ("n1025", 1025, 1.0)):
+        tool, grid = fd_tool(tp, n, rmax)
+        D = getattr(tool, name)()
+        assert D.shape == (n, n)
+        assert list(D.offsets) == list(g[f"{tag}_{name}_offsets"])
+        want = g[f"{tag}_{name}_data"]
+        got = D.data
+        assert np.array_equal(np.nan_to_num(got, nan=-7.0), np.nan_to_num(want, nan=-7.0)), "stored diagonals"
+        y = g[f"{tag}_y"]
+        out = (D @ torch.from_numpy(y).cuda()).cpu().numpy()
+        assert_bits_equal(np.nan_to_num(out, nan=-7.0), np.nan_to_num(g[f"{tag}_{name}_apply"], nan=-7.0), "D @ y")
+        data, offsets = ofd.banded_operator(name, grid.r, grid.dr)
+        assert_bits_equal(np.nan_to_num(out, nan=-7.0), np.nan_to_num(ofd.dia_apply(data, offsets, y), nan=-7.0))
+        if n == 10:
+            assert np.array_equal(np.nan_to_num(D.toarray(), nan=-7.0),
+                                  np.nan_to_num(g[f"{tag}_{name}_dense"], nan=-7.0)), "dense form"
+
+
+def test_banded_operator_composition_and_large_grid(tp):
+    """BC @ D composes lazily; a 16 Mi-point apply equals the oracle on sampled windows."""
+    n = (1 << 24) + 1
+    tool, grid = fd_tool(tp, n)
+    y = np.sin(40.0 * grid.r) + grid.r ** 2
+    yd = torch.from_numpy(y).cuda()
+    for name in ("ddx", "del2", "BC_right_extrap"):
+        out = (getattr(tool, name)() @ yd).cpu().numpy()
+        data, offsets = ofd.banded_operator(name, grid.r, grid.dr)
+        assert_bits_equal(out, ofd.dia_apply(data, offsets, y), name)
+    op = tool.BC_left_extrap() @ tool.ddx()
+    got = (op @ yd).cpu().numpy()
+    d1, o1 = ofd.banded_operator("ddx", grid.r, grid.dr)
+    d2, o2 = ofd.banded_operator("BC_left_extrap", grid.r, grid.dr)
+    assert_bits_equal(got, ofd.dia_apply(d2, o2, ofd.dia_apply(d1, o1, y)))

@@ -151,6 +151,51 @@ __global__ void __launch_bounds__(kFdThreads) fd_dia_kernel(const __grid_constan
     }
 }
 
+// Banded apply for operators whose stored diagonals are CONSTANT apart from a
+// few boundary entries (ddx, ddr, del2, BC_*: turbopy/computetools.py:140-155,
+// 225-381): the coefficients travel as kernel arguments, nothing but x is read
+// (16 B/point instead of (ndiag+2)*8).  Same summation order as scipy's
+// dia_matvec; entry (k, j) means data[k][j].
+constexpr int kMaxOverrides = 8;
+struct DiaConstArgs {
+    const double* x; double* out; int64_t n;
+    int ndiag; int off[5]; double coef[5];
+    int nov; int ov_k[kMaxOverrides]; int64_t ov_j[kMaxOverrides]; double ov_v[kMaxOverrides];
+};
+
+__device__ __forceinline__ double dia_const_row(const DiaConstArgs& a, int64_t i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (k >= a.ndiag) break;
+        const int64_t j = i + a.off[k];
+        if (j < 0 || j >= a.n) continue;
+        double c = a.coef[k];
+        if (j < 4 || j >= a.n - 4)                     // overrides only live next to the boundaries
+            for (int o = 0; o < a.nov; ++o)
+                if (a.ov_k[o] == k && a.ov_j[o] == j) c = a.ov_v[o];
+        acc = acc + c * a.x[j];
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kFdThreads) fd_dia_const_kernel(const __grid_constant__ DiaConstArgs a, bool vec) {
+    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kFdThreads + threadIdx.x;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kFdThreads;
+    const int64_t npairs = (a.n + 1) >> 1;
+    for (int64_t pr = gtid; pr < npairs; pr += gstride) {
+        const int64_t i = pr * 2;
+        const double o0 = dia_const_row(a, i);
+        if (i + 1 < a.n) {
+            const double o1 = dia_const_row(a, i + 1);
+            if (vec) st2(a.out + i, make_double2(o0, o1));
+            else { a.out[i] = o0; a.out[i + 1] = o1; }
+        } else {
+            a.out[i] = o0;
+        }
+    }
+}
+
 static ConstDiv host_recip(double b) {
     ConstDiv c;
     c.b = b;
@@ -216,6 +261,34 @@ extern "C" int tp_fd_dia_apply_f64(const double* data, const int* offsets, int n
         a.off[k] = offsets[k];
     }
     fd_dia_kernel<<<fd_blocks(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int tp_fd_dia_const_apply_f64(const double* coef, const int* offsets, int ndiag, const int* ov_diag,
+                                         const int64_t* ov_col, const double* ov_val, int nov, const double* x,
+                                         double* out, int64_t n, tp_stream_t stream) {
+    const DeviceProps& dp = device_props();
+    if (dp.status != TP_OK) return dp.status;
+    if (n < 0 || ndiag < 0 || ndiag > 5 || nov < 0 || nov > kMaxOverrides || (n > 0 && (!x || !out)) ||
+        (ndiag > 0 && (!coef || !offsets)) || (nov > 0 && (!ov_diag || !ov_col || !ov_val)))
+        return TP_E_ARG;
+    if (n == 0) return TP_OK;
+    DiaConstArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.x = x; a.out = out; a.n = n; a.ndiag = ndiag; a.nov = nov;
+    for (int k = 0; k < ndiag; ++k) {
+        if (offsets[k] < -2 || offsets[k] > 2) return TP_E_ARG;
+        a.off[k] = offsets[k];
+        a.coef[k] = coef[k];
+    }
+    for (int o = 0; o < nov; ++o) {
+        if (ov_diag[o] < 0 || ov_diag[o] >= ndiag) return TP_E_ARG;
+        if (!(ov_col[o] >= 0 && ov_col[o] < n && (ov_col[o] < 4 || ov_col[o] >= n - 4))) return TP_E_ARG;
+        a.ov_k[o] = ov_diag[o]; a.ov_j[o] = ov_col[o]; a.ov_v[o] = ov_val[o];
+    }
+    fd_dia_const_kernel<<<fd_blocks((n + 1) / 2), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        a, aligned16(out));
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

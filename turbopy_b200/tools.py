@@ -447,14 +447,78 @@ class BandedOperator:
     uses.  ``apply`` is the kernel launch; the entries are only materialised on
     request (by applying the operator to unit vectors)."""
 
-    def __init__(self, n, offsets, apply_fn, device):
+    def __init__(self, n, offsets, apply_fn, device, stored=None):
         self.shape = (n, n)
         self.offsets = np.asarray(offsets, dtype=np.int32)
         self._apply = apply_fn
         self._device = device
         self._dense = None
+        self._stored = stored            # callable -> (ndiag, n) numpy array of the stored diagonals, if known
+
+    # ---- constructors for the two stored forms --------------------------------
+    @classmethod
+    def from_constants(cls, n, offsets, coef, overrides, device):
+        """Diagonal k is the constant ``coef[k]`` except ``data[k][j] = v`` for
+        the ``(k, j, v)`` in ``overrides`` (j within 4 columns of a boundary).
+        Applied by tp_fd_dia_const_apply_f64: only the operand is read."""
+        offsets = [int(o) for o in offsets]
+        nd = len(offsets)
+        c_coef = (C.c_double * nd)(*[float(c) for c in coef])
+        c_off = (C.c_int * nd)(*offsets)
+        nov = len(overrides)
+        c_ok = (C.c_int * max(nov, 1))(*[int(k) for k, _, _ in overrides])
+        c_oj = (C.c_int64 * max(nov, 1))(*[int(j) % n for _, j, _ in overrides])
+        c_ov = (C.c_double * max(nov, 1))(*[float(v) for _, _, v in overrides])
+
+        def apply(f):
+            out = torch.empty_like(f)
+            with torch.cuda.device(f.device):
+                _lib.check(_lib.lib().tp_fd_dia_const_apply_f64(
+                    c_coef, c_off, nd, c_ok, c_oj, c_ov, nov,
+                    C.c_void_p(f.data_ptr()), C.c_void_p(out.data_ptr()), n, _stream_ptr(f.device)))
+            return out
+
+        def stored():
+            data = np.empty((nd, n))
+            for k in range(nd):
+                data[k, :] = coef[k]
+            for k, j, v in overrides:
+                data[k, j] = v
+            return data
+
+        return cls(n, offsets, apply, device, stored)
+
+    @classmethod
+    def from_diagonals(cls, data, offsets, device):
+        """Stored diagonals ``data`` ((ndiag, n) CUDA tensor, scipy's dia
+        layout), applied by tp_fd_dia_apply_f64 in scipy's summation order."""
+        data = data.contiguous()
+        nd, n = data.shape
+        offsets = [int(o) for o in offsets]
+        c_off = (C.c_int * nd)(*offsets)
+
+        def apply(f):
+            out = torch.empty_like(f)
+            with torch.cuda.device(f.device):
+                _lib.check(_lib.lib().tp_fd_dia_apply_f64(
+                    C.c_void_p(data.data_ptr()), c_off, nd, C.c_void_p(f.data_ptr()),
+                    C.c_void_p(out.data_ptr()), n, _stream_ptr(f.device)))
+            return out
+
+        return cls(n, offsets, apply, device, lambda: data.cpu().numpy())
+
+    def _compose(self, other):
+        """``self @ other``: apply ``other`` first (operator product, lazily)."""
+        if other.shape != self.shape:
+            raise ValueError("dimension mismatch")
+        lo = int(self.offsets.min() + other.offsets.min())
+        hi = int(self.offsets.max() + other.offsets.max())
+        return BandedOperator(self.shape[0], list(range(lo, hi + 1)), lambda f: self._apply(other._apply(f)),
+                              self._device)
 
     def dot(self, f):
+        if isinstance(f, BandedOperator):
+            return self._compose(f)
         if isinstance(f, torch.Tensor):
             if not _is_cuda(f):
                 raise TypeError("operand must be a CUDA tensor (or a numpy array)")
@@ -479,7 +543,11 @@ class BandedOperator:
 
     @property
     def data(self):
-        """scipy's dia layout: ``data[k, j] = A[j - offsets[k], j]``."""
+        """scipy's dia layout: ``data[k, j] = A[j - offsets[k], j]`` (the stored
+        diagonals themselves, unused corner entries included, when the operator
+        was built from them)."""
+        if self._stored is not None:
+            return self._stored()
         A = self.toarray()
         n = self.shape[0]
         out = np.zeros((len(self.offsets), n))
@@ -563,3 +631,75 @@ class FiniteDifference(ComputeTool):
             return out
 
         return BandedOperator(n, [-1, 0, 1], apply, dev)
+
+    # ---- the remaining matrix builders -------------------------
+    # Operators whose diagonals are constant apart from a few boundary entries
+    # carry their coefficients as kernel arguments (nothing but the operand is
+    # read); radial_curl, whose entries depend on r, stores its diagonals.
+    def _device(self, device):
+        if not torch.cuda.is_available():
+            _lib.check(_lib.TP_E_NODEVICE)
+        return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def _n(self):
+        return int(self.owner.grid.num_points)
+
+    def ddx(self, device=None):
+        """Centered df/dx, coefficients -+1/(2 dr) (computetools.py:140-155)."""
+        g = 1 / (2.0 * self.dr)
+        return BandedOperator.from_constants(self._n(), [-1, 1], [0.0 - g, 0.0 + g], [], self._device(device))
+
+    def ddr(self, device=None):
+        """df/dr with the r = 0 row zeroed (computetools.py:246-263)."""
+        g1 = 1 / (2.0 * self.dr)
+        return BandedOperator.from_constants(self._n(), [-1, 1], [-g1, g1], [(1, 1, 0.0)], self._device(device))
+
+    def del2(self, device=None):
+        """d2f/dx2 with the doubled first-row coefficient (computetools.py:225-244)."""
+        g2 = 1 / (self.dr ** 2)
+        return BandedOperator.from_constants(self._n(), [-1, 0, 1], [g2, -2 * g2, g2], [(2, 1, 2 * g2)],
+                                             self._device(device))
+
+    def radial_curl(self, device=None):
+        """(1/r) d(r f)/dr (computetools.py:157-187); r-dependent entries, stored on the device."""
+        dev = self._device(device)
+        n = self._n()
+        r = GridOnDevice.of(self.owner.grid, dev).r
+        g = 1 / (2.0 * self.dr)
+        data = torch.zeros((3, n), dtype=torch.float64, device=dev)
+        data[0, :-1] = -g * (r[:-1] / r[1:])
+        data[2, 1:] = g * (r[1:] / r[:-1])
+        data[2, 1] = 2.0 / self.dr              # r = 0: B ~ linear
+        data[1, -1] = 1.0 / self.dr             # r = R_w
+        data[0, -2] = 2.0 * data[0, -1]
+        return BandedOperator.from_diagonals(data, [-1, 0, 1], dev)
+
+    def _bc_left(self, c1, c2, device):
+        over = [(0, 0, 0.0), (1, 1, c1)] + ([(2, 2, c2)] if c2 is not None else [])
+        offs, coef = ([0, 1, 2], [1.0, 0.0, 0.0]) if c2 is not None else ([0, 1], [1.0, 0.0])
+        return BandedOperator.from_constants(self._n(), offs, coef, over, self._device(device))
+
+    def BC_left_extrap(self, device=None):
+        """Linear extrapolation to the left boundary point (computetools.py:265-287)."""
+        return self._bc_left(2, -1, device)
+
+    def BC_left_avg(self, device=None):
+        """computetools.py:289-311."""
+        return self._bc_left(1.5, -0.5, device)
+
+    def BC_left_quad(self, device=None):
+        """Quadratic extrapolation to the left boundary (computetools.py:313-335)."""
+        r = self.owner.grid.r
+        R2 = (r[1] ** 2 + r[2] ** 2) / (r[2] ** 2 - r[1] ** 2) / 2
+        return self._bc_left(0.5 + R2, 0.5 - R2, device)
+
+    def BC_left_flat(self, device=None):
+        """Neumann condition at the left boundary (computetools.py:337-357)."""
+        return self._bc_left(1, None, device)
+
+    def BC_right_extrap(self, device=None):
+        """Linear extrapolation to the right boundary point (computetools.py:359-381)."""
+        n = self._n()
+        return BandedOperator.from_constants(n, [-2, -1, 0], [0.0, 0.0, 1.0],
+                                             [(2, n - 1, 0.0), (1, n - 2, 2.0), (0, n - 3, -1.0)],
+                                             self._device(device))
