@@ -2,12 +2,15 @@
 // (turbopy/computetools.py:104-138 direct stencils, :189-223 del2_radial, and
 // the banded dia_matrix operators of :140-187,225-381 applied as `D @ f`).
 // Line-by-line spec: oracle/fd.py.  HBM-bound streaming kernels:
-//   centered          16 B/point  (8 read + 8 written)
-//   upwind_left       24 B/point  (y, cell_widths read; d written)
-//   del2_radial apply 24 B/point  (f, r read; out written; coefficients rebuilt
-//                                  in registers instead of 3 stored diagonals)
-// Each thread produces two consecutive outputs (one 128-bit store); the +-1
-// neighbours come from L1.  Compiled with -fmad=false.
+//   centered / constant-diagonal operators  16 B/point  (8 read + 8 written)
+//   upwind_left                             24 B/point  (y, cell_widths read; d written)
+//   del2_radial apply                       24 B/point  (f, r read; out written; coefficients rebuilt
+//                                                        in registers instead of 3 stored diagonals)
+//   stored-diagonal operators               (ndiag+2)*8 B/point
+// Each thread produces FOUR consecutive outputs per iteration from a register
+// window of the operand (two 128-bit loads + halo scalars that hit L1, two
+// 128-bit stores): 64 B in flight per thread, 2048 threads per SM.
+// Compiled with -fmad=false.
 #include "common.cuh"
 
 #include <cmath>
@@ -16,15 +19,50 @@
 namespace tp {
 
 constexpr int kFdThreads = 256;
+constexpr int kQuad = 4;
 
-static int fd_blocks(int64_t n_pairs) {
+static int fd_blocks(int64_t n_quads) {
     const DeviceProps& d = device_props();
     const int64_t full = static_cast<int64_t>(d.sm_count) * 8;
-    const int64_t need = (n_pairs + kFdThreads - 1) / kFdThreads;
+    const int64_t need = (n_quads + kFdThreads - 1) / kFdThreads;
     return static_cast<int>(need < 1 ? 1 : (need < full ? need : full));
 }
 
-// d[i] = (y[i+1] - y[i-1]) / two_dr for 0 < i < n-1; d[0] = d[n-1] = 0.
+// w[k] = y[i - H + k] for k in [0, 4 + 2H); out-of-range entries are 0 (never used).
+template <int H>
+__device__ __forceinline__ void load_window(const double* __restrict__ y, int64_t i, int64_t n, bool vec,
+                                            double (&w)[kQuad + 2 * H]) {
+    if (vec && i >= H && i + kQuad + H <= n) {
+        const double2 a = ld2(y + i), b = ld2(y + i + 2);
+#pragma unroll
+        for (int k = 0; k < H; ++k) { w[k] = y[i - H + k]; w[kQuad + H + k] = y[i + kQuad + k]; }
+        w[H] = a.x; w[H + 1] = a.y; w[H + 2] = b.x; w[H + 3] = b.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kQuad + 2 * H; ++k) {
+            const int64_t j = i - H + k;
+            w[k] = (j >= 0 && j < n) ? y[j] : 0.0;
+        }
+    }
+}
+
+__device__ __forceinline__ void store_quad(double* __restrict__ d, int64_t i, int64_t n, bool vec, const double (&o)[kQuad]) {
+    if (vec && i + kQuad <= n) {
+        st2(d + i, make_double2(o[0], o[1]));
+        st2(d + i + 2, make_double2(o[2], o[3]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < kQuad; ++k)
+            if (i + k < n) d[i + k] = o[k];
+    }
+}
+
+#define TP_QUAD_LOOP(n)                                                                    \
+    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kFdThreads + threadIdx.x;      \
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kFdThreads;                  \
+    const int64_t nquads = ((n) + kQuad - 1) / kQuad;                                      \
+    for (int64_t qd = gtid; qd < nquads; qd += gstride)
+
 // Quotient by the constant 2*dr: FAST policy with a per-value check, IEEE otherwise.
 struct ConstDiv { double b, rb; int fast_ok; };
 
@@ -35,51 +73,37 @@ __device__ __forceinline__ double div_const(double a, const ConstDiv& c) {
     return a / c.b;
 }
 
+// d[i] = (y[i+1] - y[i-1]) / two_dr for 0 < i < n-1; d[0] = d[n-1] = 0.
 __global__ void __launch_bounds__(kFdThreads) fd_centered_kernel(const double* __restrict__ y,
                                                                  double* __restrict__ d, int64_t n,
                                                                  ConstDiv two_dr, bool vec) {
-    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kFdThreads + threadIdx.x;
-    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kFdThreads;
-    const int64_t npairs = (n + 1) >> 1;
-    for (int64_t pr = gtid; pr < npairs; pr += gstride) {
-        const int64_t i = pr * 2;
-        double o0 = 0.0, o1 = 0.0;
-        if (vec && i >= 2 && i + 3 < n) {                      // interior fast path
-            const double ym = y[i - 1];
-            const double2 yc = ld2(y + i);
-            const double yp = y[i + 2];
-            o0 = div_const(yc.y - ym, two_dr);
-            o1 = div_const(yp - yc.x, two_dr);
-            st2(d + i, make_double2(o0, o1));
-        } else {
-            if (i > 0 && i < n - 1) o0 = div_const(y[i + 1] - y[i - 1], two_dr);
-            d[i] = o0;
-            if (i + 1 < n) {
-                if (i + 1 < n - 1) o1 = div_const(y[i + 2] - y[i], two_dr);
-                d[i + 1] = o1;
-            }
+    TP_QUAD_LOOP(n) {
+        const int64_t i = qd * kQuad;
+        double w[kQuad + 2], o[kQuad];
+        load_window<1>(y, i, n, vec, w);
+#pragma unroll
+        for (int k = 0; k < kQuad; ++k) {
+            const int64_t j = i + k;
+            o[k] = (j > 0 && j < n - 1) ? div_const(w[k + 2] - w[k], two_dr) : 0.0;
         }
+        store_quad(d, i, n, vec, o);
     }
 }
 
 // d[i] = (y[i] - y[i-1]) / w[i-1] for i >= 1; d[0] = 0.
 __global__ void __launch_bounds__(kFdThreads) fd_upwind_kernel(const double* __restrict__ y,
-                                                               const double* __restrict__ w,
+                                                               const double* __restrict__ cw,
                                                                double* __restrict__ d, int64_t n, bool vec) {
-    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kFdThreads + threadIdx.x;
-    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kFdThreads;
-    const int64_t npairs = (n + 1) >> 1;
-    for (int64_t pr = gtid; pr < npairs; pr += gstride) {
-        const int64_t i = pr * 2;
-        if (vec && i >= 2 && i + 1 < n) {
-            const double ym = y[i - 1];
-            const double2 yc = ld2(y + i);
-            const double w0 = w[i - 1], w1 = w[i];
-            st2(d + i, make_double2((yc.x - ym) / w0, (yc.y - yc.x) / w1));
-        } else {
-            d[i] = (i > 0) ? (y[i] - y[i - 1]) / w[i - 1] : 0.0;
-            if (i + 1 < n) d[i + 1] = (y[i + 1] - y[i]) / w[i];
+    TP_QUAD_LOOP(n) {
+        const int64_t i = qd * kQuad;
+        double w[kQuad + 2], o[kQuad];
+        load_window<1>(y, i, n, vec, w);
+#pragma unroll
+        for (int k = 0; k < kQuad; ++k) {
+            const int64_t j = i + k;
+            o[k] = (j > 0 && j < n) ? (w[k + 1] - w[k]) / cw[j - 1] : 0.0;
         }
+        store_quad(d, i, n, vec, o);
     }
 }
 
@@ -109,45 +133,53 @@ __global__ void __launch_bounds__(kFdThreads) fd_del2_radial_kernel(const double
                                                                     const double* __restrict__ r,
                                                                     double* __restrict__ out, int64_t n, double g1,
                                                                     double g2, bool vec) {
-    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kFdThreads + threadIdx.x;
-    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kFdThreads;
-    const int64_t npairs = (n + 1) >> 1;
     const double diag = -2.0 * g2;
     const double above0 = 0.0 + 2.0 * g2;
-    for (int64_t pr = gtid; pr < npairs; pr += gstride) {
-        const int64_t i = pr * 2;
-        if (vec && i >= 2 && i + 3 < n) {
-            const double fm = f[i - 1];
-            const double2 fc = ld2(f + i);
-            const double fp = f[i + 2];
-            const double2 rc = ld2(r + i);
-            st2(out + i, make_double2(del2_row(i, n, fm, fc.x, fc.y, rc.x, g1, g2, diag, above0),
-                                      del2_row(i + 1, n, fc.x, fc.y, fp, rc.y, g1, g2, diag, above0)));
-        } else {
-            for (int64_t j = i; j < i + 2 && j < n; ++j) {
-                const double fm = j > 0 ? f[j - 1] : 0.0;
-                const double fp = j < n - 1 ? f[j + 1] : 0.0;
-                out[j] = del2_row(j, n, fm, f[j], fp, r[j], g1, g2, diag, above0);
-            }
-        }
+    TP_QUAD_LOOP(n) {
+        const int64_t i = qd * kQuad;
+        double w[kQuad + 2], rr[kQuad], o[kQuad];
+        load_window<1>(f, i, n, vec, w);
+        load_window<0>(r, i, n, vec, rr);
+#pragma unroll
+        for (int k = 0; k < kQuad; ++k)
+            o[k] = (i + k < n) ? del2_row(i + k, n, w[k], w[k + 1], w[k + 2], rr[k], g1, g2, diag, above0) : 0.0;
+        store_quad(out, i, n, vec, o);
     }
 }
 
-// Generic banded apply in scipy's dia-matvec order.
+// w[base + off] for a warp-uniform runtime offset in [-2, 2] WITHOUT dynamic
+// register indexing (which would push the window into local memory).
+template <int N>
+__device__ __forceinline__ double pick(const double (&w)[N], int base, int off) {
+    // base is a compile-time constant after unrolling; the switch is warp-uniform
+    switch (off) {
+        case -2: return w[base - 2];
+        case -1: return w[base - 1];
+        case 0: return w[base];
+        case 1: return w[base + 1];
+        default: return w[base + 2];
+    }
+}
+
+// Generic banded apply in scipy's dia-matvec order, stored diagonals.
 struct DiaArgs {
     const double* data; const double* x; double* out; int64_t n; int ndiag; int off[5];
 };
 
-__global__ void __launch_bounds__(kFdThreads) fd_dia_kernel(const __grid_constant__ DiaArgs a) {
-    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kFdThreads + threadIdx.x;
-    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kFdThreads;
-    for (int64_t i = gtid; i < a.n; i += gstride) {
-        double acc = 0.0;
+__global__ void __launch_bounds__(kFdThreads) fd_dia_kernel(const __grid_constant__ DiaArgs a, bool vec) {
+    TP_QUAD_LOOP(a.n) {
+        const int64_t i = qd * kQuad;
+        double w[kQuad + 4], o[kQuad] = {0.0, 0.0, 0.0, 0.0};
+        load_window<2>(a.x, i, a.n, vec, w);
         for (int k = 0; k < a.ndiag; ++k) {
-            const int64_t j = i + a.off[k];
-            if (j >= 0 && j < a.n) acc = acc + a.data[static_cast<int64_t>(k) * a.n + j] * a.x[j];
+            const double* dk = a.data + static_cast<int64_t>(k) * a.n;
+#pragma unroll
+            for (int q = 0; q < kQuad; ++q) {
+                const int64_t j = i + q + a.off[k];
+                if (i + q < a.n && j >= 0 && j < a.n) o[q] = o[q] + dk[j] * pick(w, q + 2, a.off[k]);
+            }
         }
-        a.out[i] = acc;
+        store_quad(a.out, i, a.n, vec, o);
     }
 }
 
@@ -163,7 +195,9 @@ struct DiaConstArgs {
     int nov; int ov_k[kMaxOverrides]; int64_t ov_j[kMaxOverrides]; double ov_v[kMaxOverrides];
 };
 
-__device__ __forceinline__ double dia_const_row(const DiaConstArgs& a, int64_t i) {
+template <int Q>
+__device__ __forceinline__ double dia_const_row(const DiaConstArgs& a, int64_t i, const double (&w)[kQuad + 4],
+                                                bool edge) {
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -171,29 +205,63 @@ __device__ __forceinline__ double dia_const_row(const DiaConstArgs& a, int64_t i
         const int64_t j = i + a.off[k];
         if (j < 0 || j >= a.n) continue;
         double c = a.coef[k];
-        if (j < 4 || j >= a.n - 4)                     // overrides only live next to the boundaries
+        if (edge)                                       // overrides only live next to the boundaries
             for (int o = 0; o < a.nov; ++o)
                 if (a.ov_k[o] == k && a.ov_j[o] == j) c = a.ov_v[o];
-        acc = acc + c * a.x[j];
+        acc = acc + c * pick(w, Q + 2, a.off[k]);
     }
     return acc;
 }
 
 __global__ void __launch_bounds__(kFdThreads) fd_dia_const_kernel(const __grid_constant__ DiaConstArgs a, bool vec) {
-    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kFdThreads + threadIdx.x;
-    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kFdThreads;
-    const int64_t npairs = (a.n + 1) >> 1;
-    for (int64_t pr = gtid; pr < npairs; pr += gstride) {
-        const int64_t i = pr * 2;
-        const double o0 = dia_const_row(a, i);
-        if (i + 1 < a.n) {
-            const double o1 = dia_const_row(a, i + 1);
-            if (vec) st2(a.out + i, make_double2(o0, o1));
-            else { a.out[i] = o0; a.out[i + 1] = o1; }
-        } else {
-            a.out[i] = o0;
-        }
+    TP_QUAD_LOOP(a.n) {
+        const int64_t i = qd * kQuad;
+        double w[kQuad + 4], o[kQuad];
+        load_window<2>(a.x, i, a.n, vec, w);
+        const bool edge = (i < 8) || (i + kQuad + 8 > a.n);       // quad within reach of an override column
+        o[0] = dia_const_row<0>(a, i, w, edge);
+        o[1] = (i + 1 < a.n) ? dia_const_row<1>(a, i + 1, w, edge) : 0.0;
+        o[2] = (i + 2 < a.n) ? dia_const_row<2>(a, i + 2, w, edge) : 0.0;
+        o[3] = (i + 3 < a.n) ? dia_const_row<3>(a, i + 3, w, edge) : 0.0;
+        store_quad(a.out, i, a.n, vec, o);
     }
+}
+
+// The same operator with the offset pattern known at compile time (the five
+// patterns the reference's builders use): interior quads run unchecked with
+// static window indices; quads near a boundary take the generic rows above.
+template <int ND, int O0, int O1, int O2>
+__global__ void __launch_bounds__(kFdThreads) fd_dia_const_t_kernel(const __grid_constant__ DiaConstArgs a, bool vec) {
+    const double c0 = a.coef[0], c1 = a.coef[1], c2 = ND > 2 ? a.coef[2] : 0.0;
+    TP_QUAD_LOOP(a.n) {
+        const int64_t i = qd * kQuad;
+        double w[kQuad + 4], o[kQuad];
+        load_window<2>(a.x, i, a.n, vec, w);
+        const bool edge = (i < 8) || (i + kQuad + 8 > a.n);
+        if (__builtin_expect(!edge, 1)) {
+#pragma unroll
+            for (int q = 0; q < kQuad; ++q) {
+                double acc = 0.0;                       // scipy: y starts from zeros
+                acc = acc + c0 * w[q + 2 + O0];
+                acc = acc + c1 * w[q + 2 + O1];
+                if (ND > 2) acc = acc + c2 * w[q + 2 + O2];
+                o[q] = acc;
+            }
+        } else {
+            o[0] = dia_const_row<0>(a, i, w, true);
+            o[1] = (i + 1 < a.n) ? dia_const_row<1>(a, i + 1, w, true) : 0.0;
+            o[2] = (i + 2 < a.n) ? dia_const_row<2>(a, i + 2, w, true) : 0.0;
+            o[3] = (i + 3 < a.n) ? dia_const_row<3>(a, i + 3, w, true) : 0.0;
+        }
+        store_quad(a.out, i, a.n, vec, o);
+    }
+}
+
+template <int ND, int O0, int O1, int O2>
+static bool launch_dia_const_t(const DiaConstArgs& a, bool vec, int blocks, cudaStream_t s) {
+    if (a.ndiag != ND || a.off[0] != O0 || a.off[1] != O1 || (ND > 2 && a.off[2] != O2)) return false;
+    fd_dia_const_t_kernel<ND, O0, O1, O2><<<blocks, kFdThreads, 0, s>>>(a, vec);
+    return true;
 }
 
 static ConstDiv host_recip(double b) {
@@ -203,6 +271,8 @@ static ConstDiv host_recip(double b) {
     c.fast_ok = const_divisor_ok(b) ? 1 : 0;
     return c;
 }
+
+static int quads(int64_t n) { return fd_blocks((n + kQuad - 1) / kQuad); }
 
 }  // namespace tp
 
@@ -214,8 +284,7 @@ extern "C" int tp_fd_centered_f64(const double* y, double* d, int64_t n, double 
     if (n < 0 || (n > 0 && (!y || !d))) return TP_E_ARG;
     if (n == 0) return TP_OK;
     const bool vec = aligned16(y) && aligned16(d);
-    fd_centered_kernel<<<fd_blocks((n + 1) / 2), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        y, d, n, host_recip(two_dr), vec);
+    fd_centered_kernel<<<quads(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(y, d, n, host_recip(two_dr), vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -227,8 +296,7 @@ extern "C" int tp_fd_upwind_left_f64(const double* y, const double* widths, doub
     if (n < 0 || (n > 0 && (!y || !d)) || (n > 1 && !widths)) return TP_E_ARG;
     if (n == 0) return TP_OK;
     const bool vec = aligned16(y) && aligned16(d);
-    fd_upwind_kernel<<<fd_blocks((n + 1) / 2), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(y, widths, d, n,
-                                                                                                   vec);
+    fd_upwind_kernel<<<quads(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(y, widths, d, n, vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -240,8 +308,7 @@ extern "C" int tp_fd_del2_radial_apply_f64(const double* f, const double* r, dou
     if (n < 0 || (n > 0 && (!f || !r || !out))) return TP_E_ARG;
     if (n == 0) return TP_OK;
     const bool vec = aligned16(f) && aligned16(r) && aligned16(out);
-    fd_del2_radial_kernel<<<fd_blocks((n + 1) / 2), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        f, r, out, n, g1, g2, vec);
+    fd_del2_radial_kernel<<<quads(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(f, r, out, n, g1, g2, vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -260,7 +327,7 @@ extern "C" int tp_fd_dia_apply_f64(const double* data, const int* offsets, int n
         if (offsets[k] < -2 || offsets[k] > 2) return TP_E_ARG;
         a.off[k] = offsets[k];
     }
-    fd_dia_kernel<<<fd_blocks(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    fd_dia_kernel<<<quads(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, aligned16(x) && aligned16(out));
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -287,8 +354,15 @@ extern "C" int tp_fd_dia_const_apply_f64(const double* coef, const int* offsets,
         if (!(ov_col[o] >= 0 && ov_col[o] < n && (ov_col[o] < 4 || ov_col[o] >= n - 4))) return TP_E_ARG;
         a.ov_k[o] = ov_diag[o]; a.ov_j[o] = ov_col[o]; a.ov_v[o] = ov_val[o];
     }
-    fd_dia_const_kernel<<<fd_blocks((n + 1) / 2), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        a, aligned16(out));
+    const bool vec = aligned16(x) && aligned16(out);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int blocks = quads(n);
+    const bool done = launch_dia_const_t<2, -1, 1, 0>(a, vec, blocks, s) ||       // ddx, ddr
+                      launch_dia_const_t<3, -1, 0, 1>(a, vec, blocks, s) ||       // del2
+                      launch_dia_const_t<3, 0, 1, 2>(a, vec, blocks, s) ||        // BC_left_extrap / avg / quad
+                      launch_dia_const_t<2, 0, 1, 0>(a, vec, blocks, s) ||        // BC_left_flat
+                      launch_dia_const_t<3, -2, -1, 0>(a, vec, blocks, s);        // BC_right_extrap
+    if (!done) fd_dia_const_kernel<<<blocks, kFdThreads, 0, s>>>(a, vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
