@@ -165,6 +165,15 @@ int tp_fd_dia_const_apply_f64(const double* coef, const int* offsets, int ndiag,
                               const int* ov_diag, const int64_t* ov_col, const double* ov_val, int nov,
                               const double* x, double* out, int64_t n, tp_stream_t stream);
 
+/* ---- PoissonSolver1DRadial.solve (turbopy/computetools.py:35-59): two fp64
+ * prefix scans, I1 = cumsum(r*s*dr), I2 = cumsum(I1*dr/r with the axis fix),
+ * out = I2 - I2[n-1].  mean_dr = np.mean(Grid.cell_widths) formed by the caller
+ * (:49).  numpy's cumsum is sequential, a parallel scan is not: results agree to
+ * rounding, not bit for bit.  scratch: tp_poisson_scratch_doubles(n) doubles. */
+int64_t tp_poisson_scratch_doubles(int64_t n);
+int tp_poisson_radial_solve_f64(const double* sources, const double* r, double mean_dr, double* out,
+                                int64_t n, double* scratch, tp_stream_t stream);
+
 /* ---- kernel 3: energy / moment reduction (new; no reference function) ----
  * out8 (device) = {KE, Px, Py, Pz, sum|p|^2, n, 0, 0} with
  * KE = sum |p|^2/(m1+mass), m1 = sqrt(mass_sq + |p|^2/c2) (the gamma*m of

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
-from oracle import boris, fd, gather, grid as ogrid, refload  # noqa: E402
+from oracle import boris, fd, gather, grid as ogrid, poisson, refload  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -313,6 +313,29 @@ def golden_fd_operators(tp):
     print("fd_operators.npz:", len(out), "arrays; oracle == reference bit-for-bit")
 
 
+def golden_poisson(tp):
+    """PoissonSolver1DRadial.solve: no reference test exists; the
+    oracle is pinned here against the imported reference, bit for bit."""
+    out = {}
+    for tag, n in (("n64", 64), ("n4097", 4097), ("n1m", (1 << 20) + 1)):
+        sim = refload.make_owner(tp, grid={"N": n, "r_min": 0.0, "r_max": 2.0, "coordinate_system": "cylindrical"})
+        tool = tp.computetools.PoissonSolver1DRadial(sim, {"type": "PoissonSolver1DRadial"})
+        g = sim.grid
+        src = np.exp(-((g.r - 0.7) / 0.2) ** 2) - 0.3 * np.cos(5 * g.r)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ref = tool.solve(src)
+        mine = poisson.solve(src, g.r, g.cell_widths)
+        assert bits_equal(ref, mine), tag
+        if n <= 4097:
+            out[f"{tag}_src"], out[f"{tag}_phi"] = src, ref
+        else:
+            sel = np.r_[0:32, n // 2 - 16:n // 2 + 16, n - 32:n]
+            out[f"{tag}_sel"], out[f"{tag}_phi"] = sel, ref[sel]
+            out[f"{tag}_scale"] = np.float64(np.abs(ref).max())
+    np.savez_compressed(os.path.join(GOLDEN, "poisson.npz"), **out)
+    print("poisson.npz:", len(out), "arrays; oracle == reference bit-for-bit")
+
+
 def main():
     if not refload.available():
         raise SystemExit("needs /root/reference (build container only)")
@@ -323,6 +346,7 @@ def main():
     golden_pif(tp)
     golden_fd(tp)
     golden_fd_operators(tp)
+    golden_poisson(tp)
 
 
 if __name__ == "__main__":

@@ -21,10 +21,10 @@ stock = turbopy.ComputeTool.lookup("BorisPush")
 import turbopy_b200 as tp                     # import performs the override
 assert tp.HAVE_TURBOPY
 assert tp.ComputeTool is turbopy.ComputeTool and issubclass(tp.BorisPush, turbopy.core.ComputeTool)
-for name in ("BorisPush", "Interpolators", "FiniteDifference"):
+for name in ("BorisPush", "Interpolators", "FiniteDifference", "PoissonSolver1DRadial"):
     assert turbopy.ComputeTool.lookup(name) is getattr(tp, name), name
 assert turbopy.ComputeTool.lookup("BorisPush") is not stock
-assert turbopy.ComputeTool.lookup("PoissonSolver1DRadial").__module__ == "turbopy.computetools"   # untouched
+assert turbopy.Diagnostic.lookup("point").__module__ == "turbopy.diagnostics"      # stock diagnostics untouched
 assert turbopy.Diagnostic.lookup("kinetic_energy") is tp.KineticEnergyDiagnostic
 try:
     turbopy.ComputeTool.register("BorisPush", tp.BorisPush)          # no override -> the reference's ValueError

@@ -18,11 +18,13 @@ from ._host import ComputeTool, Diagnostic, HAVE_TURBOPY
 from .diagnostics import KineticEnergyDiagnostic, reduce_moments
 from .graph import StepGraph
 from .particles import soa_particles, to_soa
-from .tools import BandedOperator, BorisPush, FiniteDifference, GridOnDevice, Interpolators
+from .tools import (BandedOperator, BorisPush, FiniteDifference, GridOnDevice, Interpolators,
+                    PoissonSolver1DRadial)
 
 __version__ = "0.1.0"
 
-TOOL_CLASSES = {"BorisPush": BorisPush, "Interpolators": Interpolators, "FiniteDifference": FiniteDifference}
+TOOL_CLASSES = {"BorisPush": BorisPush, "Interpolators": Interpolators, "FiniteDifference": FiniteDifference,
+                "PoissonSolver1DRadial": PoissonSolver1DRadial}
 DIAGNOSTIC_CLASSES = {"kinetic_energy": KineticEnergyDiagnostic}
 
 

@@ -61,6 +61,9 @@ SIGNATURES = {
                                       C.c_int64, C.c_void_p]),
     "tp_fd_dia_const_apply_f64": (C.c_int, [c_double_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), c_i64_p,
                                             c_double_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tp_poisson_scratch_doubles": (C.c_int64, [C.c_int64]),
+    "tp_poisson_radial_solve_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int64,
+                                              C.c_void_p, C.c_void_p]),
     "tp_reduce_scratch_doubles": (C.c_int64, []),
     "tp_reduce_moments_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_double, C.c_double, C.c_double,

@@ -152,7 +152,16 @@ class GridOnDevice:
         self.r_last = float(r_host[-1])
         self.r = torch.from_numpy(r_host).to(device)
         self._widths = None
+        self._mean_width = None
         self._r_host = r_host
+
+    @property
+    def mean_cell_width(self):
+        """``np.mean(Grid.cell_widths)`` (turbopy/computetools.py:49), formed once
+        on the host with numpy so that it carries numpy's own pairwise rounding."""
+        if self._mean_width is None:
+            self._mean_width = float(np.mean(self._r_host[1:] - self._r_host[:-1]))
+        return self._mean_width
 
     @property
     def cell_widths(self):
@@ -703,3 +712,47 @@ class FiniteDifference(ComputeTool):
         return BandedOperator.from_constants(n, [-2, -1, 0], [0.0, 0.0, 1.0],
                                              [(2, n - 1, 0.0), (1, n - 2, 2.0), (0, n - 3, -1.0)],
                                              self._device(device))
+
+
+# --------------------------------------------------------------------------- PoissonSolver1DRadial
+class PoissonSolver1DRadial(ComputeTool):
+    """Solve the 1-D radial Poisson equation by two running sums -- replaces
+    ``turbopy.computetools.PoissonSolver1DRadial`` (computetools.py:20-59).
+    The running sums are parallel fp64 scans on the GPU, so the result agrees
+    with numpy's sequential ``cumsum`` to rounding, not bit for bit."""
+
+    def __init__(self, owner, input_data):
+        super().__init__(owner, input_data)
+        self._scratch = {}
+
+    def solve(self, sources):
+        """``sources``: (N,) CUDA float64 tensor (or numpy array, staged through
+        the GPU).  Returns a fresh array of the same kind (computetools.py:35-59)."""
+        grid = self.owner.grid
+        was_numpy = not isinstance(sources, torch.Tensor)
+        if was_numpy:
+            if not torch.cuda.is_available():
+                _lib.check(_lib.TP_E_NODEVICE)
+            s = torch.from_numpy(np.ascontiguousarray(np.asarray(sources, dtype=np.float64))).cuda()
+        else:
+            if not _is_cuda(sources):
+                raise TypeError("sources must be a CUDA tensor (or a numpy array)")
+            s = sources.contiguous()
+        _require_f64(s, "sources")
+        n = int(grid.num_points)
+        if s.ndim != 1 or s.shape[0] != n:
+            raise ValueError(f"operands could not be broadcast together with shapes ({n},) {tuple(s.shape)}")
+        dev = s.device
+        gd = GridOnDevice.of(grid, dev)
+        dr = gd.mean_cell_width                             # :49, cached per grid
+        lib = _lib.lib()
+        need = int(lib.tp_poisson_scratch_doubles(n))
+        scratch = self._scratch.get(dev)
+        if scratch is None or scratch.shape[0] < need:
+            scratch = self._scratch[dev] = torch.empty(need, dtype=torch.float64, device=dev)
+        out = torch.empty_like(s)
+        with torch.cuda.device(dev):
+            _lib.check(lib.tp_poisson_radial_solve_f64(C.c_void_p(s.data_ptr()), C.c_void_p(gd.r.data_ptr()), dr,
+                                                       C.c_void_p(out.data_ptr()), n,
+                                                       C.c_void_p(scratch.data_ptr()), _stream_ptr(dev)))
+        return out.cpu().numpy() if was_numpy else out
