@@ -239,8 +239,47 @@ def golden_pif(tp):
     # the initialize() field (t=0) and row i>=1 is the field of time step i-1.
     expect = [vals[0]] + vals[:20]
     assert np.allclose(ref, expect, rtol=1e-5, atol=1e-8)
+    # The reference's own point / field diagnostics driven through the same 20-step
+    # sequence (diagnose -> update -> advance, core.py:152-158): CSV bytes as goldens
+    # for the device-aware diagnostics.
+    import tempfile
+    csv_bytes = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        specs = {
+            "point": ("point", {"field": "EMField:E", "location": 0.5, "output_type": "csv",
+                                "filename": os.path.join(tmp, "point.csv")}),
+            "point_node": ("point", {"field": "EMField:E", "location": float(g.r[7]), "output_type": "csv",
+                                     "filename": os.path.join(tmp, "point_node.csv")}),
+            "field": ("field", {"field": "EMField:E", "component": 0, "output_type": "csv",
+                                "filename": os.path.join(tmp, "field.csv")}),
+            "field_dump": ("field", {"field": "EMField:E", "component": 0, "output_type": "csv",
+                                     "dump_interval": 2e-9, "filename": os.path.join(tmp, "field_dump.csv")}),
+            "field_vec": ("field", {"field": "Vec:E", "component": 1, "output_type": "csv",
+                                    "filename": os.path.join(tmp, "field_vec.csv")}),
+        }
+        sim2 = refload.make_owner(tp, grid={"N": 30, "r_min": 0.0, "r_max": 1.0},
+                                  clock={"start_time": 0.0, "end_time": 1e-8, "num_steps": 20})
+        E = fields[0].copy()
+        V = np.stack([fields[0], 2.0 * fields[0], -fields[0]], axis=1).copy()
+        diags = {}
+        for key, (kind, data) in specs.items():
+            d = tp.Diagnostic.lookup(kind)(sim2, data)
+            d.inspect_resource({"EMField:E": E, "Vec:E": V})
+            d.initialize()
+            diags[key] = d
+        while sim2.clock.is_running():
+            for d in diags.values():
+                d.diagnose()
+            t = sim2.clock.time
+            E[:] = 1.0 * np.cos(2 * np.pi * (-omega * t + k * (g.r - 0.5)))        # EMWave.update
+            V[:, 0], V[:, 1], V[:, 2] = E, 2.0 * E, -E
+            sim2.clock.advance()
+        for key, d in diags.items():
+            d.finalize()
+            with open(specs[key][1]["filename"], "rb") as fh:
+                csv_bytes["csv_" + key] = np.frombuffer(fh.read(), dtype=np.uint8)
     np.savez_compressed(os.path.join(GOLDEN, "pif.npz"), r=g.r, dr=np.float64(g.dr),
-                        times=np.array(times), fields=np.array(fields), e_at_half=np.array(vals))
+                        times=np.array(times), fields=np.array(fields), e_at_half=np.array(vals), **csv_bytes)
     print("pif.npz: gather A at x=0.5 agrees with the reference's e_0.5.csv golden")
 
 

@@ -15,7 +15,8 @@ import os
 
 from . import _lib
 from ._host import ComputeTool, Diagnostic, HAVE_TURBOPY
-from .diagnostics import KineticEnergyDiagnostic, reduce_moments
+from .diagnostics import (DeviceFieldDiagnostic, DevicePointDiagnostic, KineticEnergyDiagnostic,
+                          reduce_moments)
 from .graph import StepGraph
 from .particles import soa_particles, to_soa
 from .tools import (BandedOperator, BorisPush, FiniteDifference, GridOnDevice, Interpolators,
@@ -25,7 +26,8 @@ __version__ = "0.1.0"
 
 TOOL_CLASSES = {"BorisPush": BorisPush, "Interpolators": Interpolators, "FiniteDifference": FiniteDifference,
                 "PoissonSolver1DRadial": PoissonSolver1DRadial}
-DIAGNOSTIC_CLASSES = {"kinetic_energy": KineticEnergyDiagnostic}
+DIAGNOSTIC_CLASSES = {"kinetic_energy": KineticEnergyDiagnostic, "device_point": DevicePointDiagnostic,
+                      "device_field": DeviceFieldDiagnostic}
 
 
 def register_tools(override=True):

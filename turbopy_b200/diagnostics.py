@@ -117,3 +117,139 @@ class KineticEnergyDiagnostic(Diagnostic):
                 filename = os.path.join(directory, filename)
             with open(filename, "wb") as f:
                 np.savetxt(f, self.values(), delimiter=",")
+
+
+# --------------------------------------------------------------------------- SURVEY 8f-3
+# Device-aware versions of the stock point / field diagnostics
+# (turbopy/diagnostics.py:61-303).  They read CUDA field tensors, keep their
+# rows in a device buffer (no host sync per step) and write, at finalize(), the
+# same CSV bytes the stock diagnostics write for the same data
+# (CSVOutputUtility: np.savetxt(f, buffer, delimiter=","), diagnostics.py:55-59).
+# Registered under NEW names ("device_point", "device_field"); the stock "point"
+# and "field" stay untouched and keep serving host numpy fields.
+def _savetxt(filename, rows):
+    with open(filename, "wb") as f:
+        np.savetxt(f, rows, delimiter=",")
+
+
+class DevicePointDiagnostic(Diagnostic):
+    """``input_data``: ``"field"`` (resource name of a (ng,) CUDA field),
+    ``"location"``, ``"output_type"`` ("csv" | "stdout"), ``"filename"``.  The
+    value is ``Grid.create_interpolator(location)(field)`` (formula A,
+    turbopy/core.py:711-755) evaluated by tp_interp1d_f64 straight into the
+    row buffer."""
+
+    def __init__(self, owner, input_data):
+        super().__init__(owner, input_data)
+        self.location = input_data["location"]
+        self.field_name = input_data["field"]
+        self.output = input_data["output_type"]
+        self.field = None
+        self.rows = None
+        self._used = 0
+
+    def inspect_resource(self, resource):
+        if self.field_name in resource:
+            self.field = resource[self.field_name]
+
+    def initialize(self):
+        from .tools import GatherStatus, GridOnDevice
+        if self.field is None:
+            raise RuntimeError(f"Diagnostic field {self.field_name} was not found")
+        grid = self.owner.grid
+        assert (self.location >= grid.r_min), "Requested point is not in the grid"       # core.py:726
+        assert (self.location <= grid.r_max), "Requested point is not in the grid"       # core.py:727
+        dev = self.field.device
+        self._grid = GridOnDevice.of(grid, dev)
+        self._status = GatherStatus(dev)
+        self._xq = torch.tensor([float(self.location)], dtype=torch.float64, device=dev)
+        self.rows = torch.zeros((int(self.owner.clock.num_steps) + 1, 1), dtype=torch.float64, device=dev)
+
+    def diagnose(self):
+        f = self.field
+        if f.ndim != 1 or not f.is_cuda or f.dtype != torch.float64:
+            raise TypeError("device_point needs a (ng,) CUDA float64 field")
+        if self._used >= self.rows.shape[0]:
+            self.rows = torch.cat([self.rows, torch.zeros_like(self.rows)])
+        g = self._grid
+        row = self.rows[self._used]
+        with torch.cuda.device(f.device):
+            _lib.check(_lib.lib().tp_interp1d_f64(
+                C.c_void_p(g.r.data_ptr()), g.ng, g.dr, g.r_first, g.r_last,
+                C.c_void_p(f.data_ptr()), 1, g.ng, f.stride(0),
+                C.c_void_p(self._xq.data_ptr()), 1, 1,
+                C.c_void_p(row.data_ptr()), 1, _lib.TP_INTERP_A,
+                C.c_void_p(self._status.words.data_ptr()),
+                C.c_void_p(torch.cuda.current_stream(f.device).cuda_stream)))
+        self._used += 1
+        if self.output == "stdout":
+            print(row.cpu().numpy())
+
+    def finalize(self):
+        self.diagnose()
+        count, _, _ = self._status.read()
+        assert count == 0, "Error finding requested point in the grid"                   # core.py:729
+        if self.output == "csv":
+            _savetxt(self.input_data["filename"], self.rows.cpu().numpy())
+
+
+class DeviceFieldDiagnostic(Diagnostic):
+    """``input_data``: ``"field"``, ``"component"``, ``"output_type"``,
+    ``"filename"``, optional ``"dump_interval"`` -- the stock FieldDiagnostic's
+    keys and timing (turbopy/diagnostics.py:164-303) for a CUDA field of shape
+    (ng,) or (ng, k)."""
+
+    def __init__(self, owner, input_data):
+        super().__init__(owner, input_data)
+        self.component = input_data["component"]
+        self.field_name = input_data["field"]
+        self.output = input_data["output_type"]
+        self.field = None
+        self.dump_interval = None
+        self.last_dump = None
+        self.diagnose = self.do_diagnostic
+        self.diagnostic_size = None
+        self.field_was_found = False
+        self.rows = None
+        self._used = 0
+
+    def inspect_resource(self, resource):
+        if self.field_name in resource:
+            self.field_was_found = True
+            self.field = resource[self.field_name]
+
+    def check_step(self):
+        if self.owner.clock.time >= self.last_dump + self.dump_interval:
+            self.do_diagnostic()
+            self.last_dump = self.owner.clock.time
+
+    def do_diagnostic(self):
+        f = self.field
+        data = f[:, self.component] if f.ndim > 1 else f
+        if self.output == "stdout":
+            print(self.field_name, data.cpu().numpy())
+            return
+        if self._used < self.rows.shape[0]:
+            self.rows[self._used].copy_(data)               # device-to-device, asynchronous
+        self._used += 1
+
+    def initialize(self):
+        if not self.field_was_found:
+            raise RuntimeError(f"Diagnostic field {self.field_name} was not found")
+        self.diagnostic_size = (int(self.owner.clock.num_steps) + 1, int(self.field.shape[0]))
+        if "dump_interval" in self.input_data:
+            self.dump_interval = self.input_data["dump_interval"]
+            self.diagnose = self.check_step
+            self.last_dump = 0
+            self.diagnostic_size = (int(np.ceil(self.owner.clock.end_time / self.dump_interval) + 1),
+                                    int(self.field.shape[0]))
+        if self.output == "csv":
+            self.rows = torch.zeros(self.diagnostic_size, dtype=torch.float64, device=self.field.device)
+
+    def finalize(self):
+        self.do_diagnostic()
+        if self.output == "csv":
+            if self._used > self.rows.shape[0]:
+                # CSVOutputUtility.append would have raised IndexError on the extra row
+                raise IndexError(f"index {self.rows.shape[0]} is out of bounds for axis 0 with size {self.rows.shape[0]}")
+            _savetxt(self.input_data["filename"], self.rows.cpu().numpy())
