@@ -201,6 +201,18 @@ int tp_gather_push_host_f64(const tp_particles* p_host, const tp_push_consts* k,
 int tp_host_last_transfer(int64_t* h2d_bytes, int64_t* d2h_bytes);
 int tp_host_release(void);        /* free the internal staging buffers/streams */
 
+/* ---- on-device field update + clock for multi-step graphs ----
+ * tp_plane_wave_f64: EMWave.update of the particle_in_field example
+ *   (tests/fixtures/particle_in_field/particle_in_field.py:32-34):
+ *   E[j*e_stride] = amplitude*cos(2*pi*(-omega*t + k*(r[j]-x0))), t = clock_dev[0].
+ * tp_clock_advance_f64: SimulationClock.advance (turbopy/core.py:533-538) on a
+ *   2-double device block {time, this_step}: this_step += 1; time = start + dt*this_step.
+ * Both read/write the clock on the device, so a captured graph of
+ * [plane_wave, gather_push, clock_advance] x K advances time on every replay. */
+int tp_plane_wave_f64(const double* r, int64_t ng, double amplitude, double omega, double k, double x0,
+                      const double* clock_dev, double* E, int64_t e_stride, tp_stream_t stream);
+int tp_clock_advance_f64(double* clock_dev, double start_time, double dt, tp_stream_t stream);
+
 /* ---- CUDA-graph capture of a sequence of the calls above ------------------ */
 int tp_graph_begin(tp_stream_t stream);
 int tp_graph_end(tp_stream_t stream, void** graph_exec);

@@ -17,6 +17,7 @@ from . import _lib
 from ._host import ComputeTool, Diagnostic, HAVE_TURBOPY
 from .diagnostics import (DeviceFieldDiagnostic, DevicePointDiagnostic, KineticEnergyDiagnostic,
                           reduce_moments)
+from .cycle import DeviceClock, PlaneWave
 from .graph import StepGraph
 from .particles import soa_particles, to_soa
 from .tools import (BandedOperator, BorisPush, FiniteDifference, GridOnDevice, Interpolators,

@@ -74,6 +74,9 @@ SIGNATURES = {
                                           C.c_int, C.c_int, c_u64_p]),
     "tp_host_last_transfer": (C.c_int, [c_i64_p, c_i64_p]),
     "tp_host_release": (C.c_int, []),
+    "tp_plane_wave_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tp_clock_advance_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     "tp_graph_begin": (C.c_int, [C.c_void_p]),
     "tp_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "tp_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
