@@ -144,7 +144,14 @@ def main():
         add("fd upwind_left", n, 24, timed(lambda: fdt.upwind_left(y), it))
         D = fdt.del2_radial()
         add("fd del2_radial @ f", n, 24, timed(lambda: D @ y, it))
-        del y, fdt, D, ow
+        for name, bpp in (("ddx", 16), ("del2", 16), ("BC_left_extrap", 16), ("radial_curl", 40)):
+            D = getattr(fdt, name)()
+            add(f"fd {name}() @ f", n, bpp, timed(lambda: D @ y, it),
+                "stored diagonals" if name == "radial_curl" else "constant diagonals in kernel args")
+        ps = tp.PoissonSolver1DRadial(ow, {"type": "PoissonSolver1DRadial"})
+        add("PoissonSolver1DRadial.solve (7 launches)", n, 80, timed(lambda: ps.solve(y), it),
+            "80 B/pt over the reduce-then-scan passes; 16 B/pt algorithmic")
+        del y, fdt, D, ow, ps
         tp.GridOnDevice._cache.clear()
         torch.cuda.empty_cache()
 
@@ -158,6 +165,28 @@ def main():
         add("moments reduction (KE, P, |p|^2)", n, 24,
             timed(lambda: tp.reduce_moments(mom, M_E, 2.9979e8 ** 2, out=out, scratch=scratch), it))
         del mom
+
+    # ---- the whole cycle on the device: field update + gather/push + clock, CUDA graph of 20 steps
+    ow = owner_for(4097, dt=5e-10)
+    tool = tp.BorisPush(ow, {"type": "BorisPush"})
+    pos, mom = particles(n16)
+    mom.zero_()
+    clock = tp.DeviceClock(0.0, 5e-10)
+    wave = tp.PlaneWave(ow.grid, 1.0, 2e8)
+
+    def cycle():
+        wave.update(clock)
+        tool.gather_push(pos, mom, Q_E, M_E, E_grid=(None, wave.E, None))
+        clock.advance()
+
+    cycle()
+    with tp.StepGraph() as g:
+        for _ in range(20):
+            cycle()
+    add("pif cycle (wave update + gather/push + clock), graph of 20 steps", n16, 96, timed(g.replay, 5) / 20)
+    g.close()
+    add("pif cycle, eager (3 launches per step)", n16, 96, timed(cycle, it))
+    tool.check_status()
 
     if args.json:
         with open(args.json, "w") as f:
