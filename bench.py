@@ -227,6 +227,9 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
+    from turbopy_b200 import build as tp_build
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0 and tp_build.needs_build():
+        tp_build.build()                                           # in-tree .so missing or stale
     import turbopy_b200 as tp
     from turbopy_b200 import _lib
     from turbopy_b200.sharding import init_process_group

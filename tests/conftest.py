@@ -15,3 +15,15 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """The C-ABI library is built in-tree (python -m turbopy_b200.build); make sure
+    it exists and matches the sources before any test loads it (no-op when fresh)."""
+    from turbopy_b200 import build
+    try:
+        build.build()
+    except RuntimeError as exc:                      # no nvcc: tests that need the library will say so
+        print(f"[conftest] could not build libturbopy_b200.so: {exc}")
+    yield
