@@ -395,26 +395,33 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) gather_push_kernel(co
 // registers per thread) and their loads sit at the end of each iteration, so the
 // HBM latency is exposed (profiles/r1_v2: long_scoreboard is the top stall).
 // Here the particle arrays themselves go through the TMA: one persistent CTA
-// per SM owns a ring of NST shared-memory stages of 48 KB; a stage holds one
-// tile of kTile = 1024 particles, either as six contiguous 8 KB component slices
-// (SoA) or as two contiguous 24 KB (n,3) C-order blocks (AoS, numpy's layout).
-// One elected thread
-//   - fills a stage with cp.async.bulk loads that complete on the stage's
-//     mbarrier (expect_tx = 48 KB),
-//   - after the CTA has updated the tile in place in shared memory, drains it
-//     with cp.async.bulk stores (bulk async-group),
-//   - re-fills the stage of the PREVIOUS tile once that tile's stores have
-//     finished reading shared memory (wait_group.read 1),
-// so two tiles of loads are always in flight behind the tile being computed and
-// no thread ever waits on a global load.  The 512 threads read their two
-// particles from the stage with 128-bit LDS (conflict-free in both layouts),
-// run the same fast / exact arithmetic as the register path, and write the
-// result back with 128-bit STS.
-constexpr int kTmaThreads = 512;
-constexpr int kTile = 2 * kTmaThreads;                         // particles per tile
-constexpr uint32_t kSliceBytes = kTile * sizeof(double);       // 8 KB per component
-constexpr uint32_t kTileBytes = 6 * kSliceBytes;               // 48 KB per stage
-constexpr int kMaxStages = 4;
+// per SM owns a ring of NST shared-memory stages of 45 KB; a stage holds one
+// tile of kTile = 960 particles, either as six contiguous 7.5 KB component
+// slices (SoA) or as two contiguous 22.5 KB (n,3) C-order blocks (AoS, numpy's
+// layout).  The CTA is warp-specialised:
+//   producer (warp 15, one elected lane) -- fills a stage with cp.async.bulk
+//     loads that complete on the stage's `full` mbarrier (expect_tx = 45 KB);
+//     when the consumers have released a stage (`done` mbarrier) it drains the
+//     updated tile with cp.async.bulk stores (bulk async-group), waits until
+//     those stores have finished READING shared memory (wait_group.read 0 --
+//     only the producer stalls) and immediately re-fills the stage with the
+//     tile NST iterations ahead;
+//   consumers (warps 0-14, 480 threads) -- wait on `full`, read their two
+//     particles with 128-bit LDS (conflict-free in both layouts), run the same
+//     fast / exact arithmetic as the register path, write the result back with
+//     128-bit STS, fence.proxy.async, and arrive on `done` once per warp.  There
+//     is no CTA-wide barrier in the loop: the warps drift apart and overlap
+//     each other's LDS / fp64 / STS phases.
+// No thread ever waits on a global load, and NST-1 tiles of loads are in flight
+// behind the tile being computed (a 3-stage ring now behaves like the earlier
+// thread-0-driven 4-stage one: 88 % -> 95 % of the HBM peak at ng = 4097).
+constexpr int kTmaThreads = 512;                               // 15 consumer warps + 1 producer warp
+constexpr int kConsumers = 480;
+constexpr int kConsumerWarps = kConsumers / 32;
+constexpr int kTile = 2 * kConsumers;                          // particles per tile
+constexpr uint32_t kSliceBytes = kTile * sizeof(double);       // 7.5 KB per component
+constexpr uint32_t kTileBytes = 6 * kSliceBytes;               // 45 KB per stage
+constexpr int kMaxStages = 3;                                  // measured: 2 / 3 / 4 stages = 84 / 97 / 90 % of peak
 
 struct RingArgs {
     int nstages;
@@ -512,15 +519,42 @@ __device__ __forceinline__ void slot_write(double* xs, double* ps, int pitch, co
 // The ring driver.  fast(x, p) -> bool updates one particle in registers;
 // recover(i, xs, ps, pitch) recomputes particle i from global memory (the tile
 // has not been stored yet) and writes it into its stage slot.
+// Shared-memory header: grid barrier at byte 0, full[s] at 16 + 8 s, done[s] at 48 + 8 s.
+__device__ __forceinline__ uint64_t* ring_full(unsigned char* smem) { return reinterpret_cast<uint64_t*>(smem + 16); }
+__device__ __forceinline__ uint64_t* ring_done(unsigned char* smem) { return reinterpret_cast<uint64_t*>(smem + 48); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <bool AOS, typename Fast, typename Recover>
 __device__ __forceinline__ void tma_ring(const ParticleArgs& P, const RingArgs& ra, unsigned char* smem, Fast fast,
                                          Recover recover) {
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);       // one mbarrier per stage (header bytes 16..47)
+    uint64_t* full = ring_full(smem);
+    uint64_t* done = ring_done(smem);
     unsigned char* tiles = smem + ra.tiles_off;
     const int nst = ra.nstages;
     const int64_t t0 = blockIdx.x, tstep = gridDim.x;
-    int s = 0, prev = 0;
+    int s = 0;
     uint32_t parity = 0;
+    if (threadIdx.x >= kConsumers) {
+        // ---------------- producer warp: one elected lane drives the TMA ----------------
+        if (threadIdx.x == kConsumers) {
+            for (int64_t t = t0; t < ra.ntiles; t += tstep) {
+                mbar_wait(&done[s], parity);                    // every consumer warp released the stage
+                tile_store<AOS>(P, t, tiles + s * kTileBytes);
+                const int64_t tn = t + nst * tstep;             // the tile that reuses this stage
+                if (tn < ra.ntiles) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores done READING smem
+                    tile_load<AOS>(P, tn, tiles + s * kTileBytes, &full[s]);
+                }
+                if (++s == nst) { s = 0; parity ^= 1u; }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        return;
+    }
+    // -------------------- consumer warps --------------------
     for (int64_t t = t0; t < ra.ntiles; t += tstep) {
         mbar_wait(&full[s], parity);
         double* stage = reinterpret_cast<double*>(tiles + s * kTileBytes);
@@ -535,37 +569,27 @@ __device__ __forceinline__ void tma_ring(const ParticleArgs& P, const RingArgs& 
             if (!ok1) recover(i + 1, Slot<AOS>::x(stage, 1), Slot<AOS>::p(stage, 1), Slot<AOS>::pitch);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tile_store<AOS>(P, t, tiles + s * kTileBytes);
-            // refill the previous tile's stage: its stores were committed one
-            // iteration ago; wait until they have finished READING shared memory
-            const int64_t tn = t + (nst - 1) * tstep;
-            if (t != t0 && tn < ra.ntiles) {
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                tile_load<AOS>(P, tn, tiles + prev * kTileBytes, &full[prev]);
-            }
-        }
-        prev = s;
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&done[s]);     // one arrival per consumer warp
         if (++s == nst) { s = 0; parity ^= 1u; }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // barrier init (before the CTA-wide sync) and the prologue fills (after it)
 __device__ __forceinline__ void ring_init(const RingArgs& ra, unsigned char* smem) {
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);
     if (threadIdx.x == 0)
-        for (int s = 0; s < ra.nstages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < ra.nstages; ++s) {
+            mbar_init(&ring_full(smem)[s], 1);
+            mbar_init(&ring_done(smem)[s], kConsumerWarps);
+        }
 }
 
 template <bool AOS>
 __device__ __forceinline__ void ring_prologue(const ParticleArgs& P, const RingArgs& ra, unsigned char* smem) {
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 16);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == kConsumers) {
         for (int s = 0; s < ra.nstages; ++s) {
             const int64_t t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(s) * gridDim.x;
-            if (t < ra.ntiles) tile_load<AOS>(P, t, smem + ra.tiles_off + s * kTileBytes, &full[s]);
+            if (t < ra.ntiles) tile_load<AOS>(P, t, smem + ra.tiles_off + s * kTileBytes, &ring_full(smem)[s]);
         }
     }
 }
@@ -601,7 +625,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const _
         });
     // ragged tail (< kTile particles) on the last CTA, scalar path
     if (blockIdx.x == gridDim.x - 1) {
-        for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
+        for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {   // all 16 warps
             Vec3 x, p;
             load_one(a.p, i, x, p);
             if (gather_step_fast<FORMULA>(a, g, x, p)) store_one(a.p, i, x, p);
@@ -872,6 +896,8 @@ static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int
     ring.tiles_off = static_cast<uint32_t>((front + 127) & ~size_t(127));
     const int64_t room = d.smem_optin - 1024 - static_cast<int64_t>(ring.tiles_off);
     ring.nstages = static_cast<int>(std::min<int64_t>(kMaxStages, room / kTileBytes));
+    if (const char* cap = std::getenv("TURBOPY_B200_STAGES"))       // tuning knob: cap the ring depth
+        ring.nstages = std::min(ring.nstages, std::max(2, std::atoi(cap)));
     if (ring.nstages < 2) return false;
     smem = ring.tiles_off + static_cast<size_t>(ring.nstages) * kTileBytes;
     blocks = static_cast<int>(std::min<int64_t>(d.sm_count, ring.ntiles));
