@@ -33,14 +33,83 @@ struct GridView {
 // ---------------------------------------------------------------------------
 // fast path
 // ---------------------------------------------------------------------------
+// The two nodes of the particle's cell (and, for formula A, the coordinates of
+// their outer neighbours), fetched either from the separate arrays of a
+// GridView or from packed 64-byte node records.
+struct NodePair {
+    int j;                      // cell index from the uniform-grid guess
+    double x0, x1;              // r[j], r[j+1]
+    double xm, xp;              // r[j-1], r[j+2] (formula A only; clamped at the ends)
+    double y0[6], y1[6];        // field components at the two nodes
+};
+
+__device__ __forceinline__ int guess_cell(double x, double r_first, double inv_dr, int ng) {
+    // F2I saturates and maps NaN to 0; the clamp keeps the loads in bounds for any x
+    const int j = __double2int_rz((x - r_first) * inv_dr);
+    return max(0, min(j, ng - 2));
+}
+
 template <int FORMULA>
-__device__ __forceinline__ bool gather6_fast(const GridView& g, double x, double (&F)[6], Guard& gd) {
-    const int last = g.ng - 2;
-    // uniform-grid guess; F2I saturates and maps NaN to 0, the clamp keeps the
-    // loads in bounds for any x
-    int j = __double2int_rz((x - g.r_first) * g.inv_dr);
-    j = max(0, min(j, last));
-    const double x0 = g.r[j], x1 = g.r[j + 1];
+__device__ __forceinline__ void fetch_nodes(const GridView& g, double x, NodePair& np) {
+    const int j = guess_cell(x, g.r_first, g.inv_dr, g.ng);
+    np.j = j;
+    np.x0 = g.r[j];
+    np.x1 = g.r[j + 1];
+    if (FORMULA == TP_INTERP_A) {
+        np.xm = g.r[max(j - 1, 0)];
+        np.xp = g.r[min(j + 2, g.ng - 1)];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        np.y0[k] = 0.0; np.y1[k] = 0.0;
+        if (g.comp[k] != nullptr) {
+            const double* y = g.comp[k] + static_cast<int64_t>(j) * g.stride[k];
+            np.y0[k] = y[0];
+            np.y1[k] = y[g.stride[k]];
+        }
+    }
+}
+
+// Packed node records for grids that live in L2: record j = {r[j], Ex, Ey, Ez,
+// Bx, By, Bz, 0}[j], 64 bytes, 64-byte aligned (written by pack_nodes_kernel each
+// call).  A particle fetches its two nodes with four 256-bit loads instead of
+// fourteen scattered 8-byte loads -- the L1 pays per 128-byte line touched, so
+// random gathers get ~3.5x cheaper (profiles/r1_kernels.json, ng = 2^20+1).
+struct RecView {
+    const double* rec;
+    int ng;
+    double r_first, inv_dr, dr;
+    unsigned present;           // bit k: component k exists
+};
+
+__device__ __forceinline__ void ld_record(const double* p, double (&v)[8]) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(p + 4));
+}
+
+template <int FORMULA>
+__device__ __forceinline__ void fetch_records(const RecView& rv, double x, NodePair& np) {
+    const int j = guess_cell(x, rv.r_first, rv.inv_dr, rv.ng);
+    np.j = j;
+    double a[8], b[8];
+    const double* base = rv.rec + static_cast<int64_t>(j) * 8;
+    ld_record(base, a);
+    ld_record(base + 8, b);
+    np.x0 = a[0]; np.x1 = b[0];
+    if (FORMULA == TP_INTERP_A) {
+        np.xm = rv.rec[static_cast<int64_t>(max(j - 1, 0)) * 8];
+        np.xp = rv.rec[static_cast<int64_t>(min(j + 2, rv.ng - 1)) * 8];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { np.y0[k] = a[1 + k]; np.y1[k] = b[1 + k]; }
+}
+
+// Interpolate the present components from a NodePair.  `present` bit k = 0 means
+// the component is identically zero (F[k] = +0.0 without touching the data).
+template <int FORMULA>
+__device__ __forceinline__ bool interp_nodes(const NodePair& np, double x, double dr, int ng, unsigned present,
+                                             double (&F)[6], Guard& gd) {
+    const double x0 = np.x0, x1 = np.x1;
     bool ok = (x0 < x) && (x < x1);                 // strictly inside cell j (false for NaN)
     if (FORMULA == TP_INTERP_B) {
         // numpy.interp: slope = (y1-y0)/(x1-x0); out = slope*(x-x0) + y0
@@ -49,11 +118,7 @@ __device__ __forceinline__ bool gather6_fast(const GridView& g, double x, double
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             F[k] = 0.0;
-            if (g.comp[k] != nullptr) {
-                const double* y = g.comp[k] + static_cast<int64_t>(j) * g.stride[k];
-                const double y0 = y[0], y1 = y[g.stride[k]];
-                F[k] = quot<true>(y1 - y0, rdx, gd) * dx0 + y0;
-            }
+            if (present & (1u << k)) F[k] = quot<true>(np.y1[k] - np.y0[k], rdx, gd) * dx0 + np.y0[k];
         }
     } else if (FORMULA == TP_INTERP_C) {
         // ((x-x_lo)/(x_hi-x_lo))*y_hi + ((x_hi-x)/(x_hi-x_lo))*y_lo
@@ -63,30 +128,43 @@ __device__ __forceinline__ bool gather6_fast(const GridView& g, double x, double
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             F[k] = 0.0;
-            if (g.comp[k] != nullptr) {
-                const double* y = g.comp[k] + static_cast<int64_t>(j) * g.stride[k];
-                F[k] = w_hi * y[g.stride[k]] + w_lo * y[0];
-            }
+            if (present & (1u << k)) F[k] = w_hi * np.y1[k] + w_lo * np.y0[k];
         }
     } else {
         // create_interpolator: the window (x-dr, x+dr) must hold exactly nodes j, j+1
-        const double lo_edge = x - g.dr, hi_edge = x + g.dr;
-        const double xm = g.r[max(j - 1, 0)], xp = g.r[min(j + 2, g.ng - 1)];
-        ok = ok && (lo_edge < x0) && (x1 < hi_edge) && (j == 0 || !(lo_edge < xm)) &&
-             (j == last || !(xp < hi_edge));
+        const double lo_edge = x - dr, hi_edge = x + dr;
+        ok = ok && (lo_edge < x0) && (x1 < hi_edge) && (np.j == 0 || !(lo_edge < np.xm)) &&
+             (np.j == ng - 2 || !(np.xp < hi_edge));
         const Recip<true> rdx = make_recip<true>(x1 - x0, gd);
         const double dx0 = x - x0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             F[k] = 0.0;
-            if (g.comp[k] != nullptr) {
-                const double* y = g.comp[k] + static_cast<int64_t>(j) * g.stride[k];
-                const double y0 = y[0], y1 = y[g.stride[k]];
-                F[k] = y0 + quot<true>(dx0 * (y1 - y0), rdx, gd);
-            }
+            if (present & (1u << k)) F[k] = np.y0[k] + quot<true>(dx0 * (np.y1[k] - np.y0[k]), rdx, gd);
         }
     }
     return ok;
+}
+
+__device__ __forceinline__ unsigned present_mask(const GridView& g) {
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m |= (g.comp[k] != nullptr) ? (1u << k) : 0u;
+    return m;
+}
+
+template <int FORMULA>
+__device__ __forceinline__ bool gather6_fast(const GridView& g, double x, double (&F)[6], Guard& gd) {
+    NodePair np;
+    fetch_nodes<FORMULA>(g, x, np);
+    return interp_nodes<FORMULA>(np, x, g.dr, g.ng, present_mask(g), F, gd);
+}
+
+template <int FORMULA>
+__device__ __forceinline__ bool gather6_fast_records(const RecView& rv, double x, double (&F)[6], Guard& gd) {
+    NodePair np;
+    fetch_records<FORMULA>(rv, x, np);
+    return interp_nodes<FORMULA>(np, x, rv.dr, rv.ng, rv.present, F, gd);
 }
 
 // ---------------------------------------------------------------------------

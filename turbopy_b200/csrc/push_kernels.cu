@@ -75,6 +75,7 @@ struct GatherArgs {
     uint32_t r_smem_off;
     uint32_t comp_smem_off[6];
     unsigned long long* status;
+    const double* records;      // packed 64-byte node records (gather mode 2), else nullptr
 };
 
 // ---------------------------------------------------------------------------
@@ -310,6 +311,42 @@ __device__ __forceinline__ bool gather_step_fast(const GatherArgs& a, const Grid
     E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
     boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
     return ok && guard_ok(gd) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+}
+
+// The same with the two nodes fetched from packed records (grids that live in L2).
+template <int FORMULA>
+__device__ __forceinline__ bool gather_step_fast_records(const GatherArgs& a, const RecView& rv, Vec3& x, Vec3& p) {
+    double F[6];
+    Guard gd;
+    bool ok = gather6_fast_records<FORMULA>(rv, axis_of(x, a.axis), F, gd);
+    Vec3 E, B;
+    E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
+    boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
+    return ok && guard_ok(gd) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+}
+
+__device__ __forceinline__ RecView make_rec_view(const GatherArgs& a) {
+    RecView rv;
+    rv.rec = a.records; rv.ng = a.ng; rv.r_first = a.r_first; rv.inv_dr = a.inv_dr; rv.dr = a.dr;
+    rv.present = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rv.present |= a.comp[k] ? (1u << k) : 0u;
+    return rv;
+}
+
+// record j = {r[j], Ex[j], Ey[j], Ez[j], Bx[j], By[j], Bz[j], 0}; absent components are stored as +0.0
+__global__ void __launch_bounds__(256) pack_nodes_kernel(const __grid_constant__ GatherArgs a, double* __restrict__ rec) {
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < a.ng; j += gstride) {
+        double v[8];
+        v[0] = a.r[j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[1 + k] = a.comp[k] ? a.comp[k][j * a.stride[k]] : 0.0;
+        v[7] = 0.0;
+        double* dst = rec + j * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st2(dst + 2 * q, make_double2(v[2 * q], v[2 * q + 1]));
+    }
 }
 
 // Recovery path: reload the particle (nothing has been stored yet), complete
@@ -609,8 +646,12 @@ __device__ __noinline__ void gather_step_exact_slot(const GatherArgs& a, unsigne
     slot_write(xs, ps, pitch, x, p);
 }
 
-template <int FORMULA, bool STAGED, bool AOS>
+// GMODE: 0 = field arrays read from global memory / L2, 1 = arrays staged in
+// shared memory by the TMA, 2 = packed node records in L2 (fast path only; the
+// recovery path always reads the original arrays).
+template <int FORMULA, int GMODE, bool AOS>
 __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const __grid_constant__ TmaArgs ta) {
+    constexpr bool STAGED = GMODE == 1;
     extern __shared__ __align__(128) unsigned char smem[];
     const GatherArgs& a = ta.g;
     ring_init(ta.ring, smem);
@@ -618,8 +659,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const _
     ring_prologue<AOS>(a.p, ta.ring, smem);
     const GridView g = make_view<STAGED>(a, smem);
     if (STAGED) stage_wait(smem);
+    const RecView rv = make_rec_view(a);
     tma_ring<AOS>(
-        a.p, ta.ring, smem, [&](Vec3& x, Vec3& p) { return gather_step_fast<FORMULA>(a, g, x, p); },
+        a.p, ta.ring, smem,
+        [&](Vec3& x, Vec3& p) {
+            return GMODE == 2 ? gather_step_fast_records<FORMULA>(a, rv, x, p) : gather_step_fast<FORMULA>(a, g, x, p);
+        },
         [&](int64_t i, double* xs, double* ps, int pitch) {
             gather_step_exact_slot<FORMULA, STAGED>(a, smem, i, xs, ps, pitch);
         });
@@ -862,9 +907,9 @@ static int launch_gather_push_f(const GatherArgs& a, int formula, size_t smem, b
 }
 
 // TMA-pipelined variant: SoA or AoS, 16-byte aligned arrays, at least one full tile per SM.
-template <int FORMULA, bool STAGED, bool AOS>
+template <int FORMULA, int GMODE, bool AOS>
 static int launch_gather_push_tma(const TmaArgs& ta, size_t smem, int blocks, cudaStream_t s) {
-    auto kern = gather_push_tma_kernel<FORMULA, STAGED, AOS>;
+    auto kern = gather_push_tma_kernel<FORMULA, GMODE, AOS>;
     int rc = set_smem(kern, smem);
     if (rc) return rc;
     kern<<<blocks, kTmaThreads, smem, s>>>(ta);
@@ -873,11 +918,52 @@ static int launch_gather_push_tma(const TmaArgs& ta, size_t smem, int blocks, cu
 }
 
 template <int FORMULA>
-static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, bool staged, bool aos, cudaStream_t s) {
-    if (staged) return aos ? launch_gather_push_tma<FORMULA, true, true>(ta, smem, blocks, s)
-                           : launch_gather_push_tma<FORMULA, true, false>(ta, smem, blocks, s);
-    return aos ? launch_gather_push_tma<FORMULA, false, true>(ta, smem, blocks, s)
-               : launch_gather_push_tma<FORMULA, false, false>(ta, smem, blocks, s);
+static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, int gmode, bool aos, cudaStream_t s) {
+    switch (gmode) {
+        case 1: return aos ? launch_gather_push_tma<FORMULA, 1, true>(ta, smem, blocks, s)
+                           : launch_gather_push_tma<FORMULA, 1, false>(ta, smem, blocks, s);
+        case 2: return aos ? launch_gather_push_tma<FORMULA, 2, true>(ta, smem, blocks, s)
+                           : launch_gather_push_tma<FORMULA, 2, false>(ta, smem, blocks, s);
+        default: return aos ? launch_gather_push_tma<FORMULA, 0, true>(ta, smem, blocks, s)
+                            : launch_gather_push_tma<FORMULA, 0, false>(ta, smem, blocks, s);
+    }
+}
+
+// Scratch for the packed node records, one buffer per stream (calls on one
+// stream are ordered, so the buffer is free again when the next call runs).
+// Allocation is synchronous: a call that would have to (re)allocate while its
+// stream is being captured into a graph fails with TP_E_GRAPH -- run one eager
+// call first.
+static int records_scratch(int64_t ng, cudaStream_t s, double** out) {
+    struct Slot { cudaStream_t stream; double* buf; int64_t cap; int device; };
+    static Slot slots[16];
+    static int used = 0;
+    int dev = 0;
+    TP_CUDA_TRY(cudaGetDevice(&dev));
+    Slot* hit = nullptr;
+    for (int i = 0; i < used; ++i)
+        if (slots[i].stream == s && slots[i].device == dev) hit = &slots[i];
+    if (hit && hit->cap >= ng) { *out = hit->buf; return TP_OK; }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return TP_E_GRAPH;
+    if (!hit) {
+        if (used == 16) { used = 0; }                       // recycle (buffers of dead streams are leaked, bounded)
+        hit = &slots[used++];
+        hit->stream = s; hit->buf = nullptr; hit->cap = 0; hit->device = dev;
+    }
+    if (hit->buf) { TP_CUDA_TRY(cudaStreamSynchronize(s)); cudaFree(hit->buf); hit->buf = nullptr; hit->cap = 0; }
+    TP_CUDA_TRY(cudaMalloc(&hit->buf, static_cast<size_t>(ng) * 64));
+    hit->cap = ng;
+    *out = hit->buf;
+    return TP_OK;
+}
+
+static bool records_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("TURBOPY_B200_RECORDS");      // tuning / A-B switch, default on
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 static bool tma_enabled() {
@@ -913,10 +999,23 @@ static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_sme
     size_t smem = 0; int blocks = 0;
     if (!plan_ring(a.p.n, staged ? grid_smem : kSmemHeader, ta.ring, smem, blocks)) return TP_OK;
     int rc;
+    int gmode = staged ? 1 : 0;
+    if (!staged && records_enabled()) {
+        // the grid lives in L2: pack {r, E, B} into 64-byte node records first (ng * 64 B, a few us)
+        double* rec = nullptr;
+        if ((rc = records_scratch(a.ng, s, &rec))) return rc;
+        const DeviceProps& d = device_props();
+        const int pblocks = static_cast<int>(std::min<int64_t>((a.ng + 255) / 256, static_cast<int64_t>(d.sm_count) * 8));
+        pack_nodes_kernel<<<pblocks, 256, 0, s>>>(a, rec);
+        count_launch();
+        if ((rc = static_cast<int>(cudaGetLastError()))) return rc;
+        ta.g.records = rec;
+        gmode = 2;
+    }
     switch (formula) {
-        case TP_INTERP_A: rc = launch_gather_push_tma_v<TP_INTERP_A>(ta, smem, blocks, staged, aos, s); break;
-        case TP_INTERP_B: rc = launch_gather_push_tma_v<TP_INTERP_B>(ta, smem, blocks, staged, aos, s); break;
-        case TP_INTERP_C: rc = launch_gather_push_tma_v<TP_INTERP_C>(ta, smem, blocks, staged, aos, s); break;
+        case TP_INTERP_A: rc = launch_gather_push_tma_v<TP_INTERP_A>(ta, smem, blocks, gmode, aos, s); break;
+        case TP_INTERP_B: rc = launch_gather_push_tma_v<TP_INTERP_B>(ta, smem, blocks, gmode, aos, s); break;
+        case TP_INTERP_C: rc = launch_gather_push_tma_v<TP_INTERP_C>(ta, smem, blocks, gmode, aos, s); break;
         default: return TP_E_MODE;
     }
     launched = (rc == TP_OK);
