@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace tp {
@@ -21,10 +22,18 @@ constexpr int kBufs = 3;
 constexpr int64_t kChunk = 4ll << 20;          // most particles per chunk (192 MB of state)
 constexpr int64_t kMinChunk = 256ll << 10;
 
-// Chunk length: about n/8 so that copies and kernels of different chunks
-// overlap, within [256 Ki, 4 Mi] particles, even (keeps SoA blocks 16-B aligned).
+// Chunk length: about n/16 (tunable: TURBOPY_B200_HOST_CHUNKS; 8/16/32/64 parts measured
+// 0.91/0.93/0.90/0.84 G pushes/s end to end at 16 Mi particles) so that copies and
+// kernels of different chunks overlap and the un-overlapped fill / drain of the
+// pipeline (first H2D, last D2H) stays a small part of the call; within
+// [256 Ki, 4 Mi] particles, even (keeps SoA blocks 16-B aligned).
 inline int64_t chunk_for(int64_t n) {
-    int64_t c = (n + 7) / 8;
+    static const int parts = [] {
+        const char* e = std::getenv("TURBOPY_B200_HOST_CHUNKS");
+        const int v = e ? std::atoi(e) : 16;
+        return v >= 1 ? v : 16;
+    }();
+    int64_t c = (n + parts - 1) / parts;
     c = std::max(kMinChunk, std::min(kChunk, c));
     c = std::min(c, std::max<int64_t>(n, 2));
     return ((c + 1) / 2) * 2;
