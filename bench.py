@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--ng", type=int, default=4097, help="grid nodes")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-particles", type=int, default=1 << 20)
-    ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay the timed steps as one CUDA graph")

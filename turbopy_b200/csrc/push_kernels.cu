@@ -947,8 +947,13 @@ static int records_scratch(int64_t ng, cudaStream_t s, double** out) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return TP_E_GRAPH;
     if (!hit) {
-        if (used == 16) { used = 0; }                       // recycle (buffers of dead streams are leaked, bounded)
-        hit = &slots[used++];
+        static int next = 0;
+        if (used < 16) hit = &slots[used++];
+        else {                                              // recycle the oldest slot (its stream is most likely gone)
+            hit = &slots[next];
+            next = (next + 1) % 16;
+            if (hit->buf) { cudaDeviceSynchronize(); cudaFree(hit->buf); }
+        }
         hit->stream = s; hit->buf = nullptr; hit->cap = 0; hit->device = dev;
     }
     if (hit->buf) { TP_CUDA_TRY(cudaStreamSynchronize(s)); cudaFree(hit->buf); hit->buf = nullptr; hit->cap = 0; }
