@@ -149,8 +149,8 @@ def main():
             add(f"fd {name}() @ f", n, bpp, timed(lambda: D @ y, it),
                 "stored diagonals" if name == "radial_curl" else "constant diagonals in kernel args")
         ps = tp.PoissonSolver1DRadial(ow, {"type": "PoissonSolver1DRadial"})
-        add("PoissonSolver1DRadial.solve (7 launches)", n, 80, timed(lambda: ps.solve(y), it),
-            "80 B/pt over the reduce-then-scan passes; 16 B/pt algorithmic")
+        add("PoissonSolver1DRadial.solve (5 launches)", n, 56, timed(lambda: ps.solve(y), it),
+            "56 B/pt over the reduce-then-scan passes; 16 B/pt algorithmic")
         del y, fdt, D, ow, ps
         tp.GridOnDevice._cache.clear()
         torch.cuda.empty_cache()

@@ -1,15 +1,23 @@
 // PoissonSolver1DRadial.solve (turbopy/computetools.py:35-59) as
-// two fp64 prefix scans.  Line-by-line spec: oracle/poisson.py.
+// two chained fp64 prefix scans.  Line-by-line spec: oracle/poisson.py.
 //
 //   a[i]  = (r[i]*s[i])*dr                      I1 = cumsum(a)
 //   g[i]  = (I1[i]*dr)/r[i],  g[0] := i0 = 2*g[1] - g[2],  g -= i0
 //   I2    = cumsum(g),        out = I2 - I2[n-1]
 //
-// Each scan is reduce-then-scan over 2048-element tiles (per-tile sums, one-CTA
-// scan of the tile sums, per-tile scan with the tile's offset): no CTA ever
-// waits on another one.  numpy's cumsum is strictly sequential, so results
-// agree to rounding (tolerance in tests/test_gpu_poisson.py), not bit for bit.
-// Traffic: 80 B/point over the five passes (r,s | r,s,I1 | I1,r,I2 | I2,out).
+// Reduce-then-scan over 2048-element tiles, no CTA ever waits on another one:
+//   K1  per-tile sums of a                                   (reads r, s)
+//   K2  one CTA: exclusive scan of the tile sums -> off1[t]; i0 from the first three elements
+//   K3  per tile: a -> I1 = off1 + local scan -> g -> per-tile sums of g   (reads r, s; nothing stored)
+//   K4  one CTA: exclusive scan -> off2[t]; total = off2[T-1] + G[T-1]
+//   K5  per tile: a -> I1 -> g -> I2 = off2 + local scan -> out = I2 - total   (reads r, s; writes out)
+// I1 is recomputed instead of stored and the final shift is folded into K5:
+// 56 B/point of traffic (16 algorithmic), all of it coalesced -- a warp owns
+// 8 rows of 32 consecutive elements and scans them with shuffles.  The tile sum
+// of K3 is the last value of the SAME local scan K5 runs, so out[n-1] is
+// exactly 0 like the reference's I2 - I2[-1].
+// numpy's cumsum is strictly sequential; a parallel scan associates differently,
+// so results agree to rounding (tolerance in tests/test_gpu_poisson.py).
 #include "common.cuh"
 
 #include <algorithm>
@@ -17,131 +25,168 @@
 namespace tp {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr int kScanRows = 8;                               // rows of 32 elements per warp
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanTile = kScanThreads * kScanRows;        // 2048
 
 struct PoissonArgs {
-    const double* r; const double* s; double* I1; double* out;
-    double* tile_sums;          // ntiles doubles (reused by both scans)
-    double* scalars;            // [0] = i0, [1] = total of the second scan
+    const double* r; const double* s; double* out;
+    double* tile1;              // ntiles doubles: sums, then exclusive offsets of scan 1
+    double* tile2;              // the same for scan 2
+    double* scalars;            // [0] = i0, [1] = total of scan 2 (= I2[n-1])
     int64_t n; int64_t ntiles; double dr;
 };
 
-__device__ __forceinline__ double block_exclusive_scan(double v, double& total) {
-    __shared__ double warp_tot[kScanThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double inc = v;
+__device__ __forceinline__ double warp_inclusive(double v) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
     }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    double wbase = 0.0, tot = 0.0;
+    return v;
+}
+
+// Inclusive scan of the tile's 2048 values held as v[k] = element (warp*256 + k*32 + lane).
+// Returns the tile total; v[] becomes the inclusive prefix inside the tile.
+__device__ __forceinline__ double tile_scan(double (&v)[kScanRows]) {
+    __shared__ double warp_tot[kScanWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double carry = 0.0;
 #pragma unroll
-    for (int w = 0; w < kScanThreads / 32; ++w) {
+    for (int k = 0; k < kScanRows; ++k) {
+        const double inc = warp_inclusive(v[k]);
+        v[k] = carry + inc;
+        carry = carry + __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) warp_tot[warp] = carry;
+    __syncthreads();
+    double wbase = 0.0;
+#pragma unroll
+    for (int w = 0; w < kScanWarps - 1; ++w)
         if (w < warp) wbase += warp_tot[w];
-        tot += warp_tot[w];
-    }
-    __syncthreads();
-    total = tot;
-    return wbase + (inc - v);
-}
-
-// element of the first scan's input
-__device__ __forceinline__ double a_of(const PoissonArgs& p, int64_t i) { return (p.r[i] * p.s[i]) * p.dr; }
-
-// element of the second scan's input (needs I1 and i0)
-__device__ __forceinline__ double g_of(const PoissonArgs& p, int64_t i, double i0) {
-    if (i == 0) return i0 - i0;
-    return (p.I1[i] * p.dr) / p.r[i] - i0;
-}
-
-template <int PASS>      // 1: a[], 2: g[]
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const __grid_constant__ PoissonArgs p) {
-    const double i0 = PASS == 2 ? p.scalars[0] : 0.0;
-    for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const int64_t base = t * kScanTile + static_cast<int64_t>(threadIdx.x) * kScanItems;
-        double acc = 0.0;
+    double total = 0.0;
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            const int64_t i = base + k;
-            if (i < p.n) acc += PASS == 1 ? a_of(p, i) : g_of(p, i, i0);
-        }
-        double total;
-        block_exclusive_scan(acc, total);
-        if (threadIdx.x == 0) p.tile_sums[t] = total;
-        __syncthreads();
+    for (int w = 0; w < kScanWarps - 1; ++w) total += warp_tot[w];
+    total = total + warp_tot[kScanWarps - 1];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kScanRows; ++k) v[k] = wbase + v[k];
+    return total;
+}
+
+__device__ __forceinline__ int64_t elem_index(int64_t tile, int k) {
+    return tile * kScanTile + (threadIdx.x >> 5) * (32 * kScanRows) + k * 32 + (threadIdx.x & 31);
+}
+
+__device__ __forceinline__ double a_at(const PoissonArgs& p, int64_t i) { return (p.r[i] * p.s[i]) * p.dr; }
+
+// a[] of the tile (0 beyond n)
+__device__ __forceinline__ void load_a(const PoissonArgs& p, int64_t t, double (&v)[kScanRows], double (&rr)[kScanRows]) {
+#pragma unroll
+    for (int k = 0; k < kScanRows; ++k) {
+        const int64_t i = elem_index(t, k);
+        rr[k] = i < p.n ? p.r[i] : 1.0;
+        v[k] = i < p.n ? (rr[k] * p.s[i]) * p.dr : 0.0;
     }
 }
 
-// one CTA: exclusive scan of the tile sums in place; PASS 1 also forms i0 from
-// the first three elements in numpy's sequential order.
-template <int PASS>
-__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(const __grid_constant__ PoissonArgs p) {
+// v: inclusive local scan of a (tile_scan output) -> g of the tile (0 beyond n)
+__device__ __forceinline__ void to_g(const PoissonArgs& p, int64_t t, double off1, double i0, const double (&rr)[kScanRows],
+                                     double (&v)[kScanRows]) {
+#pragma unroll
+    for (int k = 0; k < kScanRows; ++k) {
+        const int64_t i = elem_index(t, k);
+        const double I1 = off1 + v[k];
+        double g = ((I1 * p.dr) / rr[k]) - i0;
+        if (i == 0) g = i0 - i0;                       // g[0] := i0, then g - i0
+        v[k] = i < p.n ? g : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) poisson_sums1_kernel(const __grid_constant__ PoissonArgs p) {
+    for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        double v[kScanRows], rr[kScanRows];
+        load_a(p, t, v, rr);
+        const double total = tile_scan(v);
+        if (threadIdx.x == 0) p.tile1[t] = total;
+    }
+}
+
+// one CTA: tile sums -> exclusive offsets, in place; returns the grand total through *total_out
+__device__ __forceinline__ void scan_tile_sums(double* sums, int64_t ntiles, double* total_out) {
     __shared__ double carry_s;
     if (threadIdx.x == 0) carry_s = 0.0;
     __syncthreads();
-    for (int64_t base = 0; base < p.ntiles; base += kScanThreads) {
-        const int64_t t = base + threadIdx.x;
-        const double v = t < p.ntiles ? p.tile_sums[t] : 0.0;
-        double total;
-        const double ex = block_exclusive_scan(v, total);
+    for (int64_t base = 0; base < ntiles; base += kScanTile) {
+        double v[kScanRows], in[kScanRows];
+#pragma unroll
+        for (int k = 0; k < kScanRows; ++k) {
+            const int64_t i = base + (threadIdx.x >> 5) * (32 * kScanRows) + k * 32 + (threadIdx.x & 31);
+            in[k] = i < ntiles ? sums[i] : 0.0;
+            v[k] = in[k];
+        }
+        const double total = tile_scan(v);
         const double carry = carry_s;
-        if (t < p.ntiles) p.tile_sums[t] = carry + ex;
+#pragma unroll
+        for (int k = 0; k < kScanRows; ++k) {
+            const int64_t i = base + (threadIdx.x >> 5) * (32 * kScanRows) + k * 32 + (threadIdx.x & 31);
+            if (i < ntiles) sums[i] = carry + (v[k] - in[k]);            // exclusive
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + total;
         __syncthreads();
     }
+    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+
+__global__ void __launch_bounds__(kScanThreads) poisson_offsets1_kernel(const __grid_constant__ PoissonArgs p) {
+    scan_tile_sums(p.tile1, p.ntiles, nullptr);
     if (threadIdx.x == 0) {
-        if (PASS == 1) {
-            // i0 = 2*g[1] - g[2] with I1[1] = a0 + a1, I1[2] = I1[1] + a2  (computetools.py:50-53)
-            double i0 = 0.0;
-            if (p.n >= 3) {
-                const double I1_1 = a_of(p, 0) + a_of(p, 1);
-                const double I1_2 = I1_1 + a_of(p, 2);
-                i0 = 2.0 * ((I1_1 * p.dr) / p.r[1]) - (I1_2 * p.dr) / p.r[2];
-            }
-            p.scalars[0] = i0;
-        } else {
-            p.scalars[1] = carry_s;                 // I2[n-1]
-        }
+        // i0 = 2*g[1] - g[2] with I1[1] = a0 + a1, I1[2] = I1[1] + a2 in numpy's sequential order (:50-53)
+        const double I1_1 = a_at(p, 0) + a_at(p, 1);
+        const double I1_2 = I1_1 + a_at(p, 2);
+        p.scalars[0] = 2.0 * ((I1_1 * p.dr) / p.r[1]) - (I1_2 * p.dr) / p.r[2];
     }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const __grid_constant__ PoissonArgs p) {
-    const double i0 = PASS == 2 ? p.scalars[0] : 0.0;
+__global__ void __launch_bounds__(kScanThreads) poisson_sums2_kernel(const __grid_constant__ PoissonArgs p) {
+    const double i0 = p.scalars[0];
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const int64_t base = t * kScanTile + static_cast<int64_t>(threadIdx.x) * kScanItems;
-        double v[kScanItems];
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            const int64_t i = base + k;
-            v[k] = i < p.n ? (PASS == 1 ? a_of(p, i) : g_of(p, i, i0)) : 0.0;
-            acc += v[k];
-        }
-        double total;
-        double run = p.tile_sums[t] + block_exclusive_scan(acc, total);
-        double* dst = PASS == 1 ? p.I1 : p.out;
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            const int64_t i = base + k;
-            run += v[k];
-            if (i < p.n) dst[i] = run;
-            if (PASS == 2 && i == p.n - 1) p.scalars[1] = run;     // I2[n-1] as stored: out[n-1] becomes exactly 0
-        }
-        __syncthreads();
+        double v[kScanRows], rr[kScanRows];
+        load_a(p, t, v, rr);
+        tile_scan(v);
+        to_g(p, t, p.tile1[t], i0, rr, v);
+        const double total = tile_scan(v);               // the same scan K5 runs: its last value IS the tile sum
+        if (threadIdx.x == 0) p.tile2[t] = total;
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) poisson_shift_kernel(double* out, const double* scalars, int64_t n) {
-    const double last = scalars[1];
-    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kScanThreads;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kScanThreads + threadIdx.x; i < n; i += gstride)
-        out[i] = out[i] - last;
+__global__ void __launch_bounds__(kScanThreads) poisson_offsets2_kernel(const __grid_constant__ PoissonArgs p) {
+    __shared__ double last_sum;
+    if (threadIdx.x == 0) last_sum = p.tile2[p.ntiles - 1];
+    __syncthreads();
+    scan_tile_sums(p.tile2, p.ntiles, nullptr);
+    __syncthreads();
+    // I2[n-1] exactly as K5 forms it for the last element: off2[T-1] + (local inclusive value = tile sum)
+    if (threadIdx.x == 0) p.scalars[1] = p.tile2[p.ntiles - 1] + last_sum;
+}
+
+__global__ void __launch_bounds__(kScanThreads) poisson_apply_kernel(const __grid_constant__ PoissonArgs p) {
+    const double i0 = p.scalars[0], last = p.scalars[1];
+    for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        double v[kScanRows], rr[kScanRows];
+        load_a(p, t, v, rr);
+        tile_scan(v);
+        to_g(p, t, p.tile1[t], i0, rr, v);
+        tile_scan(v);
+        const double off2 = p.tile2[t];
+#pragma unroll
+        for (int k = 0; k < kScanRows; ++k) {
+            const int64_t i = elem_index(t, k);
+            if (i < p.n) p.out[i] = (off2 + v[k]) - last;
+        }
+    }
 }
 
 }  // namespace tp
@@ -149,7 +194,7 @@ __global__ void __launch_bounds__(kScanThreads) poisson_shift_kernel(double* out
 using namespace tp;
 
 extern "C" int64_t tp_poisson_scratch_doubles(int64_t n) {
-    return n + (n + kScanTile - 1) / kScanTile + 8;      // I1 + tile sums + scalars
+    return 2 * ((n + kScanTile - 1) / kScanTile) + 8;      // two arrays of tile sums + scalars
 }
 
 extern "C" int tp_poisson_radial_solve_f64(const double* sources, const double* r, double mean_dr, double* out,
@@ -161,17 +206,15 @@ extern "C" int tp_poisson_radial_solve_f64(const double* sources, const double* 
     PoissonArgs p;
     p.r = r; p.s = sources; p.out = out; p.n = n; p.dr = mean_dr;
     p.ntiles = (n + kScanTile - 1) / kScanTile;
-    p.I1 = scratch;
-    p.tile_sums = scratch + n;
-    p.scalars = scratch + n + p.ntiles;
+    p.tile1 = scratch;
+    p.tile2 = scratch + p.ntiles;
+    p.scalars = scratch + 2 * p.ntiles;
     const int blocks = static_cast<int>(std::min<int64_t>(p.ntiles, static_cast<int64_t>(d.sm_count) * 8));
-    scan_tile_sums_kernel<1><<<blocks, kScanThreads, 0, s>>>(p);
-    scan_tile_offsets_kernel<1><<<1, kScanThreads, 0, s>>>(p);
-    scan_apply_kernel<1><<<blocks, kScanThreads, 0, s>>>(p);
-    scan_tile_sums_kernel<2><<<blocks, kScanThreads, 0, s>>>(p);
-    scan_tile_offsets_kernel<2><<<1, kScanThreads, 0, s>>>(p);
-    scan_apply_kernel<2><<<blocks, kScanThreads, 0, s>>>(p);
-    poisson_shift_kernel<<<blocks, kScanThreads, 0, s>>>(out, p.scalars, n);
-    count_launch(7);
+    poisson_sums1_kernel<<<blocks, kScanThreads, 0, s>>>(p);
+    poisson_offsets1_kernel<<<1, kScanThreads, 0, s>>>(p);
+    poisson_sums2_kernel<<<blocks, kScanThreads, 0, s>>>(p);
+    poisson_offsets2_kernel<<<1, kScanThreads, 0, s>>>(p);
+    poisson_apply_kernel<<<blocks, kScanThreads, 0, s>>>(p);
+    count_launch(5);
     return static_cast<int>(cudaGetLastError());
 }
