@@ -42,8 +42,38 @@ def _is_cuda(t):
     return isinstance(t, torch.Tensor) and t.is_cuda
 
 
+try:                                        # raw handle of torch's current stream, without building a Stream object
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:                      # pragma: no cover - older / newer torch
+    _raw_stream = None
+
+
+def _device_index(device):
+    return device.index if device.index is not None else torch.cuda.current_device()
+
+
 def _stream_ptr(device):
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(_device_index(device)))
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _on_device:
+    """``with torch.cuda.device(dev)`` that costs nothing when ``dev`` is already
+    current (one process per GPU: always)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if _device_index(device) == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def _require_f64(t, what):
@@ -79,12 +109,31 @@ def _ptr(t):
     return t.ctypes.data
 
 
+_struct_cache = {}
+
+
 def _particles_struct(position, momentum):
+    """tp_particles for the two (n,3) arrays.  A Simulation passes the same two
+    arrays every step, so the validated struct is cached on (pointers, shapes,
+    strides, dtypes)."""
+    if isinstance(position, torch.Tensor) and isinstance(momentum, torch.Tensor):
+        key = (position.data_ptr(), momentum.data_ptr(), position.shape, momentum.shape,
+               position.stride(), momentum.stride(), position.dtype, momentum.dtype)
+        hit = _struct_cache.get(key)
+        if hit is not None:
+            return hit
+    else:
+        key = None
     psn, psc = _n3_strides(position, "position")
     msn, msc = _n3_strides(momentum, "momentum")
     if position.shape[0] != momentum.shape[0]:
         raise ValueError("position and momentum must have the same number of particles")
-    return _lib.Particles(_ptr(position), psn, psc, _ptr(momentum), msn, msc, int(position.shape[0]))
+    out = _lib.Particles(_ptr(position), psn, psc, _ptr(momentum), msn, msc, int(position.shape[0]))
+    if key is not None:
+        if len(_struct_cache) > 64:
+            _struct_cache.clear()
+        _struct_cache[key] = out
+    return out
 
 
 def _push_consts(charge, mass, dt, c2):
@@ -99,6 +148,13 @@ class _FieldArg:
     def __init__(self, F, name, n, device):
         self.keep = None
         self.sn = self.sc = 0
+        if type(F) is np.ndarray and F.dtype == np.float64 and F.shape == (3,) and F.flags.c_contiguous:
+            # the common case (a module's E / B vector): the library reads the three
+            # host doubles at call time, no copy needed
+            self.mode = _lib.TP_FIELD_UNIFORM_HOST
+            self.keep = F
+            self.ptr = F.__array_interface__["data"][0]
+            return
         if _is_cuda(F):
             _require_f64(F, name)
             if F.ndim == 2 and F.shape == (n, 3) and n != 1:
@@ -279,7 +335,7 @@ class BorisPush(ComputeTool):
             dev = position.device
             e = _FieldArg(E, "E", p.n, dev)
             b = _FieldArg(B, "B", p.n, dev)
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 _lib.check(lib.tp_boris_push_f64(C.byref(p), C.byref(k),
                                                  C.c_void_p(e.ptr), e.mode, e.sn, e.sc,
                                                  C.c_void_p(b.ptr), b.mode, b.sn, b.sc, _stream_ptr(dev)))
@@ -333,7 +389,7 @@ class BorisPush(ComputeTool):
             status = self._status.get(dev)
             if status is None:
                 status = self._status[dev] = GatherStatus(dev)
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 _lib.check(lib.tp_gather_push_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
                                                   C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
             return None
