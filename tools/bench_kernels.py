@@ -133,6 +133,20 @@ def main():
     add("gather+push ng=1048577 comps=6, particles sorted by x", n16, 96, t, "grid in L2")
     del pos, mom
 
+    # ---- gather only: Interpolators.interpolate1D(x, y)(x_new), bounds check deferred (no sync per call)
+    for ng in (1025, 4097):
+        ow = owner_for(ng)
+        it_tool = tp.Interpolators(ow, {"type": "Interpolators"})
+        rr = torch.from_numpy(ow.grid.r).cuda()
+        Y = torch.stack([torch.cos((k + 1) * rr) for k in range(6)])
+        xq = 0.05 + 0.9 * torch.rand(n16, dtype=torch.float64, device="cuda")
+        for label, f, bpp in ((f"interpolate1D ng={ng}, 1-D y (numpy.interp rounding)", it_tool.interpolate1D(rr, Y[0].contiguous()), 16),
+                              (f"interpolate1D ng={ng}, (6,ng) y (scipy _call_linear rounding)", it_tool.interpolate1D(rr, Y), 56)):
+            f.deferred_check = True
+            add(label, n16, bpp, timed(lambda: f(xq), it))
+            f.check()
+        del xq
+
     # ---- kernel 2: FiniteDifference stencils
     for n in ((1 << 24) + 1, (1 << 28)):
         if args.quick and n > (1 << 25):

@@ -303,35 +303,89 @@ struct InterpArgs {
     int ncomp;
 };
 
+// The view of six consecutive components c0 .. c0+5 of the y block.
+__device__ __forceinline__ GridView interp_view(const InterpArgs& a, const GridView& g, int c0) {
+    GridView gv = g;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const bool on = c0 + c < a.ncomp;
+        gv.comp[c] = on ? g.comp[0] + static_cast<int64_t>(c0 + c) * a.g.stride[1] : nullptr;
+        gv.stride[c] = g.stride[0];
+    }
+    return gv;
+}
+
+// Recovery path of one point: complete semantics, IEEE divisions, writes its own
+// outputs.  It takes only the grid-constant block and the shared-memory base:
+// handing it the hot loop's view or result array by reference would force them
+// into local memory (that made the first version of this kernel 10x slower).
 template <int FORMULA, bool STAGED>
-__global__ void __launch_bounds__(kThreads, 2) interp_kernel(const __grid_constant__ InterpArgs a) {
+__device__ __noinline__ void interp_point_exact(const InterpArgs& a, unsigned char* smem, int64_t i, int c0) {
+    const GridView gv = interp_view(a, make_view<STAGED>(a.g, smem), c0);
+    const double x = a.xq[i * a.xq_stride];
+    double F[6];
+    const unsigned st = gather6_exact<FORMULA>(gv, x, F);
+    if (st != 0u && c0 == 0) flag_particle(a.g.status, i, st);
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int c = 0; c < 6; ++c)
+        if (c0 + c < a.ncomp) a.out[static_cast<int64_t>(c0 + c) * a.out_stride_c + i] = st ? nan : F[c];
+}
+
+// Four consecutive points per thread and iteration: two 128-bit loads of x, two
+// 128-bit stores per component (the kernel moves only 8 B in + 8 B out per
+// point and component, so it lives on bytes in flight).
+template <int FORMULA, bool STAGED, int NC>       // NC = components per pass: 1 (1-D y, the common case) or 6
+__global__ void __launch_bounds__(kThreads, NC == 1 ? 3 : 2) interp_kernel(const __grid_constant__ InterpArgs a, bool vec) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (STAGED) { stage_issue(a.g, smem); stage_wait(smem); }
     const GridView g = make_view<STAGED>(a.g, smem);
     const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * kThreads;
-    const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    for (int64_t i = gtid; i < a.n; i += gstride) {
-        const double x = a.xq[i * a.xq_stride];
-        for (int c0 = 0; c0 < a.ncomp; c0 += 6) {            // six components per pass
-            GridView gv = g;
+    const int64_t nquads = (a.n + 3) >> 2;
+    for (int c0 = 0; c0 < a.ncomp; c0 += NC) {               // NC components per pass
+        GridView gv = interp_view(a, g, c0);
+        if (NC == 1) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                const bool on = c0 + c < a.ncomp;
-                gv.comp[c] = on ? g.comp[0] + static_cast<int64_t>(c0 + c) * a.g.stride[1] : nullptr;
-                gv.stride[c] = g.stride[0];
+            for (int c = 1; c < 6; ++c) gv.comp[c] = nullptr;     // lets the compiler drop the unused lanes
+        }
+        for (int64_t qd = gtid; qd < nquads; qd += gstride) {
+            const int64_t i = qd * 4;
+            const bool full = vec && i + 4 <= a.n;
+            double x[4];
+            if (full) {
+                const double2 u = ld2(a.xq + i), v = ld2(a.xq + i + 2);
+                x[0] = u.x; x[1] = u.y; x[2] = v.x; x[3] = v.y;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) x[q] = i + q < a.n ? a.xq[(i + q) * a.xq_stride] : 0.0;
             }
-            double F[6];
-            Guard gd;
-            unsigned st = 0u;
-            bool ok = gather6_fast<FORMULA>(gv, x, F, gd) && guard_ok(gd);
+            double o[NC][4];
+            unsigned bad = 0;
 #pragma unroll
-            for (int c = 0; c < 6; ++c) ok = ok && (F[c] == F[c]);      // NaN -> numpy's fallbacks
-            if (!ok) st = gather6_exact<FORMULA>(gv, x, F);
-            if (st != 0u && c0 == 0) flag_particle(a.g.status, i, st);
+            for (int q = 0; q < 4; ++q) {
+                double F[6];
+                Guard gd;
+                bool ok = gather6_fast<FORMULA>(gv, x[q], F, gd) && guard_ok(gd);
 #pragma unroll
-            for (int c = 0; c < 6; ++c)
-                if (c0 + c < a.ncomp) a.out[static_cast<int64_t>(c0 + c) * a.out_stride_c + i] = st ? nan : F[c];
+                for (int c = 0; c < NC; ++c) { ok = ok && (F[c] == F[c]); o[c][q] = F[c]; }     // NaN -> numpy's fallbacks
+                if (!ok && i + q < a.n) bad |= 1u << q;
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                if (c0 + c >= a.ncomp) continue;
+                double* dst = a.out + static_cast<int64_t>(c0 + c) * a.out_stride_c + i;
+                if (full) {
+                    st2(dst, make_double2(o[c][0], o[c][1]));
+                    st2(dst + 2, make_double2(o[c][2], o[c][3]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (i + q < a.n) dst[q] = o[c][q];
+                }
+            }
+            if (__builtin_expect(bad != 0u, 0))              // recovery overwrites the point's outputs
+                for (int q = 0; q < 4; ++q)
+                    if (bad & (1u << q)) interp_point_exact<FORMULA, STAGED>(a, smem, i + q, c0);
         }
     }
 }
@@ -599,13 +653,22 @@ static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_sme
     return rc;
 }
 
+template <int FORMULA, bool STAGED, int NC>
+static int launch_interp_nc(const InterpArgs& a, size_t smem, cudaStream_t s);
+
 template <int FORMULA, bool STAGED>
 static int launch_interp(const InterpArgs& a, size_t smem, cudaStream_t s) {
-    auto kern = interp_kernel<FORMULA, STAGED>;
+    return a.ncomp == 1 ? launch_interp_nc<FORMULA, STAGED, 1>(a, smem, s) : launch_interp_nc<FORMULA, STAGED, 6>(a, smem, s);
+}
+
+template <int FORMULA, bool STAGED, int NC>
+static int launch_interp_nc(const InterpArgs& a, size_t smem, cudaStream_t s) {
+    auto kern = interp_kernel<FORMULA, STAGED, NC>;
     int rc = set_smem(kern, smem);
     if (rc) return rc;
-    const int blocks = grid_blocks(reinterpret_cast<const void*>(kern), smem, a.n);
-    kern<<<blocks, kThreads, smem, s>>>(a);
+    const int blocks = grid_blocks(reinterpret_cast<const void*>(kern), smem, (a.n + 3) / 4);
+    const bool vec = a.xq_stride == 1 && aligned16(a.xq) && aligned16(a.out) && a.out_stride_c % 2 == 0;
+    kern<<<blocks, kThreads, smem, s>>>(a, vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

@@ -454,6 +454,24 @@ class _Interp1D:
         self.formula = _lib.TP_INTERP_B if y.ndim == 1 else _lib.TP_INTERP_C
         self._status = GatherStatus(x.device)
 
+    #: interp1d raises its bounds error inside the call, which costs one device
+    #: sync per evaluation; set ``f.deferred_check = True`` to keep evaluations
+    #: asynchronous (out-of-range points come back as NaN) and call ``f.check()``
+    #: when convenient.
+    deferred_check = False
+
+    def check(self):
+        """Raise interp1d's bounds ValueError if any point evaluated since the
+        last check was outside ``[x[0], x[-1]]``."""
+        count, first, bits = self._status.read()
+        if count:
+            self._status.reset()
+            bad = float(self._last_xq[first]) if getattr(self, "_last_xq", None) is not None else float("nan")
+            side = "below" if bits & _lib.TP_ST_BELOW and bad < self.r_first else "above"
+            bound = self.r_first if side == "below" else self.r_last
+            raise ValueError(f"A value ({bad}) in x_new is {side} the interpolation range's "
+                             f"{'minimum' if side == 'below' else 'maximum'} value ({bound}).")
+
     def __call__(self, x_new):
         dev = self.x.device
         as_numpy = not isinstance(x_new, torch.Tensor)
@@ -473,14 +491,9 @@ class _Interp1D:
                 C.c_void_p(xq.data_ptr()), 1, n,
                 C.c_void_p(out.data_ptr()), n, self.formula,
                 C.c_void_p(self._status.words.data_ptr()), _stream_ptr(dev)))
-        count, first, bits = self._status.read()
-        if count:
-            self._status.reset()
-            bad = float(xq[first])
-            side = "below" if bits & _lib.TP_ST_BELOW and bad < self.r_first else "above"
-            bound = self.r_first if side == "below" else self.r_last
-            raise ValueError(f"A value ({bad}) in x_new is {side} the interpolation range's "
-                             f"{'minimum' if side == 'below' else 'maximum'} value ({bound}).")
+        self._last_xq = xq
+        if not self.deferred_check:
+            self.check()
         out = out.reshape(self.y.shape[:-1] + shape)
         return out.cpu().numpy() if (as_numpy and self._numpy) else out
 
