@@ -45,7 +45,7 @@ UNIT = "pushes/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--particles", type=int, default=16 << 20, help="particles per GPU")
@@ -92,45 +92,96 @@ class Owner:
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled
+    every ~2 ms from a thread (the timed region lasts tens of milliseconds, too
+    short for nvidia-smi's loop mode, which is only the fallback)."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.samples = []          # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        self._smi = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index -> physical index when CUDA_VISIBLE_DEVICES remaps
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._nvml = None
+            self._start_smi()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+    def _poll(self):
+        nv = self._nvml
+        while not self._stop.is_set():
             try:
-                sm.append(float(row[1])); smax = float(row[2])
+                mhz = nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+                self.samples.append((float(mhz), int(bits)))
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def _start_smi(self):
+        query = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self._smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={query}", "--format=csv,noheader,nounits",
+                                          "-lms", "20", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read_smi, daemon=True).start()
+        except OSError:
+            self._smi = None
+
+    def _read_smi(self):
+        names = list(self.REASONS)
+        for line in self._smi.stdout:
+            cols = [c.strip() for c in line.split(",")]
+            try:
+                mhz, self.max_mhz = float(cols[0]), float(cols[1])
             except (ValueError, IndexError):
                 continue
-            for name, val in zip(names, row[4:8]):
+            bits = 0
+            for name, val in zip(names, cols[2:6]):
                 if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    bits |= self.REASONS[name]
+            self.samples.append((mhz, bits))
+
+    def mark(self):
+        """Index of the next sample: call at the start / end of the timed region."""
+        return len(self.samples)
+
+    def stop(self, first=0, last=None):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if self._smi is not None:
+            time.sleep(0.05)
+            self._smi.terminate()
+        window = self.samples[first:last] or self.samples
+        if not window:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no clock samples"], "samples": 0}
+        bits = 0
+        for _, b in window:
+            bits |= b
+        return {"sm_mhz": float(np.median([m for m, _ in window])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(k for k, v in self.REASONS.items() if bits & v), "samples": len(window),
+                "source": "nvml, 2 ms period, timed region only" if self._nvml else "nvidia-smi -lms 20"}
 
 
 def measured_peak():
@@ -270,10 +321,11 @@ def run_b200(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(0.05)
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    s_first = sampler.mark()
     ev0.record()
     if graph is not None:
         graph.replay()
@@ -282,9 +334,10 @@ def run_b200(args):
             step(W + s)
     ev1.record()
     barrier()
+    s_last = sampler.mark()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(s_first, s_last)
     pusher.check_status()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
