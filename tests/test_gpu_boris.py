@@ -229,6 +229,44 @@ def test_push_tma_ring_vs_oracle(tp, layout):
     assert_bits_equal(mom.cpu().numpy(), rm, "momentum")
 
 
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("flayout", ["soa", "aos", "mixed", "strided"])
+def test_push_per_particle_fields_tma_ring_vs_oracle(tp, layout, flayout):
+    """push() with (n,3) E and B through the field ring (480-particle tiles, >= one per SM), every
+    particle / field layout pair, a ragged tail, recovery-path particles; "mixed" and "strided"
+    field layouts are not bulk-copyable and must take the register path with the same bits."""
+    n = 148 * 480 * 3 + 377
+    dt = 1e-12
+    tool = pusher(tp, dt)
+    pos0, mom0 = thermal_ensemble(n, seed=123)
+    mom0[::777] = 0.0
+    mom0[5::4000] = 1e-200
+    rng = np.random.default_rng(321)
+    E = rng.normal(0, 1e6, (n, 3)); B = rng.normal(0, 5.0, (n, 3))
+    B[3::2500] = 0.0
+    pos = to_layout(tp, pos0, layout); mom = to_layout(tp, mom0, layout)
+    if flayout == "strided":
+        wide = torch.zeros((n, 4), dtype=torch.float64, device="cuda")
+        wide[:, :3] = torch.from_numpy(E).cuda()
+        Ed = wide[:, :3]
+        Bd = to_layout(tp, B, "aos")
+    else:
+        Ed = to_layout(tp, E, "aos" if flayout == "aos" else "soa")
+        Bd = to_layout(tp, B, "soa" if flayout == "soa" else "aos")
+    before = tp._lib.lib().tp_launch_count()
+    for _ in range(2):
+        tool.push(pos, mom, Q_E, M_E, Ed, Bd)
+    assert tp._lib.lib().tp_launch_count() - before == 2
+    o = [np.ascontiguousarray(pos0[:, k]) for k in range(3)] + [np.ascontiguousarray(mom0[:, k]) for k in range(3)]
+    e = [np.ascontiguousarray(E[:, k]) for k in range(3)]; b = [np.ascontiguousarray(B[:, k]) for k in range(3)]
+    for _ in range(2):
+        oboris.push_soa(*o, Q_E, M_E, *e, *b, dt)
+    assert_bits_equal(pos.cpu().numpy(), np.stack(o[:3], axis=1), "position")
+    assert_bits_equal(mom.cpu().numpy(), np.stack(o[3:], axis=1), "momentum")
+    assert_bits_equal(Ed.cpu().numpy(), E, "E untouched")
+    assert_bits_equal(Bd.cpu().numpy(), B, "B untouched")
+
+
 def test_invariants_full_size(tp):
     """Config-4-shaped property test at 16 Mi particles: with E = 0 the push is a
     pure rotation, so |p| is conserved to rounding over many steps, and a random

@@ -40,7 +40,7 @@ def test_poisson_golden(golden_dir, tag, n):
     assert isinstance(out_np, np.ndarray) and np.array_equal(out_np, phi)
 
 
-@pytest.mark.parametrize("n", [3, 5, 2047, 2048, 2049, 300_001])
+@pytest.mark.parametrize("n", [3, 5, 2047, 2048, 2049, 16_383, 16_384, 16_385, 300_001])
 def test_poisson_ragged_sizes(n):
     import turbopy_b200 as tp
     grid = make_grid(n, 0.0, 1.0)
@@ -49,3 +49,31 @@ def test_poisson_ragged_sizes(n):
     phi = tool.solve(torch.from_numpy(src).cuda()).cpu().numpy()
     ref = opoisson.solve(src, grid.r, grid.cell_widths)
     assert np.abs(phi - ref).max() <= TOL * max(np.abs(ref).max(), 1e-300) * 10
+
+
+@pytest.mark.parametrize("n", [1000, 16_384, 100_003])
+@pytest.mark.parametrize("shift", [1, 2, 3])
+def test_poisson_unaligned_pointers_match_aligned(n, shift):
+    """The 256-bit path (32-byte aligned arrays) and the scalar path (any 8-byte alignment) and the single-launch
+    small-grid path all run the same arithmetic: identical bits.  Straight through the C ABI."""
+    from turbopy_b200 import _lib
+    L = _lib.lib()
+    grid = make_grid(n, 0.0, 1.5)
+    src = np.random.default_rng(7 * n + shift).normal(size=n)
+    dr = float(np.mean(grid.cell_widths))
+    scratch = torch.empty(int(L.tp_poisson_scratch_doubles(n)), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(off):
+        buf = torch.zeros((3, n + 8), dtype=torch.float64, device="cuda")
+        s_, r_, o_ = buf[0, off:off + n], buf[1, off:off + n], buf[2, off:off + n]
+        s_.copy_(torch.from_numpy(src)); r_.copy_(torch.from_numpy(grid.r))
+        _lib.check(L.tp_poisson_radial_solve_f64(s_.data_ptr(), r_.data_ptr(), dr, o_.data_ptr(), n, scratch.data_ptr(), stream))
+        torch.cuda.synchronize()
+        assert float(buf[2, :off].abs().sum()) == 0.0 and float(buf[2, off + n:].abs().sum()) == 0.0   # no stray writes
+        return o_.cpu().numpy()
+
+    aligned, shifted = run(0), run(shift)
+    assert np.array_equal(aligned, shifted)
+    ref = opoisson.solve(src, grid.r, grid.cell_widths)
+    assert np.abs(aligned - ref).max() <= TOL * np.abs(ref).max() * 10

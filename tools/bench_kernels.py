@@ -102,7 +102,12 @@ def main():
         timed(lambda: tool.push(pa, ma, Q_E, M_E, np.array([0.0, 1e5, 0.0]), np.array([0.0, 0.0, 1.0])), it))
     Ep, Bp = tp.soa_particles(n16, fill=1e4), tp.soa_particles(n16, fill=0.5)
     add("push per-particle E,B (SoA, un-fused)", n16, 144, timed(lambda: tool.push(pos, mom, Q_E, M_E, Ep, Bp), it))
-    del pa, ma, Ep, Bp
+    Ea, Ba = Ep.contiguous(), Bp.contiguous()
+    add("push per-particle E,B (SoA particles, C-order (n,3) fields)", n16, 144,
+        timed(lambda: tool.push(pos, mom, Q_E, M_E, Ea, Ba), it))
+    add("push per-particle E,B (all four arrays C-order (n,3))", n16, 144,
+        timed(lambda: tool.push(pa, ma, Q_E, M_E, Ea, Ba), it))
+    del pa, ma, Ep, Bp, Ea, Ba
 
     # ---- kernel 1b: fused gather + push
     for ng, ncomp, formula in ((30, 1, "interp"), (4097, 1, "interp"), (1025, 6, "interp"), (1025, 6, "create_interpolator"),

@@ -18,6 +18,7 @@
 #include "particle_io.cuh"
 #include "grid_stage.cuh"
 #include "tma_ring.cuh"
+#include "tma_ring_fields.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -288,6 +289,41 @@ __global__ void __launch_bounds__(kTmaThreads, 1) push_tma_kernel(const __grid_c
             Vec3 x, p;
             load_one(a.p, i, x, p);
             if (push_one_fast(a, Eu, Bu, i, x, p)) store_one(a.p, i, x, p);
+            else push_one_exact(a, i);
+        }
+    }
+}
+
+// ---- BorisPush.push with per-particle (n,3) E and B ------------------------------
+__device__ __noinline__ void push_fields_exact_slot(const PushArgs& a, int64_t i, double* xs, double* ps, int pitch) {
+    const Vec3 none = {0.0, 0.0, 0.0};
+    Vec3 x, p;
+    load_one(a.p, i, x, p);                    // global memory still holds the input
+    Guard g;
+    boris_step<false>(a.k, dt_field_q(a.k, field_at(a.E, none, i)), dt_field_q(a.k, field_at(a.B, none, i)), x, p, g);
+    slot_write(xs, ps, pitch, x, p);
+}
+
+template <bool PA, bool FA>
+__global__ void __launch_bounds__(kTmaThreads, 1) push_fields_tma_kernel(const __grid_constant__ PushTmaArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const PushArgs& a = ta.a;
+    ring_init(ta.ring, smem);
+    __syncthreads();
+    tma_ring_fields<PA, FA>(
+        a, ta.ring, smem,
+        [&](const Vec3& E, const Vec3& B, Vec3& x, Vec3& p) {
+            Guard g;
+            boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, g);
+            return guard_ok(g) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+        },
+        [&](int64_t i, double* xs, double* ps, int pitch) { push_fields_exact_slot(a, i, xs, ps, pitch); });
+    if (blockIdx.x == gridDim.x - 1) {                       // ragged tail, scalar path
+        const Vec3 none = {0.0, 0.0, 0.0};
+        for (int64_t i = ta.ring.ntiles * kTileF + threadIdx.x; i < a.p.n; i += kTmaThreads) {
+            Vec3 x, p;
+            load_one(a.p, i, x, p);
+            if (push_one_fast(a, none, none, i, x, p)) store_one(a.p, i, x, p);
             else push_one_exact(a, i);
         }
     }
@@ -606,9 +642,9 @@ static bool tma_enabled() {
 }
 
 // Ring geometry for `n` particles behind `front` bytes of other shared memory; false if the ring is not worth it.
-static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int& blocks) {
+static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int& blocks, int tile = kTile) {
     const DeviceProps& d = device_props();
-    ring.ntiles = n / kTile;
+    ring.ntiles = n / tile;
     if (!tma_enabled() || ring.ntiles < d.sm_count) return false;
     ring.tiles_off = static_cast<uint32_t>((front + 127) & ~size_t(127));
     const int64_t room = d.smem_optin - 1024 - static_cast<int64_t>(ring.tiles_off);
@@ -735,6 +771,29 @@ extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
             }
             count_launch();
             return static_cast<int>(cudaGetLastError());
+        }
+    }
+    if ((vec2 || aos16) && a.E.mode == TP_FIELD_PER_PARTICLE && a.B.mode == TP_FIELD_PER_PARTICLE) {
+        // both fields in one bulk-copyable layout: three component slices, or one C-order (n,3) block
+        auto bulk_layout = [&](const FieldArg& f) {
+            if (!aligned16(f.ptr)) return -1;
+            const int l = layout_of(f.sn, f.sc, a.p.n);
+            return l == kLayoutSoA ? (f.sc % 2 == 0 ? 0 : -1) : l == kLayoutAoS ? 1 : -1;
+        };
+        const int le = bulk_layout(a.E), lb = bulk_layout(a.B);
+        PushTmaArgs ta;
+        ta.a = a;
+        size_t smem = 0; int blocks = 0;
+        if (le >= 0 && le == lb && plan_ring(a.p.n, kSmemHeader, ta.ring, smem, blocks, kTileF)) {
+            auto launch = [&](auto kern) {
+                int r = set_smem(kern, smem);
+                if (r) return r;
+                kern<<<blocks, kTmaThreads, smem, s>>>(ta);
+                count_launch();
+                return static_cast<int>(cudaGetLastError());
+            };
+            if (aos16) return le ? launch(push_fields_tma_kernel<true, true>) : launch(push_fields_tma_kernel<true, false>);
+            return le ? launch(push_fields_tma_kernel<false, true>) : launch(push_fields_tma_kernel<false, false>);
         }
     }
     if (vec2) {

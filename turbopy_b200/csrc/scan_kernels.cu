@@ -12,10 +12,14 @@
 //   K4  one CTA: exclusive scan -> off2[t]; total = off2[T-1] + G[T-1]
 //   K5  per tile: a -> I1 -> g -> I2 = off2 + local scan -> out = I2 - total   (reads r, s; writes out)
 // I1 is recomputed instead of stored and the final shift is folded into K5:
-// 56 B/point of traffic (16 algorithmic), all of it coalesced -- a warp owns
-// 8 rows of 32 consecutive elements and scans them with shuffles.  The tile sum
-// of K3 is the last value of the SAME local scan K5 runs, so out[n-1] is
-// exactly 0 like the reference's I2 - I2[-1].
+// 56 B/point of traffic (16 algorithmic).  A thread owns 8 CONSECUTIVE elements
+// (two 256-bit loads), scans them serially in registers, and only the 256 thread
+// totals go through shuffles: one shuffle chain and one __syncthreads per tile
+// scan.  The tile sum of K3 is the last value of the SAME local scan K5 runs, so
+// out[n-1] is exactly 0 like the reference's I2 - I2[-1].  The result does not
+// depend on the launch geometry (fixed tile size, fixed association), so it is
+// reproducible run to run; grids of at most kSmallTiles tiles run K1..K5 as one
+// single-CTA launch with the same arithmetic.
 // numpy's cumsum is strictly sequential; a parallel scan associates differently,
 // so results agree to rounding (tolerance in tests/test_gpu_poisson.py).
 #include "common.cuh"
@@ -25,9 +29,10 @@
 namespace tp {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanRows = 8;                               // rows of 32 elements per warp
+constexpr int kScanRows = 8;                               // consecutive elements per thread
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kScanTile = kScanThreads * kScanRows;        // 2048
+constexpr int kSmallTiles = 8;                             // <= 16384 points: one launch, one CTA
 
 struct PoissonArgs {
     const double* r; const double* s; double* out;
@@ -35,60 +40,69 @@ struct PoissonArgs {
     double* tile2;              // the same for scan 2
     double* scalars;            // [0] = i0, [1] = total of scan 2 (= I2[n-1])
     int64_t n; int64_t ntiles; double dr;
+    bool vec;                   // r, s, out 32-byte aligned: 256-bit accesses
 };
 
-__device__ __forceinline__ double warp_inclusive(double v) {
-    const int lane = threadIdx.x & 31;
+// Inclusive scan of the tile's 2048 values held as v[k] = element (thread*8 + k).
+// Returns the tile total; v[] becomes the inclusive prefix inside the tile.
+// `phase` alternates between consecutive calls so that one barrier per scan is enough.
+__device__ __forceinline__ double tile_scan(double (&v)[kScanRows], int& phase) {
+    __shared__ double warp_tot[2][kScanWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 1; k < kScanRows; ++k) v[k] = v[k - 1] + v[k];
+    double inc = v[kScanRows - 1];                           // thread total -> inclusive over the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
-    return v;
-}
-
-// Inclusive scan of the tile's 2048 values held as v[k] = element (warp*256 + k*32 + lane).
-// Returns the tile total; v[] becomes the inclusive prefix inside the tile.
-__device__ __forceinline__ double tile_scan(double (&v)[kScanRows]) {
-    __shared__ double warp_tot[kScanWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double carry = 0.0;
+    if (lane == 31) warp_tot[phase][warp] = inc;
+    __syncthreads();
+    double wbase = 0.0, total = 0.0;
 #pragma unroll
-    for (int k = 0; k < kScanRows; ++k) {
-        const double inc = warp_inclusive(v[k]);
-        v[k] = carry + inc;
-        carry = carry + __shfl_sync(0xffffffffu, inc, 31);
+    for (int w = 0; w < kScanWarps; ++w) {
+        if (w == warp) wbase = total;
+        total += warp_tot[phase][w];
     }
-    if (lane == 0) warp_tot[warp] = carry;
-    __syncthreads();
-    double wbase = 0.0;
+    phase ^= 1;
+    const double base = wbase + (inc - v[kScanRows - 1]);    // everything before this thread's first element
 #pragma unroll
-    for (int w = 0; w < kScanWarps - 1; ++w)
-        if (w < warp) wbase += warp_tot[w];
-    double total = 0.0;
-#pragma unroll
-    for (int w = 0; w < kScanWarps - 1; ++w) total += warp_tot[w];
-    total = total + warp_tot[kScanWarps - 1];
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kScanRows; ++k) v[k] = wbase + v[k];
+    for (int k = 0; k < kScanRows; ++k) v[k] = base + v[k];
     return total;
 }
 
 __device__ __forceinline__ int64_t elem_index(int64_t tile, int k) {
-    return tile * kScanTile + (threadIdx.x >> 5) * (32 * kScanRows) + k * 32 + (threadIdx.x & 31);
+    return tile * kScanTile + static_cast<int64_t>(threadIdx.x) * kScanRows + k;
 }
 
 __device__ __forceinline__ double a_at(const PoissonArgs& p, int64_t i) { return (p.r[i] * p.s[i]) * p.dr; }
 
+__device__ __forceinline__ void ld4(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// the thread's 8 elements of `src` (fill beyond n)
+__device__ __forceinline__ void load8(const PoissonArgs& p, const double* src, int64_t t, double fill, double (&v)[kScanRows]) {
+    const int64_t i0 = elem_index(t, 0);
+    if (p.vec && i0 + kScanRows <= p.n) {
+        ld4(src + i0, v[0], v[1], v[2], v[3]);
+        ld4(src + i0 + 4, v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanRows; ++k) v[k] = i0 + k < p.n ? src[i0 + k] : fill;
+    }
+}
+
 // a[] of the tile (0 beyond n)
 __device__ __forceinline__ void load_a(const PoissonArgs& p, int64_t t, double (&v)[kScanRows], double (&rr)[kScanRows]) {
+    load8(p, p.r, t, 1.0, rr);
+    load8(p, p.s, t, 0.0, v);
 #pragma unroll
-    for (int k = 0; k < kScanRows; ++k) {
-        const int64_t i = elem_index(t, k);
-        rr[k] = i < p.n ? p.r[i] : 1.0;
-        v[k] = i < p.n ? (rr[k] * p.s[i]) * p.dr : 0.0;
-    }
+    for (int k = 0; k < kScanRows; ++k) v[k] = (rr[k] * v[k]) * p.dr;
 }
 
 // v: inclusive local scan of a (tile_scan output) -> g of the tile (0 beyond n)
@@ -104,17 +118,17 @@ __device__ __forceinline__ void to_g(const PoissonArgs& p, int64_t t, double off
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) poisson_sums1_kernel(const __grid_constant__ PoissonArgs p) {
+__device__ __forceinline__ void sums1_body(const PoissonArgs& p, int& phase) {
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         double v[kScanRows], rr[kScanRows];
         load_a(p, t, v, rr);
-        const double total = tile_scan(v);
+        const double total = tile_scan(v, phase);
         if (threadIdx.x == 0) p.tile1[t] = total;
     }
 }
 
-// one CTA: tile sums -> exclusive offsets, in place; returns the grand total through *total_out
-__device__ __forceinline__ void scan_tile_sums(double* sums, int64_t ntiles, double* total_out) {
+// one CTA: tile sums -> exclusive offsets, in place
+__device__ __forceinline__ void scan_tile_sums(double* sums, int64_t ntiles, int& phase) {
     __shared__ double carry_s;
     if (threadIdx.x == 0) carry_s = 0.0;
     __syncthreads();
@@ -122,26 +136,25 @@ __device__ __forceinline__ void scan_tile_sums(double* sums, int64_t ntiles, dou
         double v[kScanRows], in[kScanRows];
 #pragma unroll
         for (int k = 0; k < kScanRows; ++k) {
-            const int64_t i = base + (threadIdx.x >> 5) * (32 * kScanRows) + k * 32 + (threadIdx.x & 31);
+            const int64_t i = base + threadIdx.x * kScanRows + k;
             in[k] = i < ntiles ? sums[i] : 0.0;
             v[k] = in[k];
         }
-        const double total = tile_scan(v);
+        const double total = tile_scan(v, phase);
         const double carry = carry_s;
 #pragma unroll
         for (int k = 0; k < kScanRows; ++k) {
-            const int64_t i = base + (threadIdx.x >> 5) * (32 * kScanRows) + k * 32 + (threadIdx.x & 31);
+            const int64_t i = base + threadIdx.x * kScanRows + k;
             if (i < ntiles) sums[i] = carry + (v[k] - in[k]);            // exclusive
         }
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + total;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
 }
 
-__global__ void __launch_bounds__(kScanThreads) poisson_offsets1_kernel(const __grid_constant__ PoissonArgs p) {
-    scan_tile_sums(p.tile1, p.ntiles, nullptr);
+__device__ __forceinline__ void offsets1_body(const PoissonArgs& p, int& phase) {
+    scan_tile_sums(p.tile1, p.ntiles, phase);
     if (threadIdx.x == 0) {
         // i0 = 2*g[1] - g[2] with I1[1] = a0 + a1, I1[2] = I1[1] + a2 in numpy's sequential order (:50-53)
         const double I1_1 = a_at(p, 0) + a_at(p, 1);
@@ -150,43 +163,84 @@ __global__ void __launch_bounds__(kScanThreads) poisson_offsets1_kernel(const __
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) poisson_sums2_kernel(const __grid_constant__ PoissonArgs p) {
+__device__ __forceinline__ void sums2_body(const PoissonArgs& p, int& phase) {
     const double i0 = p.scalars[0];
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         double v[kScanRows], rr[kScanRows];
         load_a(p, t, v, rr);
-        tile_scan(v);
+        tile_scan(v, phase);
         to_g(p, t, p.tile1[t], i0, rr, v);
-        const double total = tile_scan(v);               // the same scan K5 runs: its last value IS the tile sum
+        const double total = tile_scan(v, phase);        // the same scan K5 runs: its last value IS the tile sum
         if (threadIdx.x == 0) p.tile2[t] = total;
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) poisson_offsets2_kernel(const __grid_constant__ PoissonArgs p) {
+__device__ __forceinline__ void offsets2_body(const PoissonArgs& p, int& phase) {
     __shared__ double last_sum;
     if (threadIdx.x == 0) last_sum = p.tile2[p.ntiles - 1];
     __syncthreads();
-    scan_tile_sums(p.tile2, p.ntiles, nullptr);
-    __syncthreads();
+    scan_tile_sums(p.tile2, p.ntiles, phase);
     // I2[n-1] exactly as K5 forms it for the last element: off2[T-1] + (local inclusive value = tile sum)
     if (threadIdx.x == 0) p.scalars[1] = p.tile2[p.ntiles - 1] + last_sum;
 }
 
-__global__ void __launch_bounds__(kScanThreads) poisson_apply_kernel(const __grid_constant__ PoissonArgs p) {
+__device__ __forceinline__ void apply_body(const PoissonArgs& p, int& phase) {
     const double i0 = p.scalars[0], last = p.scalars[1];
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         double v[kScanRows], rr[kScanRows];
         load_a(p, t, v, rr);
-        tile_scan(v);
+        tile_scan(v, phase);
         to_g(p, t, p.tile1[t], i0, rr, v);
-        tile_scan(v);
+        tile_scan(v, phase);
         const double off2 = p.tile2[t];
 #pragma unroll
-        for (int k = 0; k < kScanRows; ++k) {
-            const int64_t i = elem_index(t, k);
-            if (i < p.n) p.out[i] = (off2 + v[k]) - last;
+        for (int k = 0; k < kScanRows; ++k) v[k] = (off2 + v[k]) - last;
+        const int64_t e0 = elem_index(t, 0);
+        if (p.vec && e0 + kScanRows <= p.n) {
+            st4(p.out + e0, v[0], v[1], v[2], v[3]);
+            st4(p.out + e0 + 4, v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanRows; ++k)
+                if (e0 + k < p.n) p.out[e0 + k] = v[k];
         }
     }
+}
+
+__global__ void __launch_bounds__(kScanThreads) poisson_sums1_kernel(const __grid_constant__ PoissonArgs p) {
+    int phase = 0;
+    sums1_body(p, phase);
+}
+__global__ void __launch_bounds__(kScanThreads) poisson_offsets1_kernel(const __grid_constant__ PoissonArgs p) {
+    int phase = 0;
+    offsets1_body(p, phase);
+}
+__global__ void __launch_bounds__(kScanThreads) poisson_sums2_kernel(const __grid_constant__ PoissonArgs p) {
+    int phase = 0;
+    sums2_body(p, phase);
+}
+__global__ void __launch_bounds__(kScanThreads) poisson_offsets2_kernel(const __grid_constant__ PoissonArgs p) {
+    int phase = 0;
+    offsets2_body(p, phase);
+}
+__global__ void __launch_bounds__(kScanThreads) poisson_apply_kernel(const __grid_constant__ PoissonArgs p) {
+    int phase = 0;
+    apply_body(p, phase);
+}
+
+// K1..K5 back to back in ONE CTA (small grids: the solve is launch-latency bound).  __syncthreads orders the
+// CTA's own global writes (tile sums, scalars) before its later reads; arithmetic identical to the 5-launch path.
+__global__ void __launch_bounds__(kScanThreads) poisson_small_kernel(const __grid_constant__ PoissonArgs p) {
+    int phase = 0;
+    sums1_body(p, phase);
+    __syncthreads();
+    offsets1_body(p, phase);
+    __syncthreads();
+    sums2_body(p, phase);
+    __syncthreads();
+    offsets2_body(p, phase);
+    __syncthreads();
+    apply_body(p, phase);
 }
 
 }  // namespace tp
@@ -209,6 +263,12 @@ extern "C" int tp_poisson_radial_solve_f64(const double* sources, const double* 
     p.tile1 = scratch;
     p.tile2 = scratch + p.ntiles;
     p.scalars = scratch + 2 * p.ntiles;
+    p.vec = ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(sources) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
+    if (p.ntiles <= kSmallTiles) {
+        poisson_small_kernel<<<1, kScanThreads, 0, s>>>(p);
+        count_launch(1);
+        return static_cast<int>(cudaGetLastError());
+    }
     const int blocks = static_cast<int>(std::min<int64_t>(p.ntiles, static_cast<int64_t>(d.sm_count) * 8));
     poisson_sums1_kernel<<<blocks, kScanThreads, 0, s>>>(p);
     poisson_offsets1_kernel<<<1, kScanThreads, 0, s>>>(p);
