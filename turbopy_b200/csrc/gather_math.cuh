@@ -80,11 +80,14 @@ struct RecView {
     int ng;
     double r_first, inv_dr, dr;
     unsigned present;           // bit k: component k exists
+    uint64_t policy;            // L2 eviction policy of the record loads
 };
 
-__device__ __forceinline__ void ld_record(const double* p, double (&v)[8]) {
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(p + 4));
+__device__ __forceinline__ void ld_record(const double* p, double (&v)[8], uint64_t policy) {
+    asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p), "l"(policy));
+    asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(p + 4), "l"(policy));
 }
 
 template <int FORMULA>
@@ -93,8 +96,8 @@ __device__ __forceinline__ void fetch_records(const RecView& rv, double x, NodeP
     np.j = j;
     double a[8], b[8];
     const double* base = rv.rec + static_cast<int64_t>(j) * 8;
-    ld_record(base, a);
-    ld_record(base + 8, b);
+    ld_record(base, a, rv.policy);
+    ld_record(base + 8, b, rv.policy);
     np.x0 = a[0]; np.x1 = b[0];
     if (FORMULA == TP_INTERP_A) {
         np.xm = rv.rec[static_cast<int64_t>(max(j - 1, 0)) * 8];

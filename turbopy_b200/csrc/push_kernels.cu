@@ -104,8 +104,9 @@ __device__ __forceinline__ bool gather_step_fast_records(const GatherArgs& a, co
     return ok && guard_ok(gd) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
 }
 
-__device__ __forceinline__ RecView make_rec_view(const GatherArgs& a) {
+__device__ __forceinline__ RecView make_rec_view(const GatherArgs& a, int keep_in_l2) {
     RecView rv;
+    rv.policy = keep_in_l2 ? l2_evict_last() : l2_evict_normal();
     rv.rec = a.records; rv.ng = a.ng; rv.r_first = a.r_first; rv.inv_dr = a.inv_dr; rv.dr = a.dr;
     rv.present = 0;
 #pragma unroll
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const _
     ring_prologue<AOS>(a.p, ta.ring, smem);
     const GridView g = make_view<STAGED>(a, smem);
     if (STAGED) stage_wait(smem);
-    const RecView rv = make_rec_view(a);
+    const RecView rv = make_rec_view(a, ta.ring.stream_hint);
     tma_ring<AOS>(
         a.p, ta.ring, smem,
         [&](Vec3& x, Vec3& p) {
@@ -633,6 +634,14 @@ static bool records_enabled() {
     return on;
 }
 
+static bool l2_hints_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("TURBOPY_B200_L2HINT");       // tuning / A-B switch, default on
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 static bool tma_enabled() {
     static const bool on = [] {
         const char* e = std::getenv("TURBOPY_B200_TMA");          // tuning / A-B switch, default on
@@ -645,6 +654,7 @@ static bool tma_enabled() {
 static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int& blocks, int tile = kTile) {
     const DeviceProps& d = device_props();
     ring.ntiles = n / tile;
+    ring.stream_hint = 0;
     if (!tma_enabled() || ring.ntiles < d.sm_count) return false;
     ring.tiles_off = static_cast<uint32_t>((front + 127) & ~size_t(127));
     const int64_t room = d.smem_optin - 1024 - static_cast<int64_t>(ring.tiles_off);
@@ -678,6 +688,7 @@ static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_sme
         if ((rc = static_cast<int>(cudaGetLastError()))) return rc;
         ta.g.records = rec;
         gmode = 2;
+        ta.ring.stream_hint = l2_hints_enabled() ? 1 : 0;
     }
     switch (formula) {
         case TP_INTERP_A: rc = launch_gather_push_tma_v<TP_INTERP_A>(ta, smem, blocks, gmode, aos, s); break;

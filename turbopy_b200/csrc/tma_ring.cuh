@@ -44,12 +44,40 @@ struct RingArgs {
     int nstages;
     uint32_t tiles_off;        // byte offset of stage 0 in dynamic shared memory (128-B aligned)
     int64_t ntiles;            // full tiles; the remaining n - ntiles*kTile particles use the scalar path
+    int stream_hint;           // 1: particle loads / stores carry the L2 evict_first policy
 };
 
 __device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
                  "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
+
+// SoA tiles with the evict_first policy (the large-grid kernels: keeps the node records in L2)
+__device__ __forceinline__ void tile_load_hint(const ParticleArgs& p, int64_t tile, unsigned char* stage, uint64_t* bar,
+                                               uint64_t policy) {
+    const int64_t first = tile * kTile;
+    mbar_expect_tx(bar, kTileBytes);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        tma_bulk_g2s_hint(stage + c * kSliceBytes, p.pos + c * p.pos_sc + first, kSliceBytes, bar, policy);
+        tma_bulk_g2s_hint(stage + (3 + c) * kSliceBytes, p.mom + c * p.mom_sc + first, kSliceBytes, bar, policy);
+    }
+}
+__device__ __forceinline__ void tile_store_hint(const ParticleArgs& p, int64_t tile, const unsigned char* stage, uint64_t policy) {
+    const int64_t first = tile * kTile;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        tma_bulk_s2g_hint(p.pos + c * p.pos_sc + first, stage + c * kSliceBytes, kSliceBytes, policy);
+        tma_bulk_s2g_hint(p.mom + c * p.mom_sc + first, stage + (3 + c) * kSliceBytes, kSliceBytes, policy);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
 template <bool AOS>
@@ -157,13 +185,17 @@ __device__ __forceinline__ void tma_ring(const ParticleArgs& P, const RingArgs& 
     if (threadIdx.x >= kConsumers) {
         // ---------------- producer warp: one elected lane drives the TMA ----------------
         if (threadIdx.x == kConsumers) {
+            const bool hint = !AOS && ra.stream_hint;
+            const uint64_t policy = l2_evict_first();
             for (int64_t t = t0; t < ra.ntiles; t += tstep) {
                 mbar_wait(&done[s], parity);                    // every consumer warp released the stage
-                tile_store<AOS>(P, t, tiles + s * kTileBytes);
+                if (hint) tile_store_hint(P, t, tiles + s * kTileBytes, policy);
+                else tile_store<AOS>(P, t, tiles + s * kTileBytes);
                 const int64_t tn = t + nst * tstep;             // the tile that reuses this stage
                 if (tn < ra.ntiles) {
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores done READING smem
-                    tile_load<AOS>(P, tn, tiles + s * kTileBytes, &full[s]);
+                    if (hint) tile_load_hint(P, tn, tiles + s * kTileBytes, &full[s], policy);
+                    else tile_load<AOS>(P, tn, tiles + s * kTileBytes, &full[s]);
                 }
                 if (++s == nst) { s = 0; parity ^= 1u; }
             }
@@ -206,7 +238,9 @@ __device__ __forceinline__ void ring_prologue(const ParticleArgs& P, const RingA
     if (threadIdx.x == kConsumers) {
         for (int s = 0; s < ra.nstages; ++s) {
             const int64_t t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(s) * gridDim.x;
-            if (t < ra.ntiles) tile_load<AOS>(P, t, smem + ra.tiles_off + s * kTileBytes, &ring_full(smem)[s]);
+            if (t >= ra.ntiles) continue;
+            if (!AOS && ra.stream_hint) tile_load_hint(P, t, smem + ra.tiles_off + s * kTileBytes, &ring_full(smem)[s], l2_evict_first());
+            else tile_load<AOS>(P, t, smem + ra.tiles_off + s * kTileBytes, &ring_full(smem)[s]);
         }
     }
 }
