@@ -213,6 +213,22 @@ int tp_plane_wave_f64(const double* r, int64_t ng, double amplitude, double omeg
                       const double* clock_dev, double* E, int64_t e_stride, tp_stream_t stream);
 int tp_clock_advance_f64(double* clock_dev, double start_time, double dt, tp_stream_t stream);
 
+/* ---- particle reordering by grid cell (additive; the reference never reorders) ----
+ * Orders the particles by the cell they sit in along `axis`, so that the fused
+ * gather on a grid too large for shared memory reads each warp's node records
+ * from a few shared lines instead of one line per lane.  STABLE: the permutation
+ * equals numpy.argsort(key, kind="stable") with
+ *   key = min(trunc(max((x - r_first) * (1/dr), 0)), ncells-1) >> cells_per_bin_log2
+ * (NaN -> key 0).  position and momentum are permuted in place (same storage);
+ * perm_out (device, n int64, optional) receives new[i] = old[perm_out[i]] so that
+ * callers can reorder their own per-particle arrays with tp_permute_f64.
+ * scratch: tp_sort_scratch_bytes() bytes of device memory.  n < 2^32. */
+int64_t tp_sort_scratch_bytes(int64_t n, int64_t ncells, int cells_per_bin_log2);
+int tp_sort_by_cell_f64(const tp_particles* p, int axis, double r_first, double dr, int64_t ncells,
+                        int cells_per_bin_log2, void* scratch, int64_t* perm_out, tp_stream_t stream);
+/* array[i*stride_n] <- array[perm[i]*stride_n] for i < n; tmp: n doubles of device scratch */
+int tp_permute_f64(double* array, int64_t stride_n, int64_t n, const int64_t* perm, double* tmp, tp_stream_t stream);
+
 /* ---- CUDA-graph capture of a sequence of the calls above ------------------ */
 int tp_graph_begin(tp_stream_t stream);
 int tp_graph_end(tp_stream_t stream, void** graph_exec);

@@ -136,7 +136,21 @@ def main():
     pos[:, 0].copy_(xs); mom.zero_()
     t = timed(lambda: tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B), it)
     add("gather+push ng=1048577 comps=6, particles sorted by x", n16, 96, t, "grid in L2")
-    del pos, mom
+    # the same after tp.sort_by_cell on a random ensemble, and the cost of the sort itself
+    pos.copy_(0.05 + 0.9 * torch.rand((n16, 3), dtype=torch.float64, device="cuda")); mom.zero_()
+    keep = pos.clone()
+
+    def resort():
+        pos.copy_(keep)
+        tp.sort_by_cell(pos, mom, ow.grid)
+    t_sort = timed(resort, max(3, it // 10)) - timed(lambda: pos.copy_(keep), max(3, it // 10))
+    resort()                                    # leave the ensemble sorted for the next line
+    add("sort_by_cell (20 kernels: stable 2-pass radix sort + in-place permute)", n16, 96, t_sort,
+        "one-off; amortised over the steps until particles have drifted across bins")
+    t = timed(lambda: tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B), it)
+    tool.check_status()
+    add("gather+push ng=1048577 comps=6, after sort_by_cell", n16, 96, t, "grid in L2, warps share record lines")
+    del pos, mom, keep
 
     # ---- gather only: Interpolators.interpolate1D(x, y)(x_new), bounds check deferred (no sync per call)
     for ng in (1025, 4097):

@@ -19,7 +19,7 @@ from .diagnostics import (DeviceFieldDiagnostic, DevicePointDiagnostic, KineticE
                           reduce_moments)
 from .cycle import DeviceClock, PlaneWave
 from .graph import StepGraph
-from .particles import soa_particles, to_soa
+from .particles import soa_particles, sort_by_cell, to_soa
 from .tools import (BandedOperator, BorisPush, FiniteDifference, GridOnDevice, Interpolators,
                     PoissonSolver1DRadial)
 

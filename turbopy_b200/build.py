@@ -18,7 +18,7 @@ OBJ_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(HERE, "libturbopy_b200.so")
 
 SOURCES = ["capi.cu", "push_kernels.cu", "fd_kernels.cu", "reduce_kernels.cu", "scan_kernels.cu", "field_kernels.cu",
-           "host_path.cu"]
+           "sort_kernels.cu", "host_path.cu"]
 
 # -fmad=false is part of the arithmetic contract (no FMA contraction: results
 # are bit-identical to the reference's numpy); -lineinfo maps ncu's source page

@@ -98,6 +98,8 @@ def _n3_strides(t, what):
         sn, sc = t.strides[0] // 8, t.strides[1] // 8
     if t.shape[0] <= 1:
         sn = max(sn, 1)
+    if t.shape[0] == 0:                     # strides of an empty array carry no information
+        sc = max(sc, 1)
     if sn <= 0 or sc <= 0:
         raise ValueError(f"{what}: negative or zero strides are not supported")
     return int(sn), int(sc)
