@@ -106,6 +106,34 @@ def test_config3_shard_125m_particles_1mi_grid():
     assert abs(sub[0] - ref[0]) <= 1e-12 * ref[0]
 
 
+def test_config3_sort_by_cell_125m_particles():
+    """configs[2] size, the optional reordering: size-independent properties of the result -- keys ascend,
+    ties keep their order (stable), it is a permutation (integer checksums of every array are unchanged,
+    sum of perm = n(n-1)/2), and the arrays are exactly the gathers of the originals on a sample."""
+    import turbopy_b200 as tp
+    n, ng = 125_000_000, (1 << 20) + 1
+    grid = make_grid(ng)
+    gen = torch.Generator(device="cuda").manual_seed(3457)
+    pos, mom = tp.soa_particles(n), tp.soa_particles(n)
+    for c in range(3):
+        pos[:, c].copy_(0.05 + 0.9 * torch.rand(n, dtype=torch.float64, device="cuda", generator=gen))
+        mom[:, c].copy_(torch.randn(n, dtype=torch.float64, device="cuda", generator=gen))
+    sums = [int(a[:, c].contiguous().view(torch.int64).sum()) for a in (pos, mom) for c in range(3)]
+    idx = subset(gen, n, 4096)
+    x_before = pos[:, 0].clone()
+    perm = tp.sort_by_cell(pos, mom, grid, return_perm=True)
+    assert [int(a[:, c].contiguous().view(torch.int64).sum()) for a in (pos, mom) for c in range(3)] == sums
+    assert int(perm.sum()) == n * (n - 1) // 2
+    inv_dr = 1.0 / grid.dr
+    keys = torch.clamp(((pos[:, 0] - float(grid.r[0])) * inv_dr).floor().to(torch.int64), 0, ng - 2)
+    dk = keys[1:] - keys[:-1]
+    assert int(dk.min()) >= 0                                               # ascending cells
+    dp = perm[1:] - perm[:-1]
+    assert bool(((dk > 0) | (dp > 0)).all())                                # stable inside a cell
+    del keys, dk, dp
+    assert torch.equal(pos[idx, 0], x_before[perm[idx]])                    # new[i] = old[perm[i]]
+
+
 def test_config4_beam_256mi_particles():
     """configs[3]: 256 Mi particles, gamma log-uniform in [1, 1e3], B = 10 T, E = 0:
     |p| is conserved to rounding (pure rotation) and a subset matches the oracle."""
