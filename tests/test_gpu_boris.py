@@ -209,7 +209,7 @@ def test_error_behaviour(tp):
 
 @pytest.mark.parametrize("layout", ["soa", "aos"])
 def test_push_tma_ring_vs_oracle(tp, layout):
-    """Uniform-field push through the TMA ring (>= one 1024-particle tile per SM),
+    """Uniform-field push through the TMA ring (>= one 960-particle tile per SM),
     with a ragged tail and particles that must take the recovery path
     (zero momentum is fine; 1e-200 momenta fall below the fast path's domain)."""
     n = 148 * 1024 * 3 + 501

@@ -15,8 +15,8 @@ import os
 
 from . import _lib
 from ._host import ComputeTool, Diagnostic, HAVE_TURBOPY
-from .diagnostics import (DeviceFieldDiagnostic, DevicePointDiagnostic, KineticEnergyDiagnostic,
-                          reduce_moments)
+from .diagnostics import (DeviceFieldDiagnostic, DeviceParticleDiagnostic, DevicePointDiagnostic,
+                          KineticEnergyDiagnostic, reduce_moments)
 from .cycle import DeviceClock, PlaneWave
 from .graph import StepGraph
 from .particles import soa_particles, sort_by_cell, to_soa
@@ -28,7 +28,7 @@ __version__ = "0.1.0"
 TOOL_CLASSES = {"BorisPush": BorisPush, "Interpolators": Interpolators, "FiniteDifference": FiniteDifference,
                 "PoissonSolver1DRadial": PoissonSolver1DRadial}
 DIAGNOSTIC_CLASSES = {"kinetic_energy": KineticEnergyDiagnostic, "device_point": DevicePointDiagnostic,
-                      "device_field": DeviceFieldDiagnostic}
+                      "device_field": DeviceFieldDiagnostic, "device_particle": DeviceParticleDiagnostic}
 
 
 def register_tools(override=True):

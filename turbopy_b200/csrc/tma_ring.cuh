@@ -8,9 +8,10 @@ namespace tp {
 // ---------------------------------------------------------------------------
 // particles streamed by the TMA: the shared-memory ring
 // ---------------------------------------------------------------------------
-// The register-path kernels above keep only 16 warps per SM resident (128
-// registers per thread) and their loads sit at the end of each iteration, so the
-// HBM latency is exposed (profiles/r1_v2: long_scoreboard is the top stall).
+// The register-path kernels (push_kernel / gather_push_kernel) keep only 16 warps
+// per SM resident (128 registers per thread) and their loads sit at the end of
+// each iteration, so the HBM latency is exposed (profiles/r1_v1_gather_push.md:
+// long_scoreboard is the top stall).
 // Here the particle arrays themselves go through the TMA: one persistent CTA
 // per SM owns a ring of NST shared-memory stages of 45 KB; a stage holds one
 // tile of kTile = 960 particles, either as six contiguous 7.5 KB component

@@ -253,3 +253,58 @@ class DeviceFieldDiagnostic(Diagnostic):
                 # CSVOutputUtility.append would have raised IndexError on the extra row
                 raise IndexError(f"index {self.rows.shape[0]} is out of bounds for axis 0 with size {self.rows.shape[0]}")
             _savetxt(self.input_data["filename"], self.rows.cpu().numpy())
+
+
+class DeviceParticleDiagnostic(Diagnostic):
+    """One particle's row of a shared (n,3) CUDA tensor, every step -- the
+    device-side counterpart of the particle-in-field example's
+    ``ParticleDiagnostic`` (tests/fixtures/particle_in_field/particle_in_field.py:66-99:
+    ``output_function(self.data[0, :])`` into a ``(num_steps + 1, 3)`` CSV).
+
+    ``input_data``: ``"resource"`` (name of the shared tensor, e.g.
+    ``"ChargedParticle:position"``) or the example's ``"component"``
+    (``"position"`` / ``"momentum"``, looked up as ``"ChargedParticle:<component>"``);
+    ``"index"`` (which particle, default 0); ``"output_type"`` ("csv" | "stdout");
+    ``"filename"``.  Rows are copied device-to-device on the current stream; the
+    only host transfer is in ``finalize()``."""
+
+    def __init__(self, owner, input_data):
+        super().__init__(owner, input_data)
+        self.resource_name = input_data.get("resource", "ChargedParticle:" + str(input_data.get("component", "position")))
+        self.index = int(input_data.get("index", 0))
+        self.output = input_data["output_type"]
+        self.data = None
+        self.rows = None
+        self._used = 0
+
+    def inspect_resource(self, resource):
+        if self.resource_name in resource:
+            self.data = resource[self.resource_name]
+
+    def initialize(self):
+        if self.data is None:
+            raise RuntimeError(f"Diagnostic resource {self.resource_name} was not found")
+        d = self.data
+        if not (isinstance(d, torch.Tensor) and d.is_cuda and d.dtype == torch.float64 and d.ndim == 2):
+            raise TypeError("device_particle needs an (n,k) CUDA float64 tensor")
+        if not -d.shape[0] <= self.index < d.shape[0]:
+            raise IndexError(f"index {self.index} is out of bounds for axis 0 with size {d.shape[0]}")
+        if self.output == "csv":
+            self.rows = torch.zeros((int(self.owner.clock.num_steps) + 1, d.shape[1]), dtype=torch.float64, device=d.device)
+
+    def diagnose(self):
+        row = self.data[self.index, :]
+        if self.output == "stdout":
+            print(row.cpu().numpy())
+            return
+        if self._used < self.rows.shape[0]:
+            self.rows[self._used].copy_(row)                # device-to-device, asynchronous
+        self._used += 1
+
+    def finalize(self):
+        self.diagnose()
+        if self.output == "csv":
+            if self._used > self.rows.shape[0]:
+                # CSVOutputUtility.append would have raised IndexError on the extra row
+                raise IndexError(f"index {self.rows.shape[0]} is out of bounds for axis 0 with size {self.rows.shape[0]}")
+            _savetxt(self.input_data["filename"], self.rows.cpu().numpy())
