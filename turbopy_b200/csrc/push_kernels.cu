@@ -268,33 +268,6 @@ __device__ __noinline__ void push_one_exact_slot(const PushArgs& a, int64_t i, d
     slot_write(xs, ps, pitch, x, p);
 }
 
-template <bool AOS>
-__global__ void __launch_bounds__(kTmaThreads, 1) push_tma_kernel(const __grid_constant__ PushTmaArgs ta) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const PushArgs& a = ta.a;
-    ring_init(ta.ring, smem);
-    __syncthreads();
-    ring_prologue<AOS>(a.p, ta.ring, smem);
-    const Vec3 equ = dt_field_q(a.k, uniform_of(a.E)), bqu = dt_field_q(a.k, uniform_of(a.B));
-    tma_ring<AOS>(
-        a.p, ta.ring, smem,
-        [&](Vec3& x, Vec3& p) {
-            Guard g;
-            boris_step<true>(a.k, equ, bqu, x, p, g);
-            return guard_ok(g) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
-        },
-        [&](int64_t i, double* xs, double* ps, int pitch) { push_one_exact_slot(a, i, xs, ps, pitch); });
-    if (blockIdx.x == gridDim.x - 1) {                       // ragged tail, scalar path
-        const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
-        for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
-            Vec3 x, p;
-            load_one(a.p, i, x, p);
-            if (push_one_fast(a, Eu, Bu, i, x, p)) store_one(a.p, i, x, p);
-            else push_one_exact(a, i);
-        }
-    }
-}
-
 // ---- BorisPush.push with per-particle (n,3) E and B ------------------------------
 __device__ __noinline__ void push_fields_exact_slot(const PushArgs& a, int64_t i, double* xs, double* ps, int pitch) {
     const Vec3 none = {0.0, 0.0, 0.0};
@@ -311,7 +284,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) push_fields_tma_kernel(const _
     const PushArgs& a = ta.a;
     ring_init(ta.ring, smem);
     __syncthreads();
-    tma_ring_fields<PA, FA>(
+    tma_ring_fields<PA, FA, true>(
         a, ta.ring, smem,
         [&](const Vec3& E, const Vec3& B, Vec3& x, Vec3& p) {
             Guard g;
@@ -325,6 +298,37 @@ __global__ void __launch_bounds__(kTmaThreads, 1) push_fields_tma_kernel(const _
             Vec3 x, p;
             load_one(a.p, i, x, p);
             if (push_one_fast(a, none, none, i, x, p)) store_one(a.p, i, x, p);
+            else push_one_exact(a, i);
+        }
+    }
+}
+
+// Uniform E, B on the small-tile ring: one particle per consumer thread, 480-particle tiles, 22.5 KB stages,
+// kPushStages of them.  Measured (16 Mi particles): this ring 3 / 4 / 5 / 6 stages = 91.7 / 98.0 / 92.1 / 88.5 % of the
+// HBM peak, the 960-particle ring of the fused kernel 2 / 3 / 4 stages = 92.9 / 94.1 / 89.6 %.  (The fused gather+push
+// is the other way round: 98 % on the 960-particle ring, 83-90 % here.)
+constexpr int kPushStages = 4;
+template <bool PA>
+__global__ void __launch_bounds__(kTmaThreads, 1) push_tma_kernel(const __grid_constant__ PushTmaArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const PushArgs& a = ta.a;
+    ring_init(ta.ring, smem);
+    __syncthreads();
+    const Vec3 equ = dt_field_q(a.k, uniform_of(a.E)), bqu = dt_field_q(a.k, uniform_of(a.B));
+    tma_ring_fields<PA, false, false>(
+        a, ta.ring, smem,
+        [&](const Vec3&, const Vec3&, Vec3& x, Vec3& p) {
+            Guard g;
+            boris_step<true>(a.k, equ, bqu, x, p, g);
+            return guard_ok(g) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+        },
+        [&](int64_t i, double* xs, double* ps, int pitch) { push_one_exact_slot(a, i, xs, ps, pitch); });
+    if (blockIdx.x == gridDim.x - 1) {                       // ragged tail, scalar path
+        const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
+        for (int64_t i = ta.ring.ntiles * kTileF + threadIdx.x; i < a.p.n; i += kTmaThreads) {
+            Vec3 x, p;
+            load_one(a.p, i, x, p);
+            if (push_one_fast(a, Eu, Bu, i, x, p)) store_one(a.p, i, x, p);
             else push_one_exact(a, i);
         }
     }
@@ -659,8 +663,8 @@ static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int
     ring.tiles_off = static_cast<uint32_t>((front + 127) & ~size_t(127));
     const int64_t room = d.smem_optin - 1024 - static_cast<int64_t>(ring.tiles_off);
     ring.nstages = static_cast<int>(std::min<int64_t>(kMaxStages, room / kTileBytes));
-    if (const char* cap = std::getenv("TURBOPY_B200_STAGES"))       // tuning knob: cap the ring depth
-        ring.nstages = std::min(ring.nstages, std::max(2, std::atoi(cap)));
+    if (const char* cap = std::getenv("TURBOPY_B200_STAGES"))       // tuning knob: ring depth (2..4, as far as it fits)
+        ring.nstages = static_cast<int>(std::min<int64_t>(room / kTileBytes, std::min(4, std::max(2, std::atoi(cap)))));
     if (ring.nstages < 2) return false;
     smem = ring.tiles_off + static_cast<size_t>(ring.nstages) * kTileBytes;
     blocks = static_cast<int>(std::min<int64_t>(d.sm_count, ring.ntiles));
@@ -772,7 +776,11 @@ extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
         PushTmaArgs ta;
         ta.a = a;
         size_t smem = 0; int blocks = 0;
-        if (plan_ring(a.p.n, kSmemHeader, ta.ring, smem, blocks)) {
+        if (plan_ring(a.p.n, kSmemHeader, ta.ring, smem, blocks, kTileF)) {
+            int nst = kPushStages;
+            if (const char* cap = std::getenv("TURBOPY_B200_STAGES")) nst = std::min(kRingMaxStages, std::max(2, std::atoi(cap)));
+            ta.ring.nstages = nst;
+            smem = ta.ring.tiles_off + static_cast<size_t>(nst) * 2 * kArrayF;
             if (aos16) {
                 if ((rc = set_smem(push_tma_kernel<true>, smem))) return rc;
                 push_tma_kernel<true><<<blocks, kTmaThreads, smem, s>>>(ta);

@@ -165,9 +165,11 @@ __device__ __forceinline__ void slot_write(double* xs, double* ps, int pitch, co
 // The ring driver.  fast(x, p) -> bool updates one particle in registers;
 // recover(i, xs, ps, pitch) recomputes particle i from global memory (the tile
 // has not been stored yet) and writes it into its stage slot.
-// Shared-memory header: grid barrier at byte 0, full[s] at 16 + 8 s, done[s] at 48 + 8 s.
+// Shared-memory header (kSmemHeader = 128 B): grid barrier at byte 0, full[s] at 16 + 8 s, done[s] at 64 + 8 s, s < 6.
+constexpr int kRingMaxStages = 6;
 __device__ __forceinline__ uint64_t* ring_full(unsigned char* smem) { return reinterpret_cast<uint64_t*>(smem + 16); }
-__device__ __forceinline__ uint64_t* ring_done(unsigned char* smem) { return reinterpret_cast<uint64_t*>(smem + 48); }
+__device__ __forceinline__ uint64_t* ring_done(unsigned char* smem) { return reinterpret_cast<uint64_t*>(smem + 64); }
+static_assert(64 + 8 * kRingMaxStages <= kSmemHeader, "mbarriers must fit the shared-memory header");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
