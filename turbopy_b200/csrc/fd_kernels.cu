@@ -13,7 +13,9 @@
 // Compiled with -fmad=false.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace tp {
@@ -21,9 +23,24 @@ namespace tp {
 constexpr int kFdThreads = 256;
 constexpr int kQuad = 4;
 
-static int fd_blocks(int64_t n_quads) {
+// Persistent CTAs per SM, per kernel.  Measured on the B200 (tools/sweep_fd.py, 16 Mi and 256 Mi points, % of the
+// HBM copy peak at 2 / 3 / 4 / 5 / 6 / 8 / 12 / 16 CTAs of 256 threads per SM): these streaming kernels peak around
+// 1024-1280 threads per SM and lose 10-20 % on a ragged second wave (e.g. 6 or 8 CTAs when 5 are resident):
+//   centered      67 / 84 / 95 / 98 / 77 / 92 / 91 / 92        -> 5
+//   upwind        74 / 91 / 100 / 83 / 84 / 84 / 93 / 96       -> 4
+//   del2_radial   77 / 96 / 99 / 81 / 90 / 103 / 105 / 105     -> 12
+//   ddx, del2, BC 74 / 89 / 98 / 88 / 83 / 80 / 75 / 97        -> 4
+//   radial_curl   52 / 71 / 82 / 93 / 67 / 82 / 84 / 84        -> 5
+template <typename K>
+static int fd_blocks(K kernel, int64_t n_quads, int per_sm) {
+    (void)kernel;
     const DeviceProps& d = device_props();
-    const int64_t full = static_cast<int64_t>(d.sm_count) * 8;
+    static const int forced = [] {
+        const char* e = std::getenv("TURBOPY_B200_FD_BLOCKS");   // tuning knob
+        return e ? std::max(1, std::atoi(e)) : 0;
+    }();
+    if (forced) per_sm = forced;
+    const int64_t full = static_cast<int64_t>(d.sm_count) * per_sm;
     const int64_t need = (n_quads + kFdThreads - 1) / kFdThreads;
     return static_cast<int>(need < 1 ? 1 : (need < full ? need : full));
 }
@@ -233,12 +250,25 @@ __global__ void __launch_bounds__(kFdThreads) fd_dia_const_kernel(const __grid_c
 template <int ND, int O0, int O1, int O2>
 __global__ void __launch_bounds__(kFdThreads) fd_dia_const_t_kernel(const __grid_constant__ DiaConstArgs a, bool vec) {
     const double c0 = a.coef[0], c1 = a.coef[1], c2 = ND > 2 ? a.coef[2] : 0.0;
+    constexpr int LO = (O0 < O1 ? O0 : O1) < (ND > 2 ? O2 : 0) ? (O0 < O1 ? O0 : O1) : (ND > 2 ? O2 : 0);
+    constexpr int HI = (O0 > O1 ? O0 : O1) > (ND > 2 ? O2 : 0) ? (O0 > O1 ? O0 : O1) : (ND > 2 ? O2 : 0);
+    constexpr int HL = LO < 0 ? -LO : 0, HR = HI > 0 ? HI : 0;      // halo actually touched by this pattern
     TP_QUAD_LOOP(a.n) {
         const int64_t i = qd * kQuad;
         double w[kQuad + 4], o[kQuad];
-        load_window<2>(a.x, i, a.n, vec, w);
         const bool edge = (i < 8) || (i + kQuad + 8 > a.n);
         if (__builtin_expect(!edge, 1)) {
+            if (vec) {
+                const double2 p0 = ld2(a.x + i), p1 = ld2(a.x + i + 2);
+                w[2] = p0.x; w[3] = p0.y; w[4] = p1.x; w[5] = p1.y;
+            } else {
+#pragma unroll
+                for (int k = 0; k < kQuad; ++k) w[2 + k] = a.x[i + k];
+            }
+#pragma unroll
+            for (int k = 1; k <= HL; ++k) w[2 - k] = a.x[i - k];
+#pragma unroll
+            for (int k = 0; k < HR; ++k) w[2 + kQuad + k] = a.x[i + kQuad + k];
 #pragma unroll
             for (int q = 0; q < kQuad; ++q) {
                 double acc = 0.0;                       // scipy: y starts from zeros
@@ -248,6 +278,7 @@ __global__ void __launch_bounds__(kFdThreads) fd_dia_const_t_kernel(const __grid
                 o[q] = acc;
             }
         } else {
+            load_window<2>(a.x, i, a.n, vec, w);
             o[0] = dia_const_row<0>(a, i, w, true);
             o[1] = (i + 1 < a.n) ? dia_const_row<1>(a, i + 1, w, true) : 0.0;
             o[2] = (i + 2 < a.n) ? dia_const_row<2>(a, i + 2, w, true) : 0.0;
@@ -258,9 +289,10 @@ __global__ void __launch_bounds__(kFdThreads) fd_dia_const_t_kernel(const __grid
 }
 
 template <int ND, int O0, int O1, int O2>
-static bool launch_dia_const_t(const DiaConstArgs& a, bool vec, int blocks, cudaStream_t s) {
+static bool launch_dia_const_t(const DiaConstArgs& a, bool vec, cudaStream_t s) {
     if (a.ndiag != ND || a.off[0] != O0 || a.off[1] != O1 || (ND > 2 && a.off[2] != O2)) return false;
-    fd_dia_const_t_kernel<ND, O0, O1, O2><<<blocks, kFdThreads, 0, s>>>(a, vec);
+    auto kern = fd_dia_const_t_kernel<ND, O0, O1, O2>;
+    kern<<<quads(kern, a.n, 4), kFdThreads, 0, s>>>(a, vec);
     return true;
 }
 
@@ -272,7 +304,8 @@ static ConstDiv host_recip(double b) {
     return c;
 }
 
-static int quads(int64_t n) { return fd_blocks((n + kQuad - 1) / kQuad); }
+template <typename K>
+static int quads(K kernel, int64_t n, int per_sm) { return fd_blocks(kernel, (n + kQuad - 1) / kQuad, per_sm); }
 
 }  // namespace tp
 
@@ -284,7 +317,7 @@ extern "C" int tp_fd_centered_f64(const double* y, double* d, int64_t n, double 
     if (n < 0 || (n > 0 && (!y || !d))) return TP_E_ARG;
     if (n == 0) return TP_OK;
     const bool vec = aligned16(y) && aligned16(d);
-    fd_centered_kernel<<<quads(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(y, d, n, host_recip(two_dr), vec);
+    fd_centered_kernel<<<quads(fd_centered_kernel, n, 5), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(y, d, n, host_recip(two_dr), vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -296,7 +329,7 @@ extern "C" int tp_fd_upwind_left_f64(const double* y, const double* widths, doub
     if (n < 0 || (n > 0 && (!y || !d)) || (n > 1 && !widths)) return TP_E_ARG;
     if (n == 0) return TP_OK;
     const bool vec = aligned16(y) && aligned16(d);
-    fd_upwind_kernel<<<quads(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(y, widths, d, n, vec);
+    fd_upwind_kernel<<<quads(fd_upwind_kernel, n, 4), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(y, widths, d, n, vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -308,7 +341,7 @@ extern "C" int tp_fd_del2_radial_apply_f64(const double* f, const double* r, dou
     if (n < 0 || (n > 0 && (!f || !r || !out))) return TP_E_ARG;
     if (n == 0) return TP_OK;
     const bool vec = aligned16(f) && aligned16(r) && aligned16(out);
-    fd_del2_radial_kernel<<<quads(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(f, r, out, n, g1, g2, vec);
+    fd_del2_radial_kernel<<<quads(fd_del2_radial_kernel, n, 12), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(f, r, out, n, g1, g2, vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -327,7 +360,7 @@ extern "C" int tp_fd_dia_apply_f64(const double* data, const int* offsets, int n
         if (offsets[k] < -2 || offsets[k] > 2) return TP_E_ARG;
         a.off[k] = offsets[k];
     }
-    fd_dia_kernel<<<quads(n), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, aligned16(x) && aligned16(out));
+    fd_dia_kernel<<<quads(fd_dia_kernel, n, 5), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, aligned16(x) && aligned16(out));
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -356,13 +389,12 @@ extern "C" int tp_fd_dia_const_apply_f64(const double* coef, const int* offsets,
     }
     const bool vec = aligned16(x) && aligned16(out);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int blocks = quads(n);
-    const bool done = launch_dia_const_t<2, -1, 1, 0>(a, vec, blocks, s) ||       // ddx, ddr
-                      launch_dia_const_t<3, -1, 0, 1>(a, vec, blocks, s) ||       // del2
-                      launch_dia_const_t<3, 0, 1, 2>(a, vec, blocks, s) ||        // BC_left_extrap / avg / quad
-                      launch_dia_const_t<2, 0, 1, 0>(a, vec, blocks, s) ||        // BC_left_flat
-                      launch_dia_const_t<3, -2, -1, 0>(a, vec, blocks, s);        // BC_right_extrap
-    if (!done) fd_dia_const_kernel<<<blocks, kFdThreads, 0, s>>>(a, vec);
+    const bool done = launch_dia_const_t<2, -1, 1, 0>(a, vec, s) ||       // ddx, ddr
+                      launch_dia_const_t<3, -1, 0, 1>(a, vec, s) ||       // del2
+                      launch_dia_const_t<3, 0, 1, 2>(a, vec, s) ||        // BC_left_extrap / avg / quad
+                      launch_dia_const_t<2, 0, 1, 0>(a, vec, s) ||        // BC_left_flat
+                      launch_dia_const_t<3, -2, -1, 0>(a, vec, s);        // BC_right_extrap
+    if (!done) fd_dia_const_kernel<<<quads(fd_dia_const_kernel, n, 4), kFdThreads, 0, s>>>(a, vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

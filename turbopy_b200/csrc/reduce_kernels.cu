@@ -9,6 +9,9 @@
 // fixed order (no atomics), so two runs on the same data agree bit for bit.
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 #include <cmath>
 
 namespace tp {
@@ -104,7 +107,14 @@ extern "C" int tp_reduce_moments_f64(const double* mom, int64_t stride_n, int64_
     const bool vec = layout_of(stride_n, stride_c, n) == kLayoutSoA && aligned16(mom) && (stride_c % 2 == 0) && n >= 2;
     const int64_t items = vec ? (n + 1) / 2 : n;
     int64_t blocks = (items + kRedThreads - 1) / kRedThreads;
-    const int64_t full = static_cast<int64_t>(d.sm_count) * 8;
+    static int per_sm = 0;                                   // one resident wave of persistent CTAs
+    if (per_sm == 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, moments_partial_kernel, kRedThreads, 0) != cudaSuccess || v < 1) v = 4;
+        if (const char* e = std::getenv("TURBOPY_B200_RED_BLOCKS")) v = std::max(1, std::atoi(e));   // tuning knob
+        per_sm = v;
+    }
+    const int64_t full = static_cast<int64_t>(d.sm_count) * per_sm;
     if (blocks > full) blocks = full;
     if (blocks > kRedMaxBlocks) blocks = kRedMaxBlocks;
     if (blocks < 1) blocks = 1;

@@ -25,6 +25,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace tp {
 
@@ -269,12 +270,24 @@ extern "C" int tp_poisson_radial_solve_f64(const double* sources, const double* 
         count_launch(1);
         return static_cast<int>(cudaGetLastError());
     }
-    const int blocks = static_cast<int>(std::min<int64_t>(p.ntiles, static_cast<int64_t>(d.sm_count) * 8));
-    poisson_sums1_kernel<<<blocks, kScanThreads, 0, s>>>(p);
+    // one resident wave per kernel (the result does not depend on the grid: tiles are fixed)
+    auto wave = [&](auto kernel) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kScanThreads, 0) != cudaSuccess || v < 1) v = 3;
+        if (const char* e = std::getenv("TURBOPY_B200_SCAN_BLOCKS")) v = std::max(1, std::atoi(e));   // tuning knob
+        return static_cast<int>(std::min<int64_t>(p.ntiles, static_cast<int64_t>(d.sm_count) * v));
+    };
+    static int b1 = 0, b2 = 0, b3 = 0;
+    static int64_t planned_tiles = -1;
+    if (planned_tiles != p.ntiles) {
+        b1 = wave(poisson_sums1_kernel); b2 = wave(poisson_sums2_kernel); b3 = wave(poisson_apply_kernel);
+        planned_tiles = p.ntiles;
+    }
+    poisson_sums1_kernel<<<b1, kScanThreads, 0, s>>>(p);
     poisson_offsets1_kernel<<<1, kScanThreads, 0, s>>>(p);
-    poisson_sums2_kernel<<<blocks, kScanThreads, 0, s>>>(p);
+    poisson_sums2_kernel<<<b2, kScanThreads, 0, s>>>(p);
     poisson_offsets2_kernel<<<1, kScanThreads, 0, s>>>(p);
-    poisson_apply_kernel<<<blocks, kScanThreads, 0, s>>>(p);
+    poisson_apply_kernel<<<b3, kScanThreads, 0, s>>>(p);
     count_launch(5);
     return static_cast<int>(cudaGetLastError());
 }
