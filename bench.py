@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--particles", type=int, default=16 << 20, help="particles per GPU")
     ap.add_argument("--ng", type=int, default=4097, help="grid nodes")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-particles", type=int, default=1 << 20)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
