@@ -110,6 +110,16 @@ int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
                       const double* E, int e_mode, int64_t e_stride_n, int64_t e_stride_c,
                       const double* B, int b_mode, int64_t b_stride_n, int64_t b_stride_c,
                       tp_stream_t stream);
+/* nsteps consecutive pushes with the same E and B (the reference's time loop calling
+ * BorisPush.push nsteps times with unchanged field arguments, e.g. a uniform static
+ * E x B) in ONE pass over the particles: each particle is read once, stepped nsteps
+ * times in registers and written once.  Bit-identical to nsteps calls of
+ * tp_boris_push_f64; the traffic per push drops from 96 B to 96/nsteps B, so the
+ * kernel leaves the HBM roofline and becomes fp64-bound. */
+int tp_boris_push_steps_f64(const tp_particles* p, const tp_push_consts* k,
+                            const double* E, int e_mode, int64_t e_stride_n, int64_t e_stride_c,
+                            const double* B, int b_mode, int64_t b_stride_n, int64_t b_stride_c,
+                            int nsteps, tp_stream_t stream);
 
 /* ---- kernel 1b: fused linear gather + BorisPush.push ---------------------
  * E,B at each particle = linear interpolation of the grid fields at

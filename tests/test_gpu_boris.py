@@ -290,3 +290,42 @@ def test_invariants_full_size(tp):
         oboris.push_aos(sub_pos, sub_mom, Q_E, M_E, np.zeros(3), B, dt)
     assert_bits_equal(pos[idx].cpu().numpy(), sub_pos)
     assert_bits_equal(mom[idx].cpu().numpy(), sub_mom)
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("fields", ["uni", "pp"])
+@pytest.mark.parametrize("n", [1000, 148 * 480 * 2 + 333])
+def test_push_steps_equals_repeated_push(tp, layout, fields, n):
+    """push_steps(K) == K x push, bit for bit, on the ring and on the register path, incl. particles that
+    take the recovery path (zero and 1e-200 momenta) -- and both equal the oracle's K steps."""
+    dt, K = 1e-12, 7
+    tool = pusher(tp, dt)
+    pos0, mom0 = thermal_ensemble(n, seed=n + 1)
+    mom0[::97] = 0.0
+    mom0[5::501] = 1e-200
+    rng = np.random.default_rng(4)
+    if fields == "uni":
+        E, B = np.array([3e4, 1e5, -2e4]), np.array([0.5, -0.25, 1.0])
+        Ed, Bd = E, B
+    else:
+        E = rng.normal(0, 1e6, (n, 3)); B = rng.normal(0, 5.0, (n, 3))
+        Ed, Bd = to_layout(tp, E, "aos"), to_layout(tp, B, "aos")
+    pa, ma = to_layout(tp, pos0, layout), to_layout(tp, mom0, layout)
+    pb, mb = to_layout(tp, pos0, layout), to_layout(tp, mom0, layout)
+    before = tp._lib.lib().tp_launch_count()
+    tool.push_steps(pa, ma, Q_E, M_E, Ed, Bd, K)
+    assert tp._lib.lib().tp_launch_count() - before == 1
+    for _ in range(K):
+        tool.push(pb, mb, Q_E, M_E, Ed, Bd)
+    assert_bits_equal(pa.cpu().numpy(), pb.cpu().numpy(), "position")
+    assert_bits_equal(ma.cpu().numpy(), mb.cpu().numpy(), "momentum")
+    m = min(n, 5000)
+    rp, rm = pos0[:m].copy(), mom0[:m].copy()
+    for _ in range(K):
+        oboris.push_aos(rp, rm, Q_E, M_E, E if fields == "uni" else E[:m], B if fields == "uni" else B[:m], dt)
+    assert_bits_equal(pa[:m].cpu().numpy(), rp, "position vs oracle")
+    assert_bits_equal(ma[:m].cpu().numpy(), rm, "momentum vs oracle")
+    tool.push_steps(pa, ma, Q_E, M_E, Ed, Bd, 0)                 # no-op
+    assert_bits_equal(pa.cpu().numpy(), pb.cpu().numpy())
+    with pytest.raises(ValueError):
+        tool.push_steps(pa, ma, Q_E, M_E, Ed, Bd, -1)

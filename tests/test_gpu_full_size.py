@@ -42,6 +42,10 @@ def test_config1_million_particles_1000_steps_graph():
         oboris.push_aos(sp, sm, Q_E, M_E, E, B, dt)
     assert_bits_equal(pos.cpu().numpy()[idx], sp); assert_bits_equal(mom.cpu().numpy()[idx], sm)
     g.close()
+    # the same 1000 steps as ONE temporally blocked launch (static fields): every particle identical
+    pos2, mom2 = tp.to_soa(pos0), tp.to_soa(mom0)
+    tool.push_steps(pos2, mom2, Q_E, M_E, E, B, 1000)
+    assert torch.equal(pos2, pos) and torch.equal(mom2, mom)
 
 
 def test_config2_pif_16mi_particles():

@@ -98,6 +98,10 @@ def main():
     tool = tp.BorisPush(owner_for(10), {"type": "BorisPush"})
     pos, mom = particles(n16)
     pa, ma = pos.contiguous(), mom.contiguous()
+    for K in (4, 50):
+        t = timed(lambda: tool.push_steps(pos, mom, Q_E, M_E, np.array([0.0, 1e5, 0.0]), np.array([0.0, 0.0, 1.0]), K), max(3, it // K))
+        add(f"push_steps: {K} pushes per pass (static uniform ExB, temporal blocking)", n16 * K, 96, t,
+            f"moves 96/{K} B per push: fp64-bound, not on the HBM roofline")
     add("push uniform ExB (AoS (n,3) C-order)", n16, 96,
         timed(lambda: tool.push(pa, ma, Q_E, M_E, np.array([0.0, 1e5, 0.0]), np.array([0.0, 0.0, 1.0])), it))
     Ep, Bp = tp.soa_particles(n16, fill=1e4), tp.soa_particles(n16, fill=0.5)

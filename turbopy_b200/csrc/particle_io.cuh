@@ -31,6 +31,7 @@ struct PushArgs {
     ParticleArgs p;
     PushK k;
     FieldArg E, B;
+    int nsteps;             // consecutive pushes with the same E, B per visit of a particle (>= 1)
 };
 
 constexpr int kMaxSeg = 7;  // node coordinates + up to six separately stored components

@@ -36,16 +36,26 @@ __device__ __noinline__ void push_one_exact(const PushArgs& a, int64_t i) {
     const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);     // rebuilt here: no references into the hot loop
     Vec3 x, p;
     load_one(a.p, i, x, p);
+    const Vec3 eq = dt_field_q(a.k, field_at(a.E, Eu, i)), bq = dt_field_q(a.k, field_at(a.B, Bu, i));
     Guard g;
-    boris_step<false>(a.k, dt_field_q(a.k, field_at(a.E, Eu, i)), dt_field_q(a.k, field_at(a.B, Bu, i)), x, p, g);
+    for (int s = 0; s < a.nsteps; ++s) boris_step<false>(a.k, eq, bq, x, p, g);
     store_one(a.p, i, x, p);
+}
+
+// nsteps straight-line steps of one particle; false if any of them left the fast path's domain
+__device__ __forceinline__ bool push_steps_fast(const PushK& k, int nsteps, const Vec3& eq, const Vec3& bq, Vec3& x, Vec3& p) {
+    Guard g;
+    bool fin = true;
+    for (int s = 0; s < nsteps; ++s) {
+        boris_step<true>(k, eq, bq, x, p, g);
+        fin = fin && finite3(x.x, x.y, x.z);
+    }
+    return guard_ok(g) && fin && k.fast_ok;
 }
 
 __device__ __forceinline__ bool push_one_fast(const PushArgs& a, const Vec3& Eu, const Vec3& Bu, int64_t i,
                                               Vec3& x, Vec3& p) {
-    Guard g;
-    boris_step<true>(a.k, dt_field_q(a.k, field_at(a.E, Eu, i)), dt_field_q(a.k, field_at(a.B, Bu, i)), x, p, g);
-    return guard_ok(g) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+    return push_steps_fast(a.k, a.nsteps, dt_field_q(a.k, field_at(a.E, Eu, i)), dt_field_q(a.k, field_at(a.B, Bu, i)), x, p);
 }
 
 template <bool VEC2>
@@ -263,8 +273,9 @@ __device__ __noinline__ void push_one_exact_slot(const PushArgs& a, int64_t i, d
     const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
     Vec3 x, p;
     load_one(a.p, i, x, p);                    // the tile has not been stored yet: global memory holds the input
+    const Vec3 eq = dt_field_q(a.k, Eu), bq = dt_field_q(a.k, Bu);
     Guard g;
-    boris_step<false>(a.k, dt_field_q(a.k, Eu), dt_field_q(a.k, Bu), x, p, g);
+    for (int s = 0; s < a.nsteps; ++s) boris_step<false>(a.k, eq, bq, x, p, g);
     slot_write(xs, ps, pitch, x, p);
 }
 
@@ -273,8 +284,9 @@ __device__ __noinline__ void push_fields_exact_slot(const PushArgs& a, int64_t i
     const Vec3 none = {0.0, 0.0, 0.0};
     Vec3 x, p;
     load_one(a.p, i, x, p);                    // global memory still holds the input
+    const Vec3 eq = dt_field_q(a.k, field_at(a.E, none, i)), bq = dt_field_q(a.k, field_at(a.B, none, i));
     Guard g;
-    boris_step<false>(a.k, dt_field_q(a.k, field_at(a.E, none, i)), dt_field_q(a.k, field_at(a.B, none, i)), x, p, g);
+    for (int s = 0; s < a.nsteps; ++s) boris_step<false>(a.k, eq, bq, x, p, g);
     slot_write(xs, ps, pitch, x, p);
 }
 
@@ -287,9 +299,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) push_fields_tma_kernel(const _
     tma_ring_fields<PA, FA, true>(
         a, ta.ring, smem,
         [&](const Vec3& E, const Vec3& B, Vec3& x, Vec3& p) {
-            Guard g;
-            boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, g);
-            return guard_ok(g) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+            return push_steps_fast(a.k, a.nsteps, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p);
         },
         [&](int64_t i, double* xs, double* ps, int pitch) { push_fields_exact_slot(a, i, xs, ps, pitch); });
     if (blockIdx.x == gridDim.x - 1) {                       // ragged tail, scalar path
@@ -317,11 +327,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) push_tma_kernel(const __grid_c
     const Vec3 equ = dt_field_q(a.k, uniform_of(a.E)), bqu = dt_field_q(a.k, uniform_of(a.B));
     tma_ring_fields<PA, false, false>(
         a, ta.ring, smem,
-        [&](const Vec3&, const Vec3&, Vec3& x, Vec3& p) {
-            Guard g;
-            boris_step<true>(a.k, equ, bqu, x, p, g);
-            return guard_ok(g) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
-        },
+        [&](const Vec3&, const Vec3&, Vec3& x, Vec3& p) { return push_steps_fast(a.k, a.nsteps, equ, bqu, x, p); },
         [&](int64_t i, double* xs, double* ps, int pitch) { push_one_exact_slot(a, i, xs, ps, pitch); });
     if (blockIdx.x == gridDim.x - 1) {                       // ragged tail, scalar path
         const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
@@ -756,13 +762,16 @@ int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_
 
 using namespace tp;
 
-extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k, const double* E, int e_mode,
-                                 int64_t e_sn, int64_t e_sc, const double* B, int b_mode, int64_t b_sn,
-                                 int64_t b_sc, tp_stream_t stream) {
+static int boris_push_device(const tp_particles* p, const tp_push_consts* k, const double* E, int e_mode,
+                             int64_t e_sn, int64_t e_sc, const double* B, int b_mode, int64_t b_sn,
+                             int64_t b_sc, int nsteps, tp_stream_t stream) {
     const DeviceProps& d = device_props();
     if (d.status != TP_OK) return d.status;
+    if (nsteps < 0) return TP_E_ARG;
+    if (nsteps == 0) return TP_OK;
     PushArgs a;
     std::memset(&a, 0, sizeof(a));
+    a.nsteps = nsteps;
     bool vec2 = false, aos16 = false;
     int rc = fill_particles(p, a.p, vec2, &aos16);
     if (rc) return rc;
@@ -824,6 +833,18 @@ extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
     }
     count_launch();
     return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k, const double* E, int e_mode,
+                                 int64_t e_sn, int64_t e_sc, const double* B, int b_mode, int64_t b_sn,
+                                 int64_t b_sc, tp_stream_t stream) {
+    return boris_push_device(p, k, E, e_mode, e_sn, e_sc, B, b_mode, b_sn, b_sc, 1, stream);
+}
+
+extern "C" int tp_boris_push_steps_f64(const tp_particles* p, const tp_push_consts* k, const double* E, int e_mode,
+                                       int64_t e_sn, int64_t e_sc, const double* B, int b_mode, int64_t b_sn,
+                                       int64_t b_sc, int nsteps, tp_stream_t stream) {
+    return boris_push_device(p, k, E, e_mode, e_sn, e_sc, B, b_mode, b_sn, b_sc, nsteps, stream);
 }
 
 extern "C" int tp_gather_push_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,

@@ -352,6 +352,31 @@ class BorisPush(ComputeTool):
             return None
         raise TypeError("position/momentum must both be CUDA float64 tensors or both numpy float64 arrays")
 
+    def push_steps(self, position, momentum, charge, mass, E, B, steps):
+        """``steps`` consecutive :meth:`push` calls with unchanged ``E`` and ``B``
+        (what a time loop over a static field does, e.g. the uniform E x B of
+        tests/test_computetools.py:40-62) in one pass over the particles:
+        bit-identical to calling :meth:`push` ``steps`` times, but each particle
+        is read and written once, so the kernel is bound by fp64 issue instead
+        of HBM bandwidth.  CUDA tensors only (additive; not a reference method)."""
+        steps = int(steps)
+        if steps < 0:
+            raise ValueError("steps must be >= 0")
+        if not _is_cuda(position):
+            raise TypeError("push_steps needs CUDA float64 tensors (use push() for numpy arrays)")
+        if not _is_cuda(momentum) or momentum.device != position.device:
+            raise TypeError("position and momentum must live on the same CUDA device")
+        k = _push_consts(charge, mass, self.owner.clock.dt, self.c2)
+        p = _particles_struct(position, momentum)
+        dev = position.device
+        e = _FieldArg(E, "E", p.n, dev)
+        b = _FieldArg(B, "B", p.n, dev)
+        with _on_device(dev):
+            _lib.check(_lib.lib().tp_boris_push_steps_f64(C.byref(p), C.byref(k),
+                                                          C.c_void_p(e.ptr), e.mode, e.sn, e.sc,
+                                                          C.c_void_p(b.ptr), b.mode, b.sn, b.sc, steps, _stream_ptr(dev)))
+        return None
+
     # -- the fused path --------------------------------------------------------
     def gather_push(self, position, momentum, charge, mass, E_grid=None, B_grid=None,
                     axis=0, formula="interp", grid=None):
