@@ -1,0 +1,150 @@
+"""Seeded differential fuzzing of the two particle entry points against the oracle: random sizes (register
+path and TMA rings), layouts (SoA, C-order, strided views), field modes, grids (uniform / non-uniform,
+staged / L2), formulas, component subsets, axes, on-node and out-of-grid particles.  Bit for bit."""
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import M_E, Q_E, assert_bits_equal, make_grid, make_owner
+from oracle import boris as oboris
+from oracle import gather as ogather
+
+pytestmark = pytest.mark.gpu
+C_LIGHT = 2.9979e8
+
+
+def device_array(tp, a, kind):
+    """(n,3) numpy array -> CUDA tensor in one of the layouts the C ABI accepts"""
+    if kind == "soa":
+        return tp.to_soa(a)
+    if kind == "aos":
+        return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    wide = torch.zeros((a.shape[0], 5), dtype=torch.float64, device="cuda")      # padded rows: generic strides
+    wide[:, 1:4] = torch.from_numpy(a).cuda()
+    return wide[:, 1:4]
+
+
+def random_particles(rng, n):
+    pos = rng.uniform(0.0, 1.0, (n, 3))
+    scale = 10.0 ** rng.uniform(-3, 3)
+    mom = rng.normal(0, scale * M_E * C_LIGHT, (n, 3))
+    if n > 3:
+        mom[rng.integers(0, n, max(1, n // 50))] = 0.0
+        mom[rng.integers(0, n)] = 1e-200
+        mom[rng.integers(0, n)] = rng.normal(0, 1e-310, 3)                        # denormals
+    return pos, mom
+
+
+def random_field(rng, tp, n, name):
+    mode = rng.choice(["uni_np", "uni_dev", "uni_13", "pp_soa", "pp_aos", "pp_strided", "zero"])
+    amp = (10.0 ** rng.uniform(2, 7)) if name == "E" else (10.0 ** rng.uniform(-3, 1.5))
+    if mode == "zero":
+        v = np.zeros(3)
+        return v, v
+    if mode.startswith("uni"):
+        v = rng.normal(0, amp, 3)
+        dev = v if mode == "uni_np" else torch.from_numpy(v).cuda() if mode == "uni_dev" else torch.from_numpy(v.reshape(1, 3)).cuda()
+        return v, dev
+    v = rng.normal(0, amp, (n, 3))
+    return v, device_array(tp, v, mode[3:])
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_push(seed):
+    import turbopy_b200 as tp
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 3000)) if seed % 4 else int(rng.integers(148 * 480, 148 * 480 * 3))
+    dt = 10.0 ** rng.uniform(-14, -10)
+    tool = tp.BorisPush(make_owner(dt=dt), {"type": "BorisPush"})
+    pos0, mom0 = random_particles(rng, n)
+    layout = rng.choice(["soa", "aos", "strided"])
+    E, Ed = random_field(rng, tp, n, "E")
+    B, Bd = random_field(rng, tp, n, "B")
+    pos, mom = device_array(tp, pos0, layout), device_array(tp, mom0, layout)
+    steps = int(rng.integers(1, 4))
+    if rng.random() < 0.5:
+        tool.push_steps(pos, mom, Q_E, M_E, Ed, Bd, steps)
+    else:
+        for _ in range(steps):
+            tool.push(pos, mom, Q_E, M_E, Ed, Bd)
+    rp, rm = pos0.copy(), mom0.copy()
+    for _ in range(steps):
+        oboris.push_aos(rp, rm, Q_E, M_E, E, B, dt)
+    assert_bits_equal(pos.cpu().numpy(), rp, f"position (n={n}, {layout})")
+    assert_bits_equal(mom.cpu().numpy(), rm, f"momentum (n={n}, {layout})")
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_fuzz_gather_push(seed):
+    import turbopy_b200 as tp
+    rng = np.random.default_rng(5000 + seed)
+    ng = int(rng.choice([2, 3, 17, 30, 257, 1025, 4097, 9001, 70_001]))
+    formula = str(rng.choice(["A", "B", "C"]))
+    grid = make_grid(ng, float(rng.uniform(-2, 0)), float(rng.uniform(0.5, 3)))
+    if formula != "A" and ng > 3 and rng.random() < 0.3:                          # non-uniform coordinates
+        r = np.sort(rng.uniform(grid.r[0], grid.r[-1], ng))
+        r[0], r[-1] = grid.r[0], grid.r[-1]
+        if np.all(np.diff(r) > 0):
+            grid.r = r
+    n = int(rng.integers(1, 4000)) if seed % 3 else int(rng.integers(148 * 960, 148 * 960 * 2))
+    axis = int(rng.integers(0, 3))
+    dt = 10.0 ** rng.uniform(-14, -11)
+    tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+    pos0, mom0 = random_particles(rng, n)
+    span = grid.r[-1] - grid.r[0]
+    pos0[:, axis] = grid.r[0] + span * rng.uniform(0.0, 1.0, n)
+    k = max(1, n // 40)
+    pos0[rng.integers(0, n, k), axis] = grid.r[rng.integers(0, ng, k)]            # exactly on nodes (ends included)
+    outside = np.unique(rng.integers(0, n, max(1, n // 200))) if rng.random() < 0.5 else np.array([], dtype=np.int64)
+    pos0[outside, axis] = np.where(rng.random(len(outside)) < 0.5, grid.r[0] - span * 0.01, grid.r[-1] + span * 0.01)
+    comps = [None] * 6
+    for c in range(6):
+        if rng.random() < 0.6:
+            comps[c] = (1e5 if c < 3 else 1.0) * np.cos(rng.uniform(1, 9) * grid.r + rng.uniform(0, 6))
+    as_block = rng.random() < 0.5
+
+    def lower(three):
+        if all(c is None for c in three):
+            return None
+        if as_block:                                                              # (ng,3) generate_field(3) layout
+            return torch.from_numpy(np.stack([c if c is not None else np.zeros(ng) for c in three], axis=1)).cuda()
+        return tuple(None if c is None else torch.from_numpy(c).cuda() for c in three)
+
+    layout = rng.choice(["soa", "aos", "strided"])
+    pos, mom = device_array(tp, pos0, layout), device_array(tp, mom0, layout)
+    tool.gather_push(pos, mom, Q_E, M_E, E_grid=lower(comps[:3]), B_grid=lower(comps[3:]), axis=axis,
+                     formula={"A": "create_interpolator", "B": "interp", "C": "interp1d_nd"}[formula])
+    # oracle: status per particle from the coordinate alone; flagged particles stay untouched
+    probe = np.zeros(ng)
+    if formula == "A":
+        _, st = ogather.interp_a(pos0[:, axis], grid.r, grid.dr, probe, grid.r[0], grid.r[-1])
+    else:
+        _, st = (ogather.interp_b if formula == "B" else ogather.interp_c)(pos0[:, axis], grid.r, probe)
+    bad = st != 0
+    if bad.any():
+        with pytest.raises((ValueError, AssertionError)) as info:
+            tool.check_status()
+        assert int(re.match(r"(\d+) particle", str(info.value)).group(1)) == int(bad.sum())
+        assert f"first index {int(np.flatnonzero(bad)[0])}" in str(info.value)
+    else:
+        tool.check_status()
+    good = ~bad
+    F = []
+    for y in comps:
+        if y is None or (as_block is False and y is None):
+            F.append(np.zeros(int(good.sum())))
+            continue
+        if formula == "A":
+            v, s2 = ogather.interp_a(pos0[good, axis], grid.r, grid.dr, y, grid.r[0], grid.r[-1])
+        else:
+            v, s2 = (ogather.interp_b if formula == "B" else ogather.interp_c)(pos0[good, axis], grid.r, y)
+        assert (s2 == 0).all()
+        F.append(v)
+    rp, rm = pos0[good].copy(), mom0[good].copy()
+    oboris.push_aos(rp, rm, Q_E, M_E, np.stack(F[:3], axis=1), np.stack(F[3:], axis=1), dt)
+    gp, gm = pos.cpu().numpy(), mom.cpu().numpy()
+    assert_bits_equal(gp[good], rp, f"position (ng={ng}, n={n}, {formula}, {layout})")
+    assert_bits_equal(gm[good], rm, f"momentum (ng={ng}, n={n}, {formula}, {layout})")
+    assert_bits_equal(gp[bad], pos0[bad]); assert_bits_equal(gm[bad], mom0[bad])
