@@ -45,34 +45,50 @@ __device__ __forceinline__ void block_sum(double (&v)[kRedVals], double* out) {
     }
 }
 
-__device__ __forceinline__ void accumulate(double px, double py, double pz, double mass, double mm,
-                                           double c2, double (&acc)[kRedVals]) {
+struct MomConsts { double mass, mm, c2, rc2; int fast_ok; };
+
+// FAST: shared-reciprocal quotients and the branch-free sqrt of common.cuh -- the same bits as the IEEE
+// operations whenever the thread's guard stays clean (checked once, after the loop).
+template <bool FAST>
+__device__ __forceinline__ void accumulate(double px, double py, double pz, const MomConsts& k, Guard& g,
+                                           double (&acc)[kRedVals]) {
     const double p2 = (px * px + py * py) + pz * pz;
-    const double m1 = sqrt(mm + p2 / c2);
-    acc[0] += p2 / (m1 + mass);
+    const double m1 = root<FAST>(k.mm + quot<FAST>(p2, const_recip<FAST>(k.c2, k.rc2), g), g);
+    acc[0] += quot<FAST>(p2, make_recip<FAST>(m1 + k.mass, g), g);
     acc[1] += px; acc[2] += py; acc[3] += pz; acc[4] += p2;
 }
 
-__global__ void __launch_bounds__(kRedThreads) moments_partial_kernel(const double* __restrict__ mom, int64_t sn,
-                                                                      int64_t sc, int64_t n, double mass, double mm,
-                                                                      double c2, bool vec, double* scratch) {
-    double acc[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
+template <bool FAST>
+__device__ __forceinline__ bool moments_thread(const double* __restrict__ mom, int64_t sn, int64_t sc, int64_t n,
+                                               const MomConsts& k, bool vec, double (&acc)[kRedVals]) {
+#pragma unroll
+    for (int v = 0; v < kRedVals; ++v) acc[v] = 0.0;
+    Guard g;
     const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kRedThreads + threadIdx.x;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * kRedThreads;
     if (vec) {                                            // SoA, 128-bit loads
         const int64_t npairs = n >> 1;
         for (int64_t pr = gtid; pr < npairs; pr += gstride) {
             const double2 a = ld2(mom + 2 * pr), b = ld2(mom + sc + 2 * pr), c = ld2(mom + 2 * sc + 2 * pr);
-            accumulate(a.x, b.x, c.x, mass, mm, c2, acc);
-            accumulate(a.y, b.y, c.y, mass, mm, c2, acc);
+            accumulate<FAST>(a.x, b.x, c.x, k, g, acc);
+            accumulate<FAST>(a.y, b.y, c.y, k, g, acc);
         }
-        if ((n & 1) && gtid == 0) accumulate(mom[n - 1], mom[sc + n - 1], mom[2 * sc + n - 1], mass, mm, c2, acc);
+        if ((n & 1) && gtid == 0) accumulate<FAST>(mom[n - 1], mom[sc + n - 1], mom[2 * sc + n - 1], k, g, acc);
     } else {
         for (int64_t i = gtid; i < n; i += gstride) {
             const double* p = mom + i * sn;
-            accumulate(p[0], p[sc], p[2 * sc], mass, mm, c2, acc);
+            accumulate<FAST>(p[0], p[sc], p[2 * sc], k, g, acc);
         }
     }
+    return !FAST || (guard_ok(g) && k.fast_ok);
+}
+
+__global__ void __launch_bounds__(kRedThreads, 4) moments_partial_kernel(const double* __restrict__ mom, int64_t sn,
+                                                                      int64_t sc, int64_t n, const MomConsts k,
+                                                                      bool vec, double* scratch) {
+    double acc[kRedVals];
+    if (!moments_thread<true>(mom, sn, sc, n, k, vec, acc))      // some operand left the fast path's range:
+        moments_thread<false>(mom, sn, sc, n, k, vec, acc);      // redo this thread's share with IEEE operations
     block_sum(acc, scratch + static_cast<int64_t>(blockIdx.x) * 8);
 }
 
@@ -118,8 +134,10 @@ extern "C" int tp_reduce_moments_f64(const double* mom, int64_t stride_n, int64_
     if (blocks > full) blocks = full;
     if (blocks > kRedMaxBlocks) blocks = kRedMaxBlocks;
     if (blocks < 1) blocks = 1;
-    moments_partial_kernel<<<static_cast<int>(blocks), kRedThreads, 0, s>>>(mom, stride_n, stride_c, n, mass, mass_sq, c2,
-                                                                          vec, scratch);
+    MomConsts k;
+    k.mass = mass; k.mm = mass_sq; k.c2 = c2; k.rc2 = 1.0 / c2;
+    k.fast_ok = const_divisor_ok(c2) ? 1 : 0;
+    moments_partial_kernel<<<static_cast<int>(blocks), kRedThreads, 0, s>>>(mom, stride_n, stride_c, n, k, vec, scratch);
     moments_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, static_cast<int>(blocks), n, out8);
     count_launch(2);
     return static_cast<int>(cudaGetLastError());
