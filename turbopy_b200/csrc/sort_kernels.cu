@@ -20,7 +20,9 @@
 //   K2  row scans + digit bases       exclusive scan in (digit, warp) order
 //   K3  stable scatter of indices     out[dst] = in[i]   (warp match_any ranking, in order)
 // then  K4  per component: tmp[i] = a[perm[i]];  K5  a[i] = tmp[i].
-// Keys are recomputed from x in every kernel instead of being stored.
+// Keys are recomputed from x in every kernel instead of being stored.  Measured alternatives (16 Mi particles):
+// 10-bit digits with 6 CTAs per SM are slower (1.41 vs 1.00 ms for the scatters: the strided per-warp rows of the
+// count matrix grow), as is gathering the three components of an array in one kernel (see K4 below).
 #include "common.cuh"
 
 #include <algorithm>
@@ -29,7 +31,9 @@ namespace tp {
 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortMaxBins = 4096;
+constexpr int kSortDigitBits = 12;
+constexpr int kSortMaxBins = 1 << kSortDigitBits;
+constexpr int kSortCtasPerSm = 1;
 
 struct SortArgs {
     const double* x;            // the coordinate the gather runs along
@@ -64,7 +68,17 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const __grid_co
     const int64_t w = static_cast<int64_t>(blockIdx.x) * kSortWarps + warp;
     if (w >= a.nwarps) return;
     const int64_t lo = w * a.chunk, hi = min(a.n, lo + a.chunk);
-    for (int64_t i = lo + lane; i < hi; i += 32) atomicAdd(&mine[bin_of(a, a.x[source_of(a, i) * a.sn])], 1u);
+    for (int64_t i0 = lo + lane; i0 < hi; i0 += 32 * 4) {        // four independent (perm ->) x loads in flight per lane
+        int64_t src[4];
+        double xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) src[u] = i0 + 32 * u < hi ? source_of(a, i0 + 32 * u) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = a.x[src[u] * a.sn];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + 32 * u < hi) atomicAdd(&mine[bin_of(a, xv[u])], 1u);
+    }
     __syncwarp();
     for (int b = lane; b < a.nbins; b += 32) a.counts[static_cast<int64_t>(b) * a.nwarps + w] = mine[b];
 }
@@ -134,22 +148,35 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const __grid
     for (int b = lane; b < a.nbins; b += 32) mine[b] = a.bin_base[b] + a.counts[static_cast<int64_t>(b) * a.nwarps + w];
     __syncwarp();
     const int64_t lo = w * a.chunk, hi = min(a.n, lo + a.chunk);
-    for (int64_t base = lo; base < hi; base += 32) {           // chunk is a multiple of 32: whole warp iterates together
-        const int64_t i = base + lane;
-        const bool live = i < hi;
-        const int64_t src = live ? source_of(a, i) : 0;
-        const int b = live ? bin_of(a, a.x[src * a.sn]) : -1 - lane;   // dead lanes: unique keys, matched with nobody
-        const unsigned peers = __match_any_sync(0xffffffffu, b);
-        const int leader = __ffs(peers) - 1;
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        uint32_t slot = 0;
-        if (live && lane == leader) {                           // one lane per distinct bin: no two leaders share a counter
-            slot = mine[b];
-            mine[b] = slot + __popc(peers);
+    constexpr int kAhead = 4;                                    // iterations whose (dependent) loads are issued together
+    for (int64_t group = lo; group < hi; group += 32 * kAhead) {  // chunk is a multiple of 32: whole warp iterates together
+        int64_t src[kAhead];
+        double xv[kAhead];
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            const int64_t i = group + 32 * u + lane;
+            src[u] = i < hi ? source_of(a, i) : 0;
         }
-        slot = __shfl_sync(0xffffffffu, slot, leader);
-        if (live) a.perm[static_cast<int64_t>(slot) + rank] = src;
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) xv[u] = a.x[src[u] * a.sn];        // src = 0 for dead lanes: a valid address
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            const int64_t i = group + 32 * u + lane;
+            if (group + 32 * u >= hi) break;                     // warp-uniform
+            const bool live = i < hi;
+            const int b = live ? bin_of(a, xv[u]) : -1 - lane;   // dead lanes: unique keys, matched with nobody
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            const int leader = __ffs(peers) - 1;
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t slot = 0;
+            if (live && lane == leader) {                        // one lane per distinct bin: no two leaders share a counter
+                slot = mine[b];
+                mine[b] = slot + __popc(peers);
+            }
+            slot = __shfl_sync(0xffffffffu, slot, leader);
+            if (live) a.perm[static_cast<int64_t>(slot) + rank] = src[u];
+            __syncwarp();
+        }
     }
 }
 
@@ -180,9 +207,9 @@ static int plan_sort(int64_t n, int64_t ncells, int cells_per_bin_log2, SortPlan
     pl.shift = cells_per_bin_log2;
     pl.nkeys = ((ncells - 1) >> pl.shift) + 1;
     pl.passes = 1;
-    while ((pl.nkeys - 1) >> (12 * pl.passes)) ++pl.passes;
+    while ((pl.nkeys - 1) >> (kSortDigitBits * pl.passes)) ++pl.passes;
     const DeviceProps& d = device_props();
-    const int64_t want = static_cast<int64_t>(std::max(d.sm_count, 1)) * kSortWarps;     // one CTA per SM
+    const int64_t want = static_cast<int64_t>(std::max(d.sm_count, 1)) * kSortWarps * kSortCtasPerSm;
     int64_t chunk = (std::max<int64_t>(n, 1) + want - 1) / want;
     chunk = std::max<int64_t>(1024, (chunk + 31) / 32 * 32);
     pl.chunk = chunk;
@@ -232,7 +259,7 @@ extern "C" int tp_sort_by_cell_f64(const tp_particles* p, int axis, double r_fir
     const int blocks = static_cast<int>((pl.nwarps + kSortWarps - 1) / kSortWarps);
     const int64_t* current = nullptr;
     for (int pass = 0; pass < pl.passes; ++pass) {
-        a.digit_shift = 12 * pass;
+        a.digit_shift = kSortDigitBits * pass;
         a.nbins = static_cast<int>(std::min<int64_t>(((pl.nkeys - 1) >> a.digit_shift) + 1, kSortMaxBins));
         a.in_perm = current;
         a.perm = (pass & 1) ? perm_b : perm_a;
@@ -253,6 +280,8 @@ extern "C" int tp_sort_by_cell_f64(const tp_particles* p, int axis, double r_fir
     for (int arr = 0; arr < 2; ++arr) {
         double* ptr = arr ? p->mom : p->pos;
         const int64_t sn = arr ? p->mom_stride_n : p->pos_stride_n, sc = arr ? p->mom_stride_c : p->pos_stride_c;
+        // one component at a time: its 134 MB-per-16-Mi source plane is re-read from L2 by the three other particles of
+        // each 32-byte sector (gathering the three planes in one kernel thrashes L2: measured 1.5x slower)
         for (int c = 0; c < 3; ++c) {
             permute_gather_kernel<<<pblocks, 256, 0, s>>>(ptr + c * sc, sn, current, tmp, p->n);
             permute_copy_kernel<<<pblocks, 256, 0, s>>>(tmp, ptr + c * sc, sn, p->n);
