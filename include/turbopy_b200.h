@@ -133,6 +133,13 @@ int tp_boris_push_steps_f64(const tp_particles* p, const tp_push_consts* k,
 int tp_gather_push_f64(const tp_particles* p, const tp_push_consts* k,
                        const tp_grid_fields* g, int axis, int formula,
                        uint64_t* status, tp_stream_t stream);
+/* nsteps consecutive gather+push steps on UNCHANGED grid fields (a static field map) in one
+ * pass over the particles: bit-identical to nsteps calls of tp_gather_push_f64, 96/nsteps
+ * bytes of traffic per push.  A particle that leaves the grid during the pass is flagged
+ * once and keeps the state it had when it left (what the remaining single-step calls would
+ * have done: leave it untouched). */
+int tp_gather_push_steps_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g,
+                             int axis, int formula, int nsteps, uint64_t* status, tp_stream_t stream);
 int tp_status_reset(uint64_t* status, tp_stream_t stream);
 /* shared-memory bytes the staged variant would need; *staged = 1 if it fits */
 int tp_gather_smem_bytes(const tp_grid_fields* g, int64_t* bytes, int* staged);

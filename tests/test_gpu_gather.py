@@ -257,3 +257,41 @@ def test_fused_host_path(tp):
     pos[5, 0] = 2.0
     with pytest.raises(ValueError):
         tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=None)
+
+
+@pytest.mark.parametrize("formula", ["A", "B", "C"])
+@pytest.mark.parametrize("ng,n", [(30, 3001), (1025, 148 * 960 * 2 + 55), ((1 << 17) + 1, 148 * 960 + 9)])
+def test_gather_push_steps_equals_repeated_calls(tp, formula, ng, n):
+    """gather_push_steps(K) == K x gather_push on static grid fields, bit for bit (register path, staged ring,
+    L2 records), including particles that walk off the grid during the pass: they are flagged and keep the
+    state they left with -- exactly what K single-step calls leave behind."""
+    grid = make_grid(ng)
+    dt, K = 2e-11, 5
+    tool_a = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+    tool_b = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+    pos0, mom0 = thermal_ensemble(n, seed=ng + 11)
+    pos0[:, 0] = np.random.default_rng(ng).uniform(0.05, 0.95, n)
+    fast = np.arange(3, n, max(7, n // 40))                       # relativistic particles heading for the right edge
+    pos0[fast, 0] = 0.995
+    mom0[fast] = 0.0
+    mom0[fast, 0] = 30.0 * M_E * 2.9979e8
+    comps = smooth_fields(grid)
+    E = torch.from_numpy(np.stack(comps[:3], axis=1)).cuda()
+    B = torch.from_numpy(np.stack(comps[3:], axis=1)).cuda()
+    name = {"A": "create_interpolator", "B": "interp", "C": "interp1d_nd"}[formula]
+    pa, ma = tp.to_soa(pos0), tp.to_soa(mom0)
+    pb, mb = tp.to_soa(pos0), tp.to_soa(mom0)
+    tool_a.gather_push_steps(pa, ma, Q_E, M_E, K, E_grid=E, B_grid=B, formula=name)
+    left = 0
+    for _ in range(K):
+        tool_b.gather_push(pb, mb, Q_E, M_E, E_grid=E, B_grid=B, formula=name)
+        try:
+            tool_b.check_status()
+        except (ValueError, AssertionError):
+            left += 1
+    assert left > 0                                               # the fast particles did leave during the pass
+    assert_bits_equal(pa.cpu().numpy(), pb.cpu().numpy(), "position")
+    assert_bits_equal(ma.cpu().numpy(), mb.cpu().numpy(), "momentum")
+    gone = (pb.cpu().numpy()[:, 0] > 1.0)
+    with pytest.raises((ValueError, AssertionError), match=f"{int(gone.sum())} particle"):
+        tool_a.check_status()

@@ -14,7 +14,7 @@
 namespace tp {
 
 int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
-                       int formula, uint64_t* status, cudaStream_t s);
+                       int formula, uint64_t* status, cudaStream_t s, int nsteps);
 
 namespace {
 
@@ -205,7 +205,7 @@ extern "C" int tp_gather_push_host_f64(const tp_particles* p, const tp_push_cons
     if (p->n > 0) {
         rc = run_chunks(p, nullptr, false, nullptr, false,
                         [&](const tp_particles& dp, double*, int64_t, cudaStream_t s) {
-                            return gather_push_device(&dp, k, &dg, axis, formula, c.status_dev, s);
+                            return gather_push_device(&dp, k, &dg, axis, formula, c.status_dev, s, 1);
                         });
         if (rc) return rc;
     }

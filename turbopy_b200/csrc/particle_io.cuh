@@ -60,6 +60,7 @@ struct GatherArgs {
     uint32_t comp_smem_off[6];
     unsigned long long* status;
     const double* records;      // packed 64-byte node records (gather mode 2), else nullptr
+    int nsteps;                 // consecutive gather+push steps on unchanged grid fields per visit of a particle (>= 1)
 };
 
 // ---------------------------------------------------------------------------

@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) push_kernel(const __g
     }
 }
 
-// Generic particle: straight-line gather + push, validity in the return value.
+// Generic particle: ONE straight-line gather + push step, validity in the return value.  A wrong cell guess or
+// a particle that is off the grid makes it false; the clamped index keeps the loads in bounds.  Multi-step passes
+// (GatherArgs::nsteps) loop around this at the call sites, both particles of a thread inside one iteration, so
+// that the two independent dependency chains stay interleaved.
 template <int FORMULA>
 __device__ __forceinline__ bool gather_step_fast(const GatherArgs& a, const GridView& g, Vec3& x, Vec3& p) {
     double F[6];
@@ -112,6 +115,14 @@ __device__ __forceinline__ bool gather_step_fast_records(const GatherArgs& a, co
     E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
     boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
     return ok && guard_ok(gd) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+}
+
+// nsteps steps of one particle (scalar tails)
+template <int FORMULA>
+__device__ __forceinline__ bool gather_steps_fast(const GatherArgs& a, const GridView& g, Vec3& x, Vec3& p) {
+    bool ok = true;
+    for (int s = 0; s < a.nsteps; ++s) ok = gather_step_fast<FORMULA>(a, g, x, p) && ok;
+    return ok;
 }
 
 __device__ __forceinline__ RecView make_rec_view(const GatherArgs& a, int keep_in_l2) {
@@ -146,26 +157,28 @@ __global__ void __launch_bounds__(256) pack_nodes_kernel(const __grid_constant__
 // passing the hot loop's view or particle registers by reference would force
 // them into local memory (LDL/STL in the hot loop, profiles/r1_v3).
 template <int FORMULA>
-__device__ __forceinline__ bool exact_core(const GatherArgs& a, const GridView& g, int64_t i, Vec3& x, Vec3& p) {
+__device__ __forceinline__ void exact_core(const GatherArgs& a, const GridView& g, int64_t i, Vec3& x, Vec3& p) {
     load_one(a.p, i, x, p);
-    double F[6];
-    const unsigned st = gather6_exact<FORMULA>(g, axis_of(x, a.axis), F);
-    if (st != 0u) {
-        flag_particle(a.status, i, st);
-        return false;
+    for (int s = 0; s < a.nsteps; ++s) {
+        double F[6];
+        const unsigned st = gather6_exact<FORMULA>(g, axis_of(x, a.axis), F);
+        if (st != 0u) {                 // off the grid: flagged, keeps the state it had when it left (the input if s == 0)
+            flag_particle(a.status, i, st);
+            return;
+        }
+        Vec3 E, B;
+        E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
+        Guard gd;
+        boris_step<false>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
     }
-    Vec3 E, B;
-    E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
-    Guard gd;
-    boris_step<false>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
-    return true;
 }
 
 template <int FORMULA, bool STAGED>
 __device__ __noinline__ void gather_step_exact(const GatherArgs& a, unsigned char* smem, int64_t i) {
     const GridView g = make_view<STAGED>(a, smem);
     Vec3 x, p;
-    if (exact_core<FORMULA>(a, g, i, x, p)) store_one(a.p, i, x, p);
+    exact_core<FORMULA>(a, g, i, x, p);
+    store_one(a.p, i, x, p);            // a flagged particle stores back what it held (bit-identical to untouched for one step)
 }
 
 // ---------------------------------------------------------------------------
@@ -189,8 +202,11 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) gather_push_kernel(co
         while (pr < npairs) {
             const int64_t i = pr * 2;
             prefetch_tile(a.p, (pr - threadIdx.x + TP_PF_DIST * gstride) * 2, npairs * 2);
-            const bool ok0 = gather_step_fast<FORMULA>(a, g, x[0], p[0]);
-            const bool ok1 = gather_step_fast<FORMULA>(a, g, x[1], p[1]);
+            bool ok0 = true, ok1 = true;
+            for (int st = 0; st < a.nsteps; ++st) {
+                ok0 = gather_step_fast<FORMULA>(a, g, x[0], p[0]) && ok0;
+                ok1 = gather_step_fast<FORMULA>(a, g, x[1], p[1]) && ok1;
+            }
             if (__builtin_expect(ok0 && ok1, 1)) {
                 store_pair(a.p, i, x, p);
             } else {
@@ -207,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) gather_push_kernel(co
         if (i < a.p.n) load_one(a.p, i, x, p);
         if (STAGED) stage_wait(smem);
         while (i < a.p.n) {
-            if (__builtin_expect(gather_step_fast<FORMULA>(a, g, x, p), 1)) store_one(a.p, i, x, p);
+            if (__builtin_expect(gather_steps_fast<FORMULA>(a, g, x, p), 1)) store_one(a.p, i, x, p);
             else gather_step_exact<FORMULA, STAGED>(a, smem, i);
             i += gstride;
             if (i < a.p.n) load_one(a.p, i, x, p);
@@ -226,7 +242,7 @@ __device__ __noinline__ void gather_step_exact_slot(const GatherArgs& a, unsigne
                                                     double* ps, int pitch) {
     const GridView g = make_view<STAGED>(a, smem);
     Vec3 x, p;
-    exact_core<FORMULA>(a, g, i, x, p);          // flagged: x, p hold the untouched input
+    exact_core<FORMULA>(a, g, i, x, p);          // flagged: x, p hold the state the particle left the grid with
     slot_write(xs, ps, pitch, x, p);
 }
 
@@ -732,11 +748,14 @@ static int launch_interp_nc(const InterpArgs& a, size_t smem, cudaStream_t s) {
 
 // Entry point shared with host_path.cu
 int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
-                       int formula, uint64_t* status, cudaStream_t s) {
+                       int formula, uint64_t* status, cudaStream_t s, int nsteps) {
     const DeviceProps& d = device_props();
     if (d.status != TP_OK) return d.status;
+    if (nsteps < 0) return TP_E_ARG;
+    if (nsteps == 0) return TP_OK;
     GatherArgs a;
     std::memset(&a, 0, sizeof(a));
+    a.nsteps = nsteps;
     bool vec2 = false, aos16 = false;
     int rc = fill_particles(p, a.p, vec2, &aos16);
     if (rc) return rc;
@@ -749,7 +768,10 @@ int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_
     a.status = reinterpret_cast<unsigned long long*>(status);
     if (a.p.n == 0) return TP_OK;
     if (formula < TP_INTERP_A || formula > TP_INTERP_C) return TP_E_MODE;
-    if (vec2 || aos16) {
+    // Multi-step passes are fp64-bound, not HBM-bound: they run on the register-path kernel (whose step loop
+    // sits around the pair of particles) and leave the single-step TMA kernel free of a runtime loop, which
+    // costs it 3 % (measured: 66.6 -> 64.2 G pushes/s on the headline configuration).
+    if ((vec2 || aos16) && a.nsteps == 1) {
         bool launched = false;
         if ((rc = try_gather_push_tma(a, formula, smem, staged, aos16, s, launched))) return rc;
         if (launched) return TP_OK;
@@ -849,7 +871,12 @@ extern "C" int tp_boris_push_steps_f64(const tp_particles* p, const tp_push_cons
 
 extern "C" int tp_gather_push_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
                                   int formula, uint64_t* status, tp_stream_t stream) {
-    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream));
+    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), 1);
+}
+
+extern "C" int tp_gather_push_steps_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
+                                        int formula, int nsteps, uint64_t* status, tp_stream_t stream) {
+    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), nsteps);
 }
 
 extern "C" int tp_status_reset(uint64_t* status, tp_stream_t stream) {

@@ -378,8 +378,22 @@ class BorisPush(ComputeTool):
         return None
 
     # -- the fused path --------------------------------------------------------
+    def gather_push_steps(self, position, momentum, charge, mass, steps, E_grid=None, B_grid=None,
+                          axis=0, formula="interp", grid=None):
+        """``steps`` consecutive :meth:`gather_push` calls on unchanged grid fields (a
+        static field map) in one pass over the particles: bit-identical to calling
+        :meth:`gather_push` ``steps`` times, with one read and one write of the
+        particle state.  A particle that leaves the grid during the pass is flagged
+        once and keeps the state it left with.  CUDA tensors only (additive)."""
+        if not _is_cuda(position):
+            raise TypeError("gather_push_steps needs CUDA float64 tensors")
+        steps = int(steps)
+        if steps < 0:
+            raise ValueError("steps must be >= 0")
+        return self.gather_push(position, momentum, charge, mass, E_grid, B_grid, axis, formula, grid, _steps=steps)
+
     def gather_push(self, position, momentum, charge, mass, E_grid=None, B_grid=None,
-                    axis=0, formula="interp", grid=None):
+                    axis=0, formula="interp", grid=None, _steps=None):
         """Gather E and B at ``position[:, axis]`` by linear interpolation of the
         grid fields and push, in one kernel.
 
@@ -417,8 +431,12 @@ class BorisPush(ComputeTool):
             if status is None:
                 status = self._status[dev] = GatherStatus(dev)
             with _on_device(dev):
-                _lib.check(lib.tp_gather_push_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
-                                                  C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
+                if _steps is None:
+                    _lib.check(lib.tp_gather_push_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
+                                                      C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
+                else:
+                    _lib.check(lib.tp_gather_push_steps_f64(C.byref(p), C.byref(k), C.byref(g), axis, code, _steps,
+                                                            C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
             return None
         if isinstance(position, np.ndarray):
             r = np.ascontiguousarray(grid.r, dtype=np.float64)
