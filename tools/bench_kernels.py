@@ -130,6 +130,15 @@ def main():
         tool.check_status()
         add(f"gather+push ng={ng} comps={ncomp} formula={formula}", n16, 96, t,
             "grid in L2 (not staged)" if ng > 5000 else "grid staged in smem by TMA")
+    # static field map: K fused gather+push steps per pass
+    ow = owner_for(4097, dt=1e-13)
+    tool = tp.BorisPush(ow, {"type": "BorisPush"})
+    r = torch.from_numpy(ow.grid.r).cuda()
+    Es = (None, torch.cos(6.28 * r), None)
+    pos.copy_(0.05 + 0.9 * torch.rand((n16, 3), dtype=torch.float64, device="cuda")); mom.zero_()
+    t = timed(lambda: tool.gather_push_steps(pos, mom, Q_E, M_E, 16, E_grid=Es), max(3, it // 8))
+    tool.check_status()
+    add("gather_push_steps: 16 steps per pass (static E_y map, ng=4097)", n16 * 16, 96, t, "fp64 / shared-memory bound, not on the HBM roofline")
     # sorted particles on the big grid (cell-coherent gathers)
     ow = owner_for((1 << 20) + 1, dt=1e-13)
     tool = tp.BorisPush(ow, {"type": "BorisPush"})
