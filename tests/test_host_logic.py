@@ -133,3 +133,36 @@ def test_interpolate1d_rejects_splines_without_device():
     tool = tp.Interpolators(make_owner(), {"type": "Interpolators"})
     with pytest.raises(NotImplementedError):
         tool.interpolate1D(np.arange(4.0), np.arange(4.0), "cubic")
+
+
+def test_additive_apis_validate_before_touching_the_device():
+    """push_steps / gather_push_steps / sort_by_cell are CUDA-tensor-only additions: host arrays, bad step counts and
+    bad axes are rejected by the Python layer (no device, no library call needed), and the C ABI rejects bad
+    arguments of the new entry points without a device."""
+    import ctypes as C
+
+    import torch
+
+    import turbopy_b200 as tp
+    from turbopy_b200 import _lib
+    tool = tp.BorisPush(make_owner(), {"type": "BorisPush"})
+    pos, mom = np.zeros((4, 3)), np.zeros((4, 3))
+    with pytest.raises(TypeError):
+        tool.push_steps(pos, mom, 1.0, 1.0, np.zeros(3), np.zeros(3), 3)
+    with pytest.raises(ValueError):
+        tool.push_steps(pos, mom, 1.0, 1.0, np.zeros(3), np.zeros(3), -1)
+    with pytest.raises(TypeError):
+        tool.gather_push_steps(pos, mom, 1.0, 1.0, 2)
+    with pytest.raises(TypeError):
+        tp.sort_by_cell(torch.zeros((4, 3), dtype=torch.float64), torch.zeros((4, 3), dtype=torch.float64),
+                        make_owner().grid)
+    L = _lib.lib()
+    assert L.tp_sort_scratch_bytes(-1, 10, 0) == -1 and L.tp_sort_scratch_bytes(10, 0, 0) == -1
+    assert L.tp_sort_scratch_bytes(1 << 33, 10, 0) == -1 and L.tp_sort_scratch_bytes(10, 10, 41) == -1
+    assert L.tp_sort_scratch_bytes(1000, 1 << 20, 0) > 2 * 8 * 1000        # two permutations + one scratch plane + counts
+    assert L.tp_poisson_scratch_doubles(2048 * 3 + 1) == 2 * 4 + 8
+    if not torch.cuda.is_available():
+        p = _lib.Particles(0, 1, 1, 0, 1, 1, 0)
+        k = _lib.PushConsts(1.0, 1.0, 1.0, 1.0)
+        assert L.tp_boris_push_steps_f64(C.byref(p), C.byref(k), None, 0, 0, 0, None, 0, 0, 0, 3, None) == _lib.TP_E_NODEVICE
+        assert L.tp_permute_f64(None, 1, 0, None, None, None) == _lib.TP_E_NODEVICE
