@@ -215,6 +215,11 @@ int tp_gather_push_host_f64(const tp_particles* p_host, const tp_push_consts* k,
                             const tp_grid_fields* g_host, int axis, int formula,
                             uint64_t* status_host);
 /* bytes moved by the last host call (for bench.py's e2e accounting) */
+/* Page-lock (cudaHostRegister) / unlock a caller-owned host range so that the host entry points above copy it by
+ * asynchronous DMA.  Already page-locked memory is accepted as is.  The caller keeps the range alive and unpins it
+ * before freeing it.  Returns 0, a cudaError_t (not fatal: unpinned arrays still work, slower) or TP_E_*. */
+int tp_host_pin(void* ptr, int64_t bytes);
+int tp_host_unpin(void* ptr);
 int tp_host_last_transfer(int64_t* h2d_bytes, int64_t* d2h_bytes);
 int tp_host_release(void);        /* free the internal staging buffers/streams */
 

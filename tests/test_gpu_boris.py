@@ -329,3 +329,44 @@ def test_push_steps_equals_repeated_push(tp, layout, fields, n):
     assert_bits_equal(pa.cpu().numpy(), pb.cpu().numpy())
     with pytest.raises(ValueError):
         tool.push_steps(pa, ma, Q_E, M_E, Ed, Bd, -1)
+
+
+def test_host_path_pins_numpy_arrays_for_their_lifetime(tp):
+    """The host path page-locks the ndarray that owns the particle memory the second time it sees it and unpins
+    it when that array dies (weakref finalizer), so freshly allocated arrays at recycled addresses are pinned
+    afresh and the results stay exact; views share their owner's registration; small and foreign buffers are
+    left alone."""
+    import gc
+
+    from turbopy_b200 import tools
+    dt = 1e-12
+    tool = pusher(tp, dt)
+    E, B = np.array([3e4, 1e5, -2e4]), np.array([0.5, -0.25, 1.0])
+    n = 400_000                                               # 9.6 MB per array: above the pinning threshold
+    gc.collect()
+    base = len(tools._pinned)
+    states = lambda: sorted(str(st) for _, st in tools._pinned.values())   # noqa: E731
+    for round_ in range(3):
+        pos0, mom0 = thermal_ensemble(n, seed=40 + round_)
+        pos, mom = pos0.copy(), mom0.copy()
+        tool.push(pos, mom, Q_E, M_E, E, B)
+        assert len(tools._pinned) == base + 2 and states().count("None") == 2       # seen once: not pinned yet
+        tool.push(pos[:1000], mom[:1000], Q_E, M_E, E, B)     # a view: same owners, second sight -> pinned
+        assert len(tools._pinned) == base + 2 and states().count("True") == 2
+        tool.push(pos, mom, Q_E, M_E, E, B)
+        rp, rm = pos0.copy(), mom0.copy()
+        oboris.push_aos(rp, rm, Q_E, M_E, E, B, dt)
+        oboris.push_aos(rp[:1000], rm[:1000], Q_E, M_E, E, B, dt)
+        oboris.push_aos(rp, rm, Q_E, M_E, E, B, dt)
+        assert_bits_equal(pos, rp); assert_bits_equal(mom, rm)
+        del pos, mom
+        gc.collect()
+        assert len(tools._pinned) == base                     # unpinned / forgotten with their owners
+    small = np.zeros((10, 3)); tool.push(small, small.copy(), Q_E, M_E, E, B)
+    assert len(tools._pinned) == base
+    buf = bytearray(8 * 3 * n)
+    foreign = np.frombuffer(buf, dtype=np.float64).reshape(n, 3)
+    own = np.zeros((n, 3))
+    tool.push(foreign, own, Q_E, M_E, E, B)                    # memory owned by a bytearray: never pinned
+    tool.push(foreign, own, Q_E, M_E, E, B)
+    assert len(tools._pinned) == base + 1 and states().count("True") == 1

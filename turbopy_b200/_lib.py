@@ -78,6 +78,8 @@ SIGNATURES = {
     "tp_gather_push_host_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts), C.POINTER(GridFields),
                                           C.c_int, C.c_int, c_u64_p]),
     "tp_host_last_transfer": (C.c_int, [c_i64_p, c_i64_p]),
+    "tp_host_pin": (C.c_int, [C.c_void_p, C.c_int64]),
+    "tp_host_unpin": (C.c_int, [C.c_void_p]),
     "tp_host_release": (C.c_int, []),
     "tp_plane_wave_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
