@@ -178,3 +178,32 @@ def test_fuzz_finite_difference(seed):
             got = (getattr(tool, name)() @ yd).cpu().numpy()
             assert_bits_equal(nn(got), nn(ofd.dia_apply(data, offsets, y)), f"{name} n={n} off={off}")
     assert float(buf[:off].abs().sum()) == 0.0 and float(buf[off + n:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_non_finite_inputs_follow_ieee_like_numpy(layout):
+    """Infinite / NaN momenta, positions and fields take the recovery path (plain IEEE operations in the
+    reference's order): the same entries come out NaN / +-inf as in numpy, every finite entry bit-identical.
+    (NaN sign and payload are not compared: x86 and the GPU produce different default NaNs.)"""
+    import turbopy_b200 as tp
+    rng = np.random.default_rng(77)
+    n = 148 * 480 * 2 + 91
+    dt = 1e-12
+    tool = tp.BorisPush(make_owner(dt=dt), {"type": "BorisPush"})
+    pos0, mom0 = random_particles(rng, n)
+    E = rng.normal(0, 1e5, (n, 3)); B = rng.normal(0, 1.0, (n, 3))
+    idx = rng.choice(n, 600, replace=False)
+    specials = [np.inf, -np.inf, np.nan, 1e308, -1e308, 5e-324, 0.0, -0.0]
+    for k, i in enumerate(idx):
+        target = (mom0, pos0, E, B)[k % 4]
+        target[i, (k // 4) % 3] = specials[(k // 12) % len(specials)]
+    pos, mom = device_array(tp, pos0, layout), device_array(tp, mom0, layout)
+    tool.push(pos, mom, Q_E, M_E, device_array(tp, E, "aos"), device_array(tp, B, "aos"))
+    rp, rm = pos0.copy(), mom0.copy()
+    with np.errstate(all="ignore"):
+        oboris.push_aos(rp, rm, Q_E, M_E, E, B, dt)
+    for got, want, what in ((pos.cpu().numpy(), rp, "position"), (mom.cpu().numpy(), rm, "momentum")):
+        assert np.array_equal(np.isnan(got), np.isnan(want)), what
+        ok = ~np.isnan(want)
+        assert_bits_equal(got[ok], want[ok], what)
+    assert np.isnan(rm).any() and np.isinf(rp[~np.isnan(rp)]).any()       # the test did exercise both
