@@ -56,6 +56,7 @@ def interp_b(xq, xp, fp):
             alt = np.where(np.isnan(alt) & (fp[j] == fp[jn]), fp[j], alt)
             out = np.where(bad, alt, out)
     out = np.where((j == n - 1) | (xp[j] == xq), fp[j], out)
+    out = np.where(np.isnan(xq), xq, out)               # numpy.interp hands a NaN abscissa straight back
     out = np.where(status != OK, np.nan, out)
     return out, status
 

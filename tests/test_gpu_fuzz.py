@@ -207,3 +207,35 @@ def test_non_finite_inputs_follow_ieee_like_numpy(layout):
         ok = ~np.isnan(want)
         assert_bits_equal(got[ok], want[ok], what)
     assert np.isnan(rm).any() and np.isinf(rp[~np.isnan(rp)]).any()       # the test did exercise both
+
+
+@pytest.mark.parametrize("formula", ["B", "C"])
+@pytest.mark.parametrize("ng", [257, 70_001])
+def test_nan_positions_in_the_fused_gather(formula, ng):
+    """A NaN coordinate is not "outside the grid" for interp1d (no flag); numpy.interp / scipy hand back NaN fields,
+    so that particle's state turns NaN exactly like in the reference while its neighbours are untouched by it."""
+    import turbopy_b200 as tp
+    rng = np.random.default_rng(ng)
+    n = 148 * 960 + 321
+    dt = 1e-12
+    grid = make_grid(ng)
+    tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+    pos0, mom0 = random_particles(rng, n)
+    pos0[:, 0] = rng.uniform(0.02, 0.98, n)
+    nan_idx = rng.choice(n, 50, replace=False)
+    pos0[nan_idx, 0] = np.nan
+    comps = [1e5 * np.cos((k + 1) * grid.r) for k in range(3)] + [np.sin((k + 2) * grid.r) for k in range(3)]
+    E = torch.from_numpy(np.stack(comps[:3], axis=1)).cuda(); B = torch.from_numpy(np.stack(comps[3:], axis=1)).cuda()
+    pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, formula={"B": "interp", "C": "interp1d_nd"}[formula])
+    tool.check_status()                                           # nothing flagged
+    fn = ogather.interp_b if formula == "B" else ogather.interp_c
+    F = [fn(pos0[:, 0], grid.r, c)[0] for c in comps]
+    rp, rm = pos0.copy(), mom0.copy()
+    with np.errstate(all="ignore"):
+        oboris.push_aos(rp, rm, Q_E, M_E, np.stack(F[:3], axis=1), np.stack(F[3:], axis=1), dt)
+    for got, want in ((pos.cpu().numpy(), rp), (mom.cpu().numpy(), rm)):
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert_bits_equal(got[ok], want[ok])
+    assert np.isnan(rm[nan_idx]).all()
