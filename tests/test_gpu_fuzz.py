@@ -239,3 +239,41 @@ def test_nan_positions_in_the_fused_gather(formula, ng):
         ok = ~np.isnan(want)
         assert_bits_equal(got[ok], want[ok])
     assert np.isnan(rm[nan_idx]).all()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_interpolate1d_awkward_points(seed):
+    """interpolate1D on the GPU against the oracle (itself pinned to numpy / scipy): infinite node values
+    (numpy.interp's NaN fallbacks), NaN abscissas, points exactly on and one ulp off the nodes, both ends,
+    uniform and non-uniform grids, 1-D and 2-D y."""
+    import turbopy_b200 as tp
+    rng = np.random.default_rng(300 + seed)
+    ng = int(rng.choice([2, 3, 11, 30, 257, 1025, 20_001]))
+    lo, hi = float(rng.uniform(-3, 0)), float(rng.uniform(0.1, 4))
+    xp = make_grid(ng, lo, hi).r
+    if seed % 3 == 0 and ng > 3:
+        xp = np.sort(np.concatenate([[lo, hi], rng.uniform(lo, hi, ng - 2)]))
+        if len(np.unique(xp)) != ng:
+            xp = make_grid(ng, lo, hi).r
+    lo, hi = float(xp[0]), float(xp[-1])                      # the grid's own end points (r_max is rounded into r[-1])
+    y = np.cos(3 * xp) * 10.0 ** rng.uniform(-2, 5)
+    if seed % 2 and ng > 3:
+        y[rng.integers(0, ng)] = np.inf
+        y[rng.integers(0, ng)] = -np.inf
+    xq = np.concatenate([rng.uniform(lo, hi, 5000), xp[rng.integers(0, ng, 200)], [lo, hi, np.nan],
+                         np.nextafter(xp[rng.integers(0, ng, 100)], hi).clip(lo, hi),
+                         np.nextafter(xp[rng.integers(0, ng, 100)], lo).clip(lo, hi)])
+    tool = tp.Interpolators(make_owner(), {"type": "Interpolators"})
+
+    def same(got, want, what):
+        assert np.array_equal(np.isnan(got), np.isnan(want)), what
+        ok = ~np.isnan(want)
+        assert_bits_equal(got[ok], want[ok], what)
+
+    with np.errstate(all="ignore"):
+        want, st = ogather.interp_b(xq, xp, y)
+        assert (st == 0).all()
+        same(tool.interpolate1D(xp, y)(xq), want, f"B ng={ng}")
+        y2 = np.stack([y, -2 * y, y * y])
+        want, st = ogather.interp_c(xq, xp, y2)
+        same(tool.interpolate1D(xp, y2)(xq), want, f"C ng={ng}")

@@ -65,6 +65,7 @@ for trial in range(12):
     xp = r if trial %% 3 else np.sort(np.concatenate([[lo, hi], rng.uniform(lo, hi, ng - 2)]))
     if len(np.unique(xp)) != len(xp):
         xp = r
+    lo, hi = float(xp[0]), float(xp[-1])                   # the grid's own end points (r_max is rounded into r[-1])
     y = np.cos(3 * xp) * 10.0 ** rng.uniform(-2, 5)
     if trial %% 4 == 3 and ng > 3:
         y[rng.integers(0, ng)] = np.inf                    # numpy.interp's NaN fallbacks
