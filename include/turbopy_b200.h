@@ -98,6 +98,18 @@ typedef struct tp_grid_fields {
     int64_t       comp_stride[6];
 } tp_grid_fields;
 
+/* A grid whose node coordinates are EXACTLY r[i] = start + span*((double)i*step) for i < n-1 and
+ * r[n-1] = start + span*1.0, each operation rounded once -- the arithmetic of turboPy's
+ * Grid.r = r_min + (r_max - r_min)*np.linspace(0, 1, N) (turbopy/core.py:666-667,709).  The caller
+ * asserts this (the Python layer checks it bit for bit against Grid.r on the host before using the
+ * *_lin_* entry points); the kernels then rebuild r in registers instead of reading it from HBM. */
+typedef struct tp_linspace {
+    double  start;
+    double  span;
+    double  step;
+    int64_t n;
+} tp_linspace;
+
 /* ---- library / device ----------------------------------------------------- */
 int         tp_version(void);
 const char* tp_error_string(int code);
@@ -187,6 +199,13 @@ int tp_fd_dia_const_apply_f64(const double* coef, const int* offsets, int ndiag,
  * out = I2 - I2[n-1].  mean_dr = np.mean(Grid.cell_widths) formed by the caller
  * (:49).  numpy's cumsum is sequential, a parallel scan is not: results agree to
  * rounding, not bit for bit.  scratch: tp_poisson_scratch_doubles(n) doubles. */
+/* The three r-dependent kernels on a tp_linspace grid: same results bit for bit, r (and cell_widths) never read:
+ * upwind_left 24 -> 16 B/point, del2_radial 24 -> 16 B/point, the Poisson passes 56 -> 32 B/point. */
+int tp_fd_upwind_left_lin_f64(const double* y, const tp_linspace* grid, double* d, int64_t n, tp_stream_t stream);
+int tp_fd_del2_radial_apply_lin_f64(const double* f, const tp_linspace* grid, double* out, int64_t n,
+                                    double g1, double g2, tp_stream_t stream);
+int tp_poisson_radial_solve_lin_f64(const double* sources, const tp_linspace* grid, double mean_dr, double* out,
+                                    int64_t n, double* scratch, tp_stream_t stream);
 int64_t tp_poisson_scratch_doubles(int64_t n);
 int tp_poisson_radial_solve_f64(const double* sources, const double* r, double mean_dr, double* out,
                                 int64_t n, double* scratch, tp_stream_t stream);

@@ -47,6 +47,7 @@ def test_struct_layouts_match_header(lib):
     assert C.sizeof(lib.Particles) == 7 * 8
     assert C.sizeof(lib.PushConsts) == 4 * 8
     assert C.sizeof(lib.GridFields) == 5 * 8 + 6 * 8 + 6 * 8
+    assert C.sizeof(lib.Linspace) == 4 * 8
 
 
 def test_sass_is_sm100_with_tma(lib):

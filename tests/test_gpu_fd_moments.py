@@ -179,3 +179,36 @@ def test_banded_operator_composition_and_large_grid(tp):
     d1, o1 = ofd.banded_operator("ddx", grid.r, grid.dr)
     d2, o2 = ofd.banded_operator("BC_left_extrap", grid.r, grid.dr)
     assert_bits_equal(got, ofd.dia_apply(d2, o2, ofd.dia_apply(d1, o1, y)))
+
+
+@pytest.mark.parametrize("n", [3, 10, 1000, 300_001])
+def test_linspace_grids_rebuild_r_in_registers_with_the_same_bits(tp, n, monkeypatch):
+    """On a turboPy grid (r = r_min + (r_max - r_min) * linspace(0, 1, N)) upwind_left, del2_radial and the Poisson
+    solve rebuild the node coordinates from three doubles instead of reading r / cell_widths; a grid whose array
+    does not match the formula (or TURBOPY_B200_LINSPACE=0) reads the arrays.  Same bits either way."""
+    from oracle import poisson as opoisson
+    rng = np.random.default_rng(n)
+    y = rng.normal(size=n)
+    yd = torch.from_numpy(y).cuda()
+    results = {}
+    for mode in ("lin", "arrays"):
+        if mode == "arrays":
+            monkeypatch.setenv("TURBOPY_B200_LINSPACE", "0")
+        tool, grid = fd_tool(tp, n, 2.5)                       # a fresh Grid object: probed once per grid
+        gd = tp.GridOnDevice.of(grid, yd.device)
+        assert (gd.linspace is not None) == (mode == "lin")
+        ps = tp.PoissonSolver1DRadial(tool.owner, {"type": "PoissonSolver1DRadial"})
+        with np.errstate(all="ignore"):
+            results[mode] = (tool.upwind_left(yd).cpu().numpy(), (tool.del2_radial() @ yd).cpu().numpy(),
+                             ps.solve(yd).cpu().numpy())
+            want = (ofd.upwind_left(y, grid.cell_widths), ofd.del2_radial_apply(y, grid.r, grid.dr))
+        for got, ref, what in zip(results[mode][:2], want, ("upwind", "del2_radial")):
+            assert_bits_equal(np.nan_to_num(got, nan=-7.0), np.nan_to_num(ref, nan=-7.0), f"{what} ({mode})")
+        ref = opoisson.solve(y, grid.r, grid.cell_widths)
+        assert np.abs(results[mode][2] - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1e-300)
+    for a, b in zip(results["lin"], results["arrays"]):
+        assert_bits_equal(np.nan_to_num(a, nan=-7.0), np.nan_to_num(b, nan=-7.0), "lin vs arrays")
+    # a stretched grid is not a linspace: detected, arrays are read
+    tool, grid = fd_tool(tp, max(n, 4), 2.5)
+    grid.r = grid.r ** 1.5
+    assert tp.GridOnDevice.of(grid, yd.device).linspace is None

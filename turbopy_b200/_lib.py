@@ -37,6 +37,10 @@ class GridFields(C.Structure):
                 ("comp", C.c_void_p * 6), ("comp_stride", C.c_int64 * 6)]
 
 
+class Linspace(C.Structure):
+    _fields_ = [("start", C.c_double), ("span", C.c_double), ("step", C.c_double), ("n", C.c_int64)]
+
+
 #: every symbol include/turbopy_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "tp_version": (C.c_int, []),
@@ -66,6 +70,11 @@ SIGNATURES = {
                                       C.c_int64, C.c_void_p]),
     "tp_fd_dia_const_apply_f64": (C.c_int, [c_double_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), c_i64_p,
                                             c_double_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tp_fd_upwind_left_lin_f64": (C.c_int, [C.c_void_p, C.POINTER(Linspace), C.c_void_p, C.c_int64, C.c_void_p]),
+    "tp_fd_del2_radial_apply_lin_f64": (C.c_int, [C.c_void_p, C.POINTER(Linspace), C.c_void_p, C.c_int64,
+                                                  C.c_double, C.c_double, C.c_void_p]),
+    "tp_poisson_radial_solve_lin_f64": (C.c_int, [C.c_void_p, C.POINTER(Linspace), C.c_double, C.c_void_p, C.c_int64,
+                                                  C.c_void_p, C.c_void_p]),
     "tp_poisson_scratch_doubles": (C.c_int64, [C.c_int64]),
     "tp_poisson_radial_solve_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int64,
                                               C.c_void_p, C.c_void_p]),

@@ -107,18 +107,30 @@ __global__ void __launch_bounds__(kFdThreads) fd_centered_kernel(const double* _
     }
 }
 
-// d[i] = (y[i] - y[i-1]) / w[i-1] for i >= 1; d[0] = 0.
+// d[i] = (y[i] - y[i-1]) / w[i-1] for i >= 1; d[0] = 0.  LIN: w[i-1] = r[i] - r[i-1] rebuilt from the linspace
+// parameters (Grid.cell_widths = r[1:] - r[:-1], turbopy/core.py:670) instead of being read.
+template <bool LIN>
 __global__ void __launch_bounds__(kFdThreads) fd_upwind_kernel(const double* __restrict__ y,
-                                                               const double* __restrict__ cw,
+                                                               const double* __restrict__ cw, const LinGrid lg,
                                                                double* __restrict__ d, int64_t n, bool vec) {
     TP_QUAD_LOOP(n) {
         const int64_t i = qd * kQuad;
         double w[kQuad + 2], o[kQuad];
         load_window<1>(y, i, n, vec, w);
+        const double di = LIN ? static_cast<double>(i) : 0.0;
+        double rprev = (LIN && i > 0) ? lin_r_at(lg, di, -1, i - 1) : 0.0;
 #pragma unroll
         for (int k = 0; k < kQuad; ++k) {
             const int64_t j = i + k;
-            o[k] = (j > 0 && j < n) ? (w[k + 1] - w[k]) / cw[j - 1] : 0.0;
+            double width = 1.0;
+            if (LIN) {
+                const double rj = j < n ? lin_r_at(lg, di, k, j) : 0.0;
+                width = rj - rprev;
+                rprev = rj;
+            } else if (j > 0 && j < n) {
+                width = cw[j - 1];
+            }
+            o[k] = (j > 0 && j < n) ? (w[k + 1] - w[k]) / width : 0.0;
         }
         store_quad(d, i, n, vec, o);
     }
@@ -146,8 +158,9 @@ __device__ __forceinline__ double del2_row(int64_t i, int64_t n, double fm, doub
     return acc;
 }
 
+template <bool LIN>
 __global__ void __launch_bounds__(kFdThreads) fd_del2_radial_kernel(const double* __restrict__ f,
-                                                                    const double* __restrict__ r,
+                                                                    const double* __restrict__ r, const LinGrid lg,
                                                                     double* __restrict__ out, int64_t n, double g1,
                                                                     double g2, bool vec) {
     const double diag = -2.0 * g2;
@@ -156,7 +169,13 @@ __global__ void __launch_bounds__(kFdThreads) fd_del2_radial_kernel(const double
         const int64_t i = qd * kQuad;
         double w[kQuad + 2], rr[kQuad], o[kQuad];
         load_window<1>(f, i, n, vec, w);
-        load_window<0>(r, i, n, vec, rr);
+        if (LIN) {
+            const double di = static_cast<double>(i);
+#pragma unroll
+            for (int k = 0; k < kQuad; ++k) rr[k] = i + k < n ? lin_r_at(lg, di, k, i + k) : 1.0;
+        } else {
+            load_window<0>(r, i, n, vec, rr);
+        }
 #pragma unroll
         for (int k = 0; k < kQuad; ++k)
             o[k] = (i + k < n) ? del2_row(i + k, n, w[k], w[k + 1], w[k + 2], rr[k], g1, g2, diag, above0) : 0.0;
@@ -322,6 +341,12 @@ extern "C" int tp_fd_centered_f64(const double* y, double* d, int64_t n, double 
     return static_cast<int>(cudaGetLastError());
 }
 
+static int fill_lin(const tp_linspace* g, int64_t n, LinGrid& lg) {
+    if (!g || g->n != n) return TP_E_ARG;
+    lg.start = g->start; lg.span = g->span; lg.step = g->step; lg.n = g->n;
+    return TP_OK;
+}
+
 extern "C" int tp_fd_upwind_left_f64(const double* y, const double* widths, double* d, int64_t n,
                                      tp_stream_t stream) {
     const DeviceProps& dp = device_props();
@@ -329,7 +354,23 @@ extern "C" int tp_fd_upwind_left_f64(const double* y, const double* widths, doub
     if (n < 0 || (n > 0 && (!y || !d)) || (n > 1 && !widths)) return TP_E_ARG;
     if (n == 0) return TP_OK;
     const bool vec = aligned16(y) && aligned16(d);
-    fd_upwind_kernel<<<quads(fd_upwind_kernel, n, 4), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(y, widths, d, n, vec);
+    fd_upwind_kernel<false><<<quads(fd_upwind_kernel<false>, n, 4), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        y, widths, LinGrid{}, d, n, vec);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int tp_fd_upwind_left_lin_f64(const double* y, const tp_linspace* grid, double* d, int64_t n, tp_stream_t stream) {
+    const DeviceProps& dp = device_props();
+    if (dp.status != TP_OK) return dp.status;
+    if (n < 0 || (n > 0 && (!y || !d))) return TP_E_ARG;
+    if (n == 0) return TP_OK;
+    LinGrid lg;
+    int rc = fill_lin(grid, n, lg);
+    if (rc) return rc;
+    const bool vec = aligned16(y) && aligned16(d);
+    fd_upwind_kernel<true><<<quads(fd_upwind_kernel<true>, n, 4), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        y, nullptr, lg, d, n, vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -341,7 +382,24 @@ extern "C" int tp_fd_del2_radial_apply_f64(const double* f, const double* r, dou
     if (n < 0 || (n > 0 && (!f || !r || !out))) return TP_E_ARG;
     if (n == 0) return TP_OK;
     const bool vec = aligned16(f) && aligned16(r) && aligned16(out);
-    fd_del2_radial_kernel<<<quads(fd_del2_radial_kernel, n, 12), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(f, r, out, n, g1, g2, vec);
+    fd_del2_radial_kernel<false><<<quads(fd_del2_radial_kernel<false>, n, 12), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        f, r, LinGrid{}, out, n, g1, g2, vec);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int tp_fd_del2_radial_apply_lin_f64(const double* f, const tp_linspace* grid, double* out, int64_t n, double g1,
+                                               double g2, tp_stream_t stream) {
+    const DeviceProps& dp = device_props();
+    if (dp.status != TP_OK) return dp.status;
+    if (n < 0 || (n > 0 && (!f || !out))) return TP_E_ARG;
+    if (n == 0) return TP_OK;
+    LinGrid lg;
+    int rc = fill_lin(grid, n, lg);
+    if (rc) return rc;
+    const bool vec = aligned16(f) && aligned16(out);
+    fd_del2_radial_kernel<true><<<quads(fd_del2_radial_kernel<true>, n, 4), kFdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        f, nullptr, lg, out, n, g1, g2, vec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

@@ -42,6 +42,8 @@ struct PoissonArgs {
     double* scalars;            // [0] = i0, [1] = total of scan 2 (= I2[n-1])
     int64_t n; int64_t ntiles; double dr;
     bool vec;                   // r, s, out 32-byte aligned: 256-bit accesses
+    bool lin;                   // r == nullptr: node coordinates rebuilt from the linspace parameters below
+    LinGrid lg;
 };
 
 // Inclusive scan of the tile's 2048 values held as v[k] = element (thread*8 + k).
@@ -77,7 +79,8 @@ __device__ __forceinline__ int64_t elem_index(int64_t tile, int k) {
     return tile * kScanTile + static_cast<int64_t>(threadIdx.x) * kScanRows + k;
 }
 
-__device__ __forceinline__ double a_at(const PoissonArgs& p, int64_t i) { return (p.r[i] * p.s[i]) * p.dr; }
+__device__ __forceinline__ double r_at(const PoissonArgs& p, int64_t i) { return p.lin ? lin_r(p.lg, i) : p.r[i]; }
+__device__ __forceinline__ double a_at(const PoissonArgs& p, int64_t i) { return (r_at(p, i) * p.s[i]) * p.dr; }
 
 __device__ __forceinline__ void ld4(const double* p, double& a, double& b, double& c, double& d) {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
@@ -100,7 +103,14 @@ __device__ __forceinline__ void load8(const PoissonArgs& p, const double* src, i
 
 // a[] of the tile (0 beyond n)
 __device__ __forceinline__ void load_a(const PoissonArgs& p, int64_t t, double (&v)[kScanRows], double (&rr)[kScanRows]) {
-    load8(p, p.r, t, 1.0, rr);
+    if (p.lin) {
+        const int64_t i0 = elem_index(t, 0);
+        const double di0 = static_cast<double>(i0);
+#pragma unroll
+        for (int k = 0; k < kScanRows; ++k) rr[k] = i0 + k < p.n ? lin_r_at(p.lg, di0, k, i0 + k) : 1.0;
+    } else {
+        load8(p, p.r, t, 1.0, rr);
+    }
     load8(p, p.s, t, 0.0, v);
 #pragma unroll
     for (int k = 0; k < kScanRows; ++k) v[k] = (rr[k] * v[k]) * p.dr;
@@ -160,7 +170,7 @@ __device__ __forceinline__ void offsets1_body(const PoissonArgs& p, int& phase) 
         // i0 = 2*g[1] - g[2] with I1[1] = a0 + a1, I1[2] = I1[1] + a2 in numpy's sequential order (:50-53)
         const double I1_1 = a_at(p, 0) + a_at(p, 1);
         const double I1_2 = I1_1 + a_at(p, 2);
-        p.scalars[0] = 2.0 * ((I1_1 * p.dr) / p.r[1]) - (I1_2 * p.dr) / p.r[2];
+        p.scalars[0] = 2.0 * ((I1_1 * p.dr) / r_at(p, 1)) - (I1_2 * p.dr) / r_at(p, 2);
     }
 }
 
@@ -252,14 +262,20 @@ extern "C" int64_t tp_poisson_scratch_doubles(int64_t n) {
     return 2 * ((n + kScanTile - 1) / kScanTile) + 8;      // two arrays of tile sums + scalars
 }
 
-extern "C" int tp_poisson_radial_solve_f64(const double* sources, const double* r, double mean_dr, double* out,
-                                           int64_t n, double* scratch, tp_stream_t stream) {
+static int poisson_solve(const double* sources, const double* r, const tp_linspace* grid, double mean_dr, double* out,
+                         int64_t n, double* scratch, tp_stream_t stream) {
     const DeviceProps& d = device_props();
     if (d.status != TP_OK) return d.status;
-    if (n < 3 || !sources || !r || !out || !scratch) return TP_E_ARG;
+    if (n < 3 || !sources || (!r && !grid) || !out || !scratch) return TP_E_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PoissonArgs p;
     p.r = r; p.s = sources; p.out = out; p.n = n; p.dr = mean_dr;
+    p.lin = r == nullptr;
+    p.lg = LinGrid{0.0, 0.0, 0.0, 0};
+    if (p.lin) {
+        if (grid->n != n) return TP_E_ARG;
+        p.lg = LinGrid{grid->start, grid->span, grid->step, grid->n};
+    }
     p.ntiles = (n + kScanTile - 1) / kScanTile;
     p.tile1 = scratch;
     p.tile2 = scratch + p.ntiles;
@@ -290,4 +306,16 @@ extern "C" int tp_poisson_radial_solve_f64(const double* sources, const double* 
     poisson_apply_kernel<<<b3, kScanThreads, 0, s>>>(p);
     count_launch(5);
     return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int tp_poisson_radial_solve_f64(const double* sources, const double* r, double mean_dr, double* out,
+                                           int64_t n, double* scratch, tp_stream_t stream) {
+    if (!r) return TP_E_ARG;
+    return poisson_solve(sources, r, nullptr, mean_dr, out, n, scratch, stream);
+}
+
+extern "C" int tp_poisson_radial_solve_lin_f64(const double* sources, const tp_linspace* grid, double mean_dr, double* out,
+                                               int64_t n, double* scratch, tp_stream_t stream) {
+    if (!grid) return TP_E_ARG;
+    return poisson_solve(sources, nullptr, grid, mean_dr, out, n, scratch, stream);
 }

@@ -261,6 +261,34 @@ class GridOnDevice:
         self._widths = None
         self._mean_width = None
         self._r_host = r_host
+        self._linspace = False              # not probed yet
+
+    @property
+    def linspace(self):
+        """A ``tp_linspace`` describing ``Grid.r`` exactly, or None.  turboPy builds
+        ``r = r_min + (r_max - r_min) * np.linspace(0, 1, N)`` (turbopy/core.py:666-667,709),
+        i.e. ``r[i] = r_min + span*(i*step)`` with ``step = 1/(N-1)`` and the last node
+        ``r_min + span*1.0``, every operation rounded once.  When the grid's array matches
+        that formula bit for bit (checked here on the host, once per grid) the kernels that
+        only need ``r`` rebuild it in registers instead of reading it."""
+        if self._linspace is False:
+            self._linspace = None
+            r = self._r_host
+            n = r.shape[0]
+            if n >= 2 and os.environ.get("TURBOPY_B200_LINSPACE", "1") != "0":
+                step = 1.0 / (n - 1)
+                t = np.arange(n, dtype=np.float64) * step
+                t[-1] = 1.0
+                start = float(r[0])
+                spans = [float(r[-1]) - start]
+                lo, hi = getattr(self, "_bounds", (None, None))
+                if lo is not None and hi is not None:
+                    spans.insert(0, float(hi) - float(lo))      # the reference's own (r_max - r_min)
+                for span in spans:
+                    if np.array_equal((start + span * t).view(np.uint64), r.view(np.uint64)):
+                        self._linspace = _lib.Linspace(start, span, step, n)
+                        break
+        return self._linspace
 
     @property
     def mean_cell_width(self):
@@ -269,6 +297,15 @@ class GridOnDevice:
         if self._mean_width is None:
             self._mean_width = float(np.mean(self._r_host[1:] - self._r_host[:-1]))
         return self._mean_width
+
+    def widths_follow_r(self, grid):
+        """True when ``grid.cell_widths`` is what the reference computes from ``r``
+        (``r[1:] - r[:-1]``, turbopy/core.py:670) -- checked once per grid."""
+        if getattr(self, "_widths_ok", None) is None:
+            w = np.asarray(getattr(grid, "cell_widths", None))
+            self._widths_ok = bool(w.shape == (self.ng - 1,) and
+                                   np.array_equal(w.view(np.uint64), (self._r_host[1:] - self._r_host[:-1]).view(np.uint64)))
+        return self._widths_ok
 
     @property
     def cell_widths(self):
@@ -283,6 +320,7 @@ class GridOnDevice:
         hit = cls._cache.get(key)
         if hit is None or hit[0] is not grid:
             hit = (grid, cls(grid.r, grid.dr, device))
+            hit[1]._bounds = (getattr(grid, "r_min", None), getattr(grid, "r_max", None))
             cls._cache[key] = hit
         return hit[1]
 
@@ -778,12 +816,18 @@ class FiniteDifference(ComputeTool):
     def upwind_left(self, y):
         """Left upwind estimate of dy/dx; a fresh array (computetools.py:122-138)."""
         t, was_numpy = self._device_in(y)
-        w = GridOnDevice.of(self.owner.grid, t.device).cell_widths
+        gd = GridOnDevice.of(self.owner.grid, t.device)
         d = torch.empty_like(t)
         with torch.cuda.device(t.device):
-            _lib.check(_lib.lib().tp_fd_upwind_left_f64(C.c_void_p(t.data_ptr()), C.c_void_p(w.data_ptr()),
-                                                        C.c_void_p(d.data_ptr()), t.shape[0],
-                                                        _stream_ptr(t.device)))
+            if gd.linspace is not None and gd.widths_follow_r(self.owner.grid):
+                _lib.check(_lib.lib().tp_fd_upwind_left_lin_f64(C.c_void_p(t.data_ptr()), C.byref(gd.linspace),
+                                                                C.c_void_p(d.data_ptr()), t.shape[0],
+                                                                _stream_ptr(t.device)))
+            else:
+                w = gd.cell_widths
+                _lib.check(_lib.lib().tp_fd_upwind_left_f64(C.c_void_p(t.data_ptr()), C.c_void_p(w.data_ptr()),
+                                                            C.c_void_p(d.data_ptr()), t.shape[0],
+                                                            _stream_ptr(t.device)))
         return d.cpu().numpy() if was_numpy else d
 
     def del2_radial(self, device=None):
@@ -798,12 +842,19 @@ class FiniteDifference(ComputeTool):
         g2 = 1 / (self.dr ** 2)                 # :211
         n = gd.ng
 
+        lin = gd.linspace
+
         def apply(f):
             out = torch.empty_like(f)
             with torch.cuda.device(f.device):
-                _lib.check(_lib.lib().tp_fd_del2_radial_apply_f64(
-                    C.c_void_p(f.data_ptr()), C.c_void_p(gd.r.data_ptr()), C.c_void_p(out.data_ptr()),
-                    n, g1, g2, _stream_ptr(f.device)))
+                if lin is not None:
+                    _lib.check(_lib.lib().tp_fd_del2_radial_apply_lin_f64(
+                        C.c_void_p(f.data_ptr()), C.byref(lin), C.c_void_p(out.data_ptr()),
+                        n, g1, g2, _stream_ptr(f.device)))
+                else:
+                    _lib.check(_lib.lib().tp_fd_del2_radial_apply_f64(
+                        C.c_void_p(f.data_ptr()), C.c_void_p(gd.r.data_ptr()), C.c_void_p(out.data_ptr()),
+                        n, g1, g2, _stream_ptr(f.device)))
             return out
 
         return BandedOperator(n, [-1, 0, 1], apply, dev)
@@ -919,7 +970,12 @@ class PoissonSolver1DRadial(ComputeTool):
             scratch = self._scratch[dev] = torch.empty(need, dtype=torch.float64, device=dev)
         out = torch.empty_like(s)
         with torch.cuda.device(dev):
-            _lib.check(lib.tp_poisson_radial_solve_f64(C.c_void_p(s.data_ptr()), C.c_void_p(gd.r.data_ptr()), dr,
-                                                       C.c_void_p(out.data_ptr()), n,
-                                                       C.c_void_p(scratch.data_ptr()), _stream_ptr(dev)))
+            if gd.linspace is not None:
+                _lib.check(lib.tp_poisson_radial_solve_lin_f64(C.c_void_p(s.data_ptr()), C.byref(gd.linspace), dr,
+                                                               C.c_void_p(out.data_ptr()), n,
+                                                               C.c_void_p(scratch.data_ptr()), _stream_ptr(dev)))
+            else:
+                _lib.check(lib.tp_poisson_radial_solve_f64(C.c_void_p(s.data_ptr()), C.c_void_p(gd.r.data_ptr()), dr,
+                                                           C.c_void_p(out.data_ptr()), n,
+                                                           C.c_void_p(scratch.data_ptr()), _stream_ptr(dev)))
         return out.cpu().numpy() if was_numpy else out
