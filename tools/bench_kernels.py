@@ -187,16 +187,18 @@ def main():
         fdt = tp.FiniteDifference(ow, {"type": "FiniteDifference", "method": "centered"})
         y = torch.sin(torch.linspace(0, 6.28, n, dtype=torch.float64, device="cuda"))
         add("fd centered_difference", n, 16, timed(lambda: fdt.centered_difference(y), it), "incl. torch.empty_like")
-        add("fd upwind_left", n, 24, timed(lambda: fdt.upwind_left(y), it))
+        lin = tp.GridOnDevice.of(ow.grid, y.device).linspace is not None     # r rebuilt in registers: 8 B/pt less
+        lin_note = "linspace grid: r / cell_widths not read" if lin else "reads the r / cell_widths array"
+        add("fd upwind_left", n, 16 if lin else 24, timed(lambda: fdt.upwind_left(y), it), lin_note)
         D = fdt.del2_radial()
-        add("fd del2_radial @ f", n, 24, timed(lambda: D @ y, it))
+        add("fd del2_radial @ f", n, 16 if lin else 24, timed(lambda: D @ y, it), lin_note)
         for name, bpp in (("ddx", 16), ("del2", 16), ("BC_left_extrap", 16), ("radial_curl", 40)):
             D = getattr(fdt, name)()
             add(f"fd {name}() @ f", n, bpp, timed(lambda: D @ y, it),
                 "stored diagonals" if name == "radial_curl" else "constant diagonals in kernel args")
         ps = tp.PoissonSolver1DRadial(ow, {"type": "PoissonSolver1DRadial"})
-        add("PoissonSolver1DRadial.solve (5 launches)", n, 56, timed(lambda: ps.solve(y), it),
-            "56 B/pt over the reduce-then-scan passes; 16 B/pt algorithmic")
+        add("PoissonSolver1DRadial.solve (5 launches)", n, 32 if lin else 56, timed(lambda: ps.solve(y), it),
+            ("32" if lin else "56") + " B/pt over the reduce-then-scan passes; 16 B/pt algorithmic; " + lin_note)
         del y, fdt, D, ow, ps
         tp.GridOnDevice._cache.clear()
         torch.cuda.empty_cache()
