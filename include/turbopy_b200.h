@@ -166,6 +166,14 @@ int tp_interp1d_f64(const double* r, int64_t ng, double dr, double r_first, doub
                     const double* xq, int64_t xq_stride, int64_t n,
                     double* out, int64_t out_stride_c, int formula,
                     uint64_t* status, tp_stream_t stream);
+/* The same with the abscissas asserted to be a tp_linspace grid (r is still passed: the recovery path for
+ * on-node / edge / out-of-range points reads it): the fast path rebuilds x[j], x[j+1] in registers instead of
+ * loading them.  Used for formulas B and C on grids staged in shared memory; other cases run the generic kernel. */
+int tp_interp1d_lin_f64(const double* r, int64_t ng, double dr, double r_first, double r_last,
+                        const double* y, int ncomp, int64_t y_stride_c, int64_t y_stride_n,
+                        const double* xq, int64_t xq_stride, int64_t n,
+                        double* out, int64_t out_stride_c, int formula, const tp_linspace* grid,
+                        uint64_t* status, tp_stream_t stream);
 
 /* ---- kernel 2: FiniteDifference 1-D stencils ------------------------------
  * centered_difference (turbopy/computetools.py:104-120): d[i]=(y[i+1]-y[i-1])/two_dr,

@@ -295,3 +295,29 @@ def test_gather_push_steps_equals_repeated_calls(tp, formula, ng, n):
     gone = (pb.cpu().numpy()[:, 0] > 1.0)
     with pytest.raises((ValueError, AssertionError), match=f"{int(gone.sum())} particle"):
         tool_a.check_status()
+
+
+@pytest.mark.parametrize("ng", [2, 30, 4097])
+def test_interpolate1d_linspace_abscissas_same_bits(tp, ng, monkeypatch):
+    """interpolate1D over turboPy's own grid coordinates rebuilds x[j], x[j+1] in registers; over any other
+    abscissas (or with TURBOPY_B200_LINSPACE=0) it loads them.  Same bits, 1-D and 2-D y, on-node / end / NaN points."""
+    grid = make_grid(ng, -0.75, 2.25)
+    tool = tp.Interpolators(make_owner(grid=grid), {"type": "Interpolators"})
+    rng = np.random.default_rng(ng)
+    y = np.cos(3 * grid.r) * 1e3
+    y2 = np.stack([y, -y, y * y])
+    xq = np.concatenate([rng.uniform(grid.r[0], grid.r[-1], 200_001), grid.r[rng.integers(0, ng, 50)],
+                         [grid.r[0], grid.r[-1], np.nan]])
+    f1, f2 = tool.interpolate1D(grid.r, y), tool.interpolate1D(grid.r, y2)
+    assert f1._lin is not None and f2._lin is not None
+    monkeypatch.setenv("TURBOPY_B200_LINSPACE", "0")
+    g1, g2 = tool.interpolate1D(grid.r, y), tool.interpolate1D(grid.r, y2)
+    assert g1._lin is None and g2._lin is None
+    with np.errstate(all="ignore"):
+        want1, _ = ogather.interp_b(xq, grid.r, y)
+        want2, _ = ogather.interp_c(xq, grid.r, y2)
+    for got, want in ((f1(xq), want1), (g1(xq), want1), (f2(xq), want2), (g2(xq), want2)):
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert_bits_equal(np.nan_to_num(got, nan=-7.0), np.nan_to_num(want, nan=-7.0))
+    monkeypatch.delenv("TURBOPY_B200_LINSPACE")
+    assert tool.interpolate1D(grid.r ** 3, y)._lin is None or ng == 2        # stretched abscissas: not a linspace

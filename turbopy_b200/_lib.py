@@ -62,6 +62,10 @@ SIGNATURES = {
                                   C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                   C.c_void_p, C.c_int64, C.c_int64,
                                   C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "tp_interp1d_lin_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                      C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                                      C.c_void_p, C.c_int64, C.c_int64,
+                                      C.c_void_p, C.c_int64, C.c_int, C.POINTER(Linspace), C.c_void_p, C.c_void_p]),
     "tp_fd_centered_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
     "tp_fd_upwind_left_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tp_fd_del2_radial_apply_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

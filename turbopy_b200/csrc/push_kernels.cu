@@ -364,6 +364,7 @@ struct InterpArgs {
     const double* xq; int64_t xq_stride; int64_t n;
     double* out; int64_t out_stride_c;
     int ncomp;
+    LinGrid lin;                // LIN kernels: the node coordinates as linspace parameters
 };
 
 // The view of six consecutive components c0 .. c0+5 of the y block.
@@ -397,7 +398,9 @@ __device__ __noinline__ void interp_point_exact(const InterpArgs& a, unsigned ch
 // Four consecutive points per thread and iteration: two 128-bit loads of x, two
 // 128-bit stores per component (the kernel moves only 8 B in + 8 B out per
 // point and component, so it lives on bytes in flight).
-template <int FORMULA, bool STAGED, int NC>       // NC = components per pass: 1 (1-D y, the common case) or 6
+// LIN: the abscissas are a tp_linspace grid -- the fast path rebuilds x[j], x[j+1] instead of loading them (the
+// kernel is bound by its random shared-memory loads: four per point for a 1-D y, two with LIN).
+template <int FORMULA, bool STAGED, int NC, bool LIN = false>   // NC = components per pass: 1 (1-D y, the common case) or 6
 __global__ void __launch_bounds__(kThreads, NC == 1 ? 3 : 2) interp_kernel(const __grid_constant__ InterpArgs a, bool vec) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (STAGED) { stage_issue(a.g, smem); stage_wait(smem); }
@@ -428,7 +431,8 @@ __global__ void __launch_bounds__(kThreads, NC == 1 ? 3 : 2) interp_kernel(const
             for (int q = 0; q < 4; ++q) {
                 double F[6];
                 Guard gd;
-                bool ok = gather6_fast<FORMULA>(gv, x[q], F, gd) && guard_ok(gd);
+                bool ok = (LIN ? gather6_fast_lin<FORMULA>(gv, a.lin, x[q], F, gd) : gather6_fast<FORMULA>(gv, x[q], F, gd)) &&
+                          guard_ok(gd);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) { ok = ok && (F[c] == F[c]); o[c][q] = F[c]; }     // NaN -> numpy's fallbacks
                 if (!ok && i + q < a.n) bad |= 1u << q;
@@ -726,17 +730,18 @@ static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_sme
     return rc;
 }
 
-template <int FORMULA, bool STAGED, int NC>
+template <int FORMULA, bool STAGED, int NC, bool LIN = false>
 static int launch_interp_nc(const InterpArgs& a, size_t smem, cudaStream_t s);
 
-template <int FORMULA, bool STAGED>
+template <int FORMULA, bool STAGED, bool LIN = false>
 static int launch_interp(const InterpArgs& a, size_t smem, cudaStream_t s) {
-    return a.ncomp == 1 ? launch_interp_nc<FORMULA, STAGED, 1>(a, smem, s) : launch_interp_nc<FORMULA, STAGED, 6>(a, smem, s);
+    return a.ncomp == 1 ? launch_interp_nc<FORMULA, STAGED, 1, LIN>(a, smem, s)
+                        : launch_interp_nc<FORMULA, STAGED, 6, LIN>(a, smem, s);
 }
 
-template <int FORMULA, bool STAGED, int NC>
+template <int FORMULA, bool STAGED, int NC, bool LIN>
 static int launch_interp_nc(const InterpArgs& a, size_t smem, cudaStream_t s) {
-    auto kern = interp_kernel<FORMULA, STAGED, NC>;
+    auto kern = interp_kernel<FORMULA, STAGED, NC, LIN>;
     int rc = set_smem(kern, smem);
     if (rc) return rc;
     const int blocks = grid_blocks(reinterpret_cast<const void*>(kern), smem, (a.n + 3) / 4);
@@ -899,10 +904,10 @@ extern "C" int tp_gather_smem_bytes(const tp_grid_fields* g, int64_t* bytes, int
     return TP_OK;
 }
 
-extern "C" int tp_interp1d_f64(const double* r, int64_t ng, double dr, double r_first, double r_last,
-                               const double* y, int ncomp, int64_t y_stride_c, int64_t y_stride_n,
-                               const double* xq, int64_t xq_stride, int64_t n, double* out,
-                               int64_t out_stride_c, int formula, uint64_t* status, tp_stream_t stream) {
+static int interp1d_impl(const double* r, int64_t ng, double dr, double r_first, double r_last,
+                         const double* y, int ncomp, int64_t y_stride_c, int64_t y_stride_n,
+                         const double* xq, int64_t xq_stride, int64_t n, double* out,
+                         int64_t out_stride_c, int formula, const tp_linspace* lin, uint64_t* status, tp_stream_t stream) {
     const DeviceProps& d = device_props();
     if (d.status != TP_OK) return d.status;
     if (!r || !y || !xq || !out || !status || n < 0 || ncomp < 1) return TP_E_ARG;
@@ -926,6 +931,12 @@ extern "C" int tp_interp1d_f64(const double* r, int64_t ng, double dr, double r_
     a.g.status = reinterpret_cast<unsigned long long*>(status);
     a.xq = xq; a.xq_stride = xq_stride; a.n = n; a.out = out; a.out_stride_c = out_stride_c; a.ncomp = ncomp;
     if (n == 0) return TP_OK;
+    if (lin) {
+        if (lin->n != ng) return TP_E_ARG;
+        a.lin = LinGrid{lin->start, lin->span, lin->step, lin->n};
+        if (staged && formula == TP_INTERP_B) return launch_interp<TP_INTERP_B, true, true>(a, smem, s);
+        if (staged && formula == TP_INTERP_C) return launch_interp<TP_INTERP_C, true, true>(a, smem, s);
+    }                                                    // (formula A / grids gathered through L2: the generic kernels)
     if (staged) {
         switch (formula) {
             case TP_INTERP_A: return launch_interp<TP_INTERP_A, true>(a, smem, s);
@@ -938,4 +949,22 @@ extern "C" int tp_interp1d_f64(const double* r, int64_t ng, double dr, double r_
         case TP_INTERP_B: return launch_interp<TP_INTERP_B, false>(a, 0, s);
         default: return launch_interp<TP_INTERP_C, false>(a, 0, s);
     }
+}
+
+extern "C" int tp_interp1d_f64(const double* r, int64_t ng, double dr, double r_first, double r_last,
+                               const double* y, int ncomp, int64_t y_stride_c, int64_t y_stride_n,
+                               const double* xq, int64_t xq_stride, int64_t n, double* out,
+                               int64_t out_stride_c, int formula, uint64_t* status, tp_stream_t stream) {
+    return interp1d_impl(r, ng, dr, r_first, r_last, y, ncomp, y_stride_c, y_stride_n, xq, xq_stride, n, out, out_stride_c,
+                         formula, nullptr, status, stream);
+}
+
+extern "C" int tp_interp1d_lin_f64(const double* r, int64_t ng, double dr, double r_first, double r_last,
+                                   const double* y, int ncomp, int64_t y_stride_c, int64_t y_stride_n,
+                                   const double* xq, int64_t xq_stride, int64_t n, double* out,
+                                   int64_t out_stride_c, int formula, const tp_linspace* grid, uint64_t* status,
+                                   tp_stream_t stream) {
+    if (!grid) return TP_E_ARG;
+    return interp1d_impl(r, ng, dr, r_first, r_last, y, ncomp, y_stride_c, y_stride_n, xq, xq_stride, n, out, out_stride_c,
+                         formula, grid, status, stream);
 }

@@ -263,6 +263,26 @@ class GridOnDevice:
         self._r_host = r_host
         self._linspace = False              # not probed yet
 
+    @staticmethod
+    def probe_linspace(r, bounds=(None, None)):
+        """``_lib.Linspace`` if the host array ``r`` equals ``start + span*(i*step)`` (last node
+        ``start + span*1.0``) bit for bit, else None."""
+        n = r.shape[0]
+        if n < 2 or os.environ.get("TURBOPY_B200_LINSPACE", "1") == "0":
+            return None
+        step = 1.0 / (n - 1)
+        t = np.arange(n, dtype=np.float64) * step
+        t[-1] = 1.0
+        start = float(r[0])
+        spans = [float(r[-1]) - start]
+        lo, hi = bounds
+        if lo is not None and hi is not None:
+            spans.insert(0, float(hi) - float(lo))      # the reference's own (r_max - r_min)
+        for span in spans:
+            if np.array_equal((start + span * t).view(np.uint64), r.view(np.uint64)):
+                return _lib.Linspace(start, span, step, n)
+        return None
+
     @property
     def linspace(self):
         """A ``tp_linspace`` describing ``Grid.r`` exactly, or None.  turboPy builds
@@ -272,22 +292,7 @@ class GridOnDevice:
         that formula bit for bit (checked here on the host, once per grid) the kernels that
         only need ``r`` rebuild it in registers instead of reading it."""
         if self._linspace is False:
-            self._linspace = None
-            r = self._r_host
-            n = r.shape[0]
-            if n >= 2 and os.environ.get("TURBOPY_B200_LINSPACE", "1") != "0":
-                step = 1.0 / (n - 1)
-                t = np.arange(n, dtype=np.float64) * step
-                t[-1] = 1.0
-                start = float(r[0])
-                spans = [float(r[-1]) - start]
-                lo, hi = getattr(self, "_bounds", (None, None))
-                if lo is not None and hi is not None:
-                    spans.insert(0, float(hi) - float(lo))      # the reference's own (r_max - r_min)
-                for span in spans:
-                    if np.array_equal((start + span * t).view(np.uint64), r.view(np.uint64)):
-                        self._linspace = _lib.Linspace(start, span, step, n)
-                        break
+            self._linspace = self.probe_linspace(self._r_host, getattr(self, "_bounds", (None, None)))
         return self._linspace
 
     @property
@@ -562,7 +567,7 @@ class _Interp1D:
     default axis=-1).  Out-of-range points raise ValueError like
     ``interp1d(bounds_error=True)``."""
 
-    def __init__(self, x, y):
+    def __init__(self, x, y, bounds=(None, None)):
         self._numpy = not isinstance(x, torch.Tensor)
         if self._numpy:
             if not torch.cuda.is_available():
@@ -589,6 +594,8 @@ class _Interp1D:
         self.dr = (self.r_last - self.r_first) / (x.shape[0] - 1)      # index guess only
         self.formula = _lib.TP_INTERP_B if y.ndim == 1 else _lib.TP_INTERP_C
         self._status = GatherStatus(x.device)
+        # abscissas that are exactly turboPy's linspace grid (Grid.r): the kernel rebuilds them in registers
+        self._lin = GridOnDevice.probe_linspace(np.ascontiguousarray(self.x.cpu().numpy()), bounds)
 
     #: interp1d raises its bounds error inside the call, which costs one device
     #: sync per evaluation; set ``f.deferred_check = True`` to keep evaluations
@@ -621,12 +628,14 @@ class _Interp1D:
         k = self._y2.shape[0]
         out = torch.empty((k, n), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().tp_interp1d_f64(
-                C.c_void_p(self.x.data_ptr()), self.x.shape[0], self.dr, self.r_first, self.r_last,
-                C.c_void_p(self._y2.data_ptr()), k, self._y2.stride(0), self._y2.stride(1),
-                C.c_void_p(xq.data_ptr()), 1, n,
-                C.c_void_p(out.data_ptr()), n, self.formula,
-                C.c_void_p(self._status.words.data_ptr()), _stream_ptr(dev)))
+            head = (C.c_void_p(self.x.data_ptr()), self.x.shape[0], self.dr, self.r_first, self.r_last,
+                    C.c_void_p(self._y2.data_ptr()), k, self._y2.stride(0), self._y2.stride(1),
+                    C.c_void_p(xq.data_ptr()), 1, n, C.c_void_p(out.data_ptr()), n, self.formula)
+            tail = (C.c_void_p(self._status.words.data_ptr()), _stream_ptr(dev))
+            if self._lin is not None:
+                _lib.check(_lib.lib().tp_interp1d_lin_f64(*head, C.byref(self._lin), *tail))
+            else:
+                _lib.check(_lib.lib().tp_interp1d_f64(*head, *tail))
         self._last_xq = xq
         if not self.deferred_check:
             self.check()
@@ -649,7 +658,8 @@ class Interpolators(ComputeTool):
             raise NotImplementedError(
                 f"interpolate1D(kind={kind!r}): only 'linear' is implemented by turbopy_b200 "
                 "(the field gather of the particle hot path); use the stock turboPy tool for splines")
-        return _Interp1D(x, y)
+        grid = getattr(self.owner, "grid", None)
+        return _Interp1D(x, y, (getattr(grid, "r_min", None), getattr(grid, "r_max", None)))
 
 
 # --------------------------------------------------------------------------- FiniteDifference
