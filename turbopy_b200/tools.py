@@ -369,6 +369,17 @@ class GatherStatus:
             raise exc(self.message(count, first, bits))
 
 
+def _field_key(F):
+    """Hashable identity of a grid-field argument (None if it cannot be cached)."""
+    if F is None:
+        return 0
+    if isinstance(F, torch.Tensor):
+        return (F.data_ptr(), tuple(F.shape), F.stride(), F.dtype)
+    if isinstance(F, (tuple, list)) and len(F) == 3 and all(c is None or isinstance(c, torch.Tensor) for c in F):
+        return tuple(0 if c is None else (c.data_ptr(), tuple(c.shape), c.stride(), c.dtype) for c in F)
+    return None
+
+
 def _grid_components(F, name, ng):
     """Lower a grid field to three (tensor-or-None, node stride) pairs."""
     if F is None or (np.isscalar(F) and F == 0):
@@ -411,6 +422,7 @@ class BorisPush(ComputeTool):
         super().__init__(owner, input_data)
         self.c2 = 2.9979e8 ** 2             # computetools.py:405 (pinned by tests/test_computetools.py:12)
         self._status = {}
+        self._grid_cache = {}
 
     # -- the reference method ------------------------------------------------
     def push(self, position, momentum, charge, mass, E, B):
@@ -508,18 +520,30 @@ class BorisPush(ComputeTool):
         lib = _lib.lib()
         p = _particles_struct(position, momentum)
         ng = int(grid.num_points) if hasattr(grid, "num_points") else int(len(grid.r))
-        comps = _grid_components(E_grid, "E_grid", ng) + _grid_components(B_grid, "B_grid", ng)
-        g = _lib.GridFields()
-        g.ng, g.dr = ng, float(grid.dr)
         if _is_cuda(position):
             dev = position.device
-            gd = GridOnDevice.of(grid, dev)
-            g.r, g.r_first, g.r_last = gd.r.data_ptr(), gd.r_first, gd.r_last
-            for c, (t, st) in enumerate(comps):
-                if t is not None and not (_is_cuda(t) and t.device == dev):
-                    raise TypeError("grid fields must be CUDA tensors on the particles' device")
-                g.comp[c] = t.data_ptr() if t is not None else None
-                g.comp_stride[c] = st
+            # a Simulation passes the same field tensors every step: the lowered tp_grid_fields is cached on
+            # (grid, device, tensor pointers / shapes / strides); a struct only holds pointers and strides, so a
+            # hit on recycled memory of the same shape is still the right struct
+            key = (id(grid), dev, _field_key(E_grid), _field_key(B_grid))
+            hit = self._grid_cache.get(key) if None not in key[2:] else None
+            if hit is not None and hit[0] is grid:
+                g = hit[1]
+            else:
+                comps = _grid_components(E_grid, "E_grid", ng) + _grid_components(B_grid, "B_grid", ng)
+                g = _lib.GridFields()
+                g.ng, g.dr = ng, float(grid.dr)
+                gd = GridOnDevice.of(grid, dev)
+                g.r, g.r_first, g.r_last = gd.r.data_ptr(), gd.r_first, gd.r_last
+                for c, (t, st) in enumerate(comps):
+                    if t is not None and not (_is_cuda(t) and t.device == dev):
+                        raise TypeError("grid fields must be CUDA tensors on the particles' device")
+                    g.comp[c] = t.data_ptr() if t is not None else None
+                    g.comp_stride[c] = st
+                if None not in key[2:]:
+                    if len(self._grid_cache) > 16:
+                        self._grid_cache.clear()
+                    self._grid_cache[key] = (grid, g)
             status = self._status.get(dev)
             if status is None:
                 status = self._status[dev] = GatherStatus(dev)
@@ -535,6 +559,9 @@ class BorisPush(ComputeTool):
             if not isinstance(momentum, np.ndarray):
                 raise TypeError("position/momentum must both be CUDA float64 tensors or both numpy float64 arrays")
             _pin_host(position); _pin_host(momentum)
+            comps = _grid_components(E_grid, "E_grid", ng) + _grid_components(B_grid, "B_grid", ng)
+            g = _lib.GridFields()
+            g.ng, g.dr = ng, float(grid.dr)
             r = np.ascontiguousarray(grid.r, dtype=np.float64)
             g.r, g.r_first, g.r_last = r.ctypes.data, float(r[0]), float(r[-1])
             for c, (t, st) in enumerate(comps):
