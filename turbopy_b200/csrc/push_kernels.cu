@@ -626,7 +626,9 @@ static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, 
 // stream are ordered, so the buffer is free again when the next call runs).
 // Allocation is synchronous: a call that would have to (re)allocate while its
 // stream is being captured into a graph fails with TP_E_GRAPH -- run one eager
-// call first.
+// call first.  A buffer that is outgrown or whose slot is recycled is RETIRED,
+// not freed: a CUDA graph captured earlier may still point at it (64 B per grid
+// node; released with the process).
 static int records_scratch(int64_t ng, cudaStream_t s, double** out) {
     struct Slot { cudaStream_t stream; double* buf; int64_t cap; int device; };
     static Slot slots[16];
@@ -645,13 +647,14 @@ static int records_scratch(int64_t ng, cudaStream_t s, double** out) {
         else {                                              // recycle the oldest slot (its stream is most likely gone)
             hit = &slots[next];
             next = (next + 1) % 16;
-            if (hit->buf) { cudaDeviceSynchronize(); cudaFree(hit->buf); }
+            hit->buf = nullptr;                             // retired (see above)
         }
         hit->stream = s; hit->buf = nullptr; hit->cap = 0; hit->device = dev;
     }
-    if (hit->buf) { TP_CUDA_TRY(cudaStreamSynchronize(s)); cudaFree(hit->buf); hit->buf = nullptr; hit->cap = 0; }
-    TP_CUDA_TRY(cudaMalloc(&hit->buf, static_cast<size_t>(ng) * 64));
-    hit->cap = ng;
+    const int64_t grown = std::max<int64_t>(std::max<int64_t>(ng, 1024), 2 * hit->cap);   // geometric: few retirements
+    hit->buf = nullptr; hit->cap = 0;                       // an outgrown buffer is retired (see above)
+    TP_CUDA_TRY(cudaMalloc(&hit->buf, static_cast<size_t>(grown) * 64));
+    hit->cap = grown;
     *out = hit->buf;
     return TP_OK;
 }
