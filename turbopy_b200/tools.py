@@ -324,6 +324,8 @@ class GridOnDevice:
         key = (id(grid), device.type, device.index if device.index is not None else torch.cuda.current_device())
         hit = cls._cache.get(key)
         if hit is None or hit[0] is not grid:
+            if len(cls._cache) >= 32:       # grids are few and long-lived; do not let a churn of them pile up device copies
+                cls._cache.clear()
             hit = (grid, cls(grid.r, grid.dr, device))
             hit[1]._bounds = (getattr(grid, "r_min", None), getattr(grid, "r_max", None))
             cls._cache[key] = hit
