@@ -130,6 +130,18 @@ for n in (3, 4, 64, 1000):
     src = rng.normal(size=n)
     with np.errstate(all="ignore"):
         same(opoisson.solve(src, sim.grid.r, sim.grid.cell_widths), ps.solve(src), f"poisson n={n}")
+# ---- the reference's Grid.r IS the linspace formula the *_lin_* kernels rebuild in registers
+import turbopy_b200 as tp                                  # (auto-registration disabled by the environment)
+for trial in range(40):
+    n = int(rng.integers(2, 3000))
+    lo = float(rng.uniform(-5, 5)); hi = lo + float(10.0 ** rng.uniform(-4, 3))
+    sim = refload.make_owner(turbopy, grid={"N": n, "r_min": lo, "r_max": hi})
+    lin = tp.GridOnDevice.probe_linspace(np.ascontiguousarray(sim.grid.r), (sim.grid.r_min, sim.grid.r_max))
+    assert lin is not None and lin.n == n, (n, lo, hi)
+    i = np.arange(n, dtype=np.float64); t = i * lin.step; t[-1] = 1.0
+    same(lin.start + lin.span * t, sim.grid.r, "linspace formula vs Grid.r")
+    same(sim.grid.r[1:] - sim.grid.r[:-1], sim.grid.cell_widths, "cell_widths = r[1:] - r[:-1]")
+assert tp.GridOnDevice.probe_linspace(np.linspace(0.0, 1.0, 50) ** 2) is None
 print("ORACLE-PINNED")
 """
 
