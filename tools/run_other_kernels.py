@@ -31,6 +31,10 @@ pos.copy_(torch.rand((n, 3), dtype=torch.float64, device="cuda"))
 mom.copy_(torch.randn((n, 3), dtype=torch.float64, device="cuda") * (M_E * 2.9979e8 * 0.1))
 for _ in range(reps):
     tool.push(pos, mom, Q_E, M_E, np.array([0.0, 1e5, 0.0]), np.array([0.0, 0.0, 1.0]))      # push_tma_kernel
+Ep, Bp = tp.soa_particles(n, fill=1e4), tp.soa_particles(n, fill=0.5)
+for _ in range(reps):
+    tool.push(pos, mom, Q_E, M_E, Ep, Bp)                                                    # push_fields_tma_kernel
+del Ep, Bp
 out8 = None
 for _ in range(reps):
     out8 = tp.reduce_moments(mom, M_E, 2.9979e8 ** 2)                                          # moments_partial_kernel
