@@ -1,6 +1,6 @@
 """CPU oracle for the turboPy particle hot path -- TEST INFRASTRUCTURE ONLY.
 
-This package restates, in plain numpy (and in C under ``oracle/c``), the
+This package restates, in plain numpy, the
 arithmetic of the reference's hot path so that the CUDA kernels can be checked
 bit-for-bit:
 

@@ -13,7 +13,7 @@ Two forms:
               *timed* as the CPU baseline, because it has the reference's
               memory behaviour (~25 full-array temporaries).
 ``push_soa``  component-wise on six length-N arrays: the line-by-line spec of
-              the CUDA kernel (``turbopy_b200/csrc/boris.cuh``).
+              the CUDA kernel (``turbopy_b200/csrc/boris_math.cuh``).
 """
 import numpy as np
 

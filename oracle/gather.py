@@ -12,7 +12,7 @@ C  the same call with N-D ``y``  -> scipy ``interp1d._call_linear``
 scipy/numpy are third-party code that is absent from /root/reference; their
 published algorithms are restated here and pinned by comparing against the
 installed scipy/numpy on seeded inputs (``make_golden.py``,
-``tests/test_oracle_gather.py``), and against the reference's own call sites
+``tests/test_oracle_goldens.py``, ``tests/test_oracle_vs_reference.py``), and against the reference's own call sites
 (tests/test_core.py:164-170, tests/test_computetools.py:71-79, the golden
 tests/fixtures/particle_in_field/output/e_0.5.csv).
 """

@@ -233,7 +233,7 @@ def golden_pif(tp):
         t = clock.start_time + clock.dt * step
         E = 1.0 * np.cos(2 * np.pi * (-omega * t + k * (g.r - 0.5)))
         times.append(t); fields.append(E); vals.append(float(np.squeeze(f(E))))
-    csv = os.path.join(refload.REFERENCE, "tests/fixtures/particle_in_field/output/e_0.5.csv")
+    csv = os.path.join(refload.FIXTURES, "particle_in_field/output/e_0.5.csv")
     ref = np.genfromtxt(csv, delimiter=",")
     # fundamental_cycle diagnoses *before* update (core.py:152-157): CSV row 0 is
     # the initialize() field (t=0) and row i>=1 is the field of time step i-1.

@@ -1,26 +1,64 @@
-"""Import the UNMODIFIED reference from /root/reference -- TEST INFRASTRUCTURE
-ONLY, and only usable in the build container (the GPU box has no
-/root/reference; nothing that runs there may call this).
+"""Import the UNMODIFIED reference -- TEST INFRASTRUCTURE ONLY.
 
-The three shims in ``oracle/shims`` (qtoml -> tomllib, np.int/np.float aliases,
-a minimal xarray.DataArray) are the only environment changes; no reference
-source is modified or copied.
+Where it is looked for, in order:
+1. ``$TURBOPY_REFERENCE`` if set;
+2. ``/root/reference`` (the build container);
+3. ``oracle/_ref`` -- the byte-for-byte copy ``oracle/stage_reference.py`` makes in the build container; it is
+   git-ignored but travels to the GPU box with the snapshot, so the oracle-vs-reference tests, the drop-in
+   ``Simulation.run()`` tests and ``bench.py``'s CPU arms run the real reference there as well.
+
+The three shims in ``oracle/shims`` (qtoml -> tomllib, np.int/np.float aliases, a minimal xarray.DataArray) are the
+only environment changes; no reference source is modified.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s CPU arms may import this module; the product never does.
 """
 import os
 import sys
 
-REFERENCE = os.environ.get("TURBOPY_REFERENCE", "/root/reference")
-SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+HERE = os.path.dirname(os.path.abspath(__file__))
+SHIMS = os.path.join(HERE, "shims")
+STAGED = os.path.join(HERE, "_ref")
+
+
+def _candidates():
+    env = os.environ.get("TURBOPY_REFERENCE")
+    if env:
+        nested = os.path.join(env, "tests", "fixtures")
+        yield env, nested if os.path.isdir(nested) else os.path.join(env, "fixtures")
+    yield "/root/reference", "/root/reference/tests/fixtures"
+    yield STAGED, os.path.join(STAGED, "fixtures")
+
+
+def locate():
+    """(directory holding the ``turbopy`` package, directory holding ``particle_in_field/``) or (None, None)."""
+    for root, fixtures in _candidates():
+        if os.path.isfile(os.path.join(root, "turbopy", "core.py")):
+            return root, fixtures
+    return None, None
+
+
+REFERENCE, FIXTURES = locate()
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE, "turbopy"))
+    return REFERENCE is not None
+
+
+def kind():
+    """Where the reference comes from: 'source' (/root/reference), 'staged' (oracle/_ref) or None."""
+    if REFERENCE is None:
+        return None
+    return "staged" if os.path.abspath(REFERENCE) == os.path.abspath(STAGED) else "source"
+
+
+def paths():
+    """sys.path entries (shims first) a subprocess needs to import the reference."""
+    return [SHIMS, REFERENCE]
 
 
 def load():
     """Returns the imported reference ``turbopy`` package."""
     if not available():
-        raise ImportError(f"reference not present at {REFERENCE}")
+        raise ImportError("reference not present (/root/reference or oracle/_ref; run python -m oracle.stage_reference)")
     sys.dont_write_bytecode = True          # /root/reference is read-only
     for p in (REFERENCE, SHIMS):
         if p not in sys.path:
@@ -32,6 +70,18 @@ def load():
         np.float = float                     # tests/test_computetools.py:29-30
     import turbopy
     return turbopy
+
+
+def load_pif():
+    """The reference's particle-in-field app module (tests/fixtures/particle_in_field/particle_in_field.py),
+    imported unmodified (its ``import xarray`` / ``import pytest`` resolve to the shim / the installed pytest)."""
+    load()
+    import importlib.util
+    path = os.path.join(FIXTURES, "particle_in_field", "particle_in_field.py")
+    spec = importlib.util.spec_from_file_location("reference_pif", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def make_owner(turbopy, grid=None, clock=None):

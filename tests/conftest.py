@@ -7,6 +7,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# turbopy_b200 is a plugin for turboPy: put the UNMODIFIED reference on sys.path before anything imports the
+# package (build container: /root/reference; GPU box: the staged copy under oracle/_ref), so that the tools
+# register into the reference's own registry and the tests drive them through it.
+from oracle import refload  # noqa: E402
+
+if refload.available():
+    refload.load()
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

@@ -1,4 +1,4 @@
-"""CPU, build container only (needs /root/reference): the oracle restatement against the UNMODIFIED reference on
+"""CPU (needs the reference: /root/reference in the build container, the staged oracle/_ref on the GPU box): the oracle restatement against the UNMODIFIED reference on
 seeded random inputs including the awkward ones (non-finite values, on-node and end points, NaN abscissas,
 repeated values).  Runs in a subprocess so that the stock tools are the ones registered (importing turbopy_b200
 overrides them).  make_golden.py pins the oracle once when the goldens are generated; this keeps it pinned."""
@@ -12,7 +12,7 @@ from oracle import refload
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-pytestmark = pytest.mark.skipif(not refload.available(), reason="reference not present (GPU box)")
+pytestmark = pytest.mark.skipif(not refload.available(), reason="reference neither at /root/reference nor staged under oracle/_ref")
 
 SCRIPT = r"""
 import sys

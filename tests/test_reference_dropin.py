@@ -1,4 +1,4 @@
-"""CPU, build container only (needs /root/reference): the tools drop into the
+"""CPU (needs the reference: /root/reference in the build container, the staged oracle/_ref on the GPU box): the tools drop into the
 UNMODIFIED turboPy through its own registry and Simulation plumbing."""
 import subprocess
 import sys
@@ -10,7 +10,7 @@ from oracle import refload
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-pytestmark = pytest.mark.skipif(not refload.available(), reason="reference not present (GPU box)")
+pytestmark = pytest.mark.skipif(not refload.available(), reason="reference neither at /root/reference nor staged under oracle/_ref")
 
 SCRIPT = r"""
 import sys
