@@ -128,6 +128,40 @@ def test_beam_trajectory_2000_steps(tp, golden):
     assert_bits_equal(mom.cpu().numpy(), golden["beam_traj_mom2000"])
 
 
+def _sha(a):
+    import hashlib
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("how", ["push", "push_steps_100"])
+def test_beam_10k_steps_config4(tp, golden_dir, how):
+    """BASELINE configs[3] at its stated length: 65 536 beam particles (gamma up to 1e3, B = 10 T) over all 10 000
+    steps, bit-for-bit against the UNMODIFIED reference (tests/golden/beam_10k.npz, oracle/make_golden_10k.py;
+    north-star bound: 1e-9 relative after 1000 steps -- this is exact after 10 000).  Through ``push`` step by step
+    and through ``push_steps(K=100)`` x 100; checkpoints at steps 100 / 1000 / 5000 / 10 000."""
+    g = np.load(f"{golden_dir}/beam_10k.npz")
+    n, steps = int(g["n"]), int(g["steps"])
+    pos0, mom0 = beam_ensemble(n, seed=4567)
+    tool = pusher(tp, float(g["dt"]))
+    pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    E, B = np.zeros(3), np.array([0.0, 0.0, float(g["B0"])])
+    done = 0
+    for cp in (int(c) for c in g["checkpoints"]):
+        if how == "push":
+            for _ in range(cp - done):
+                tool.push(pos, mom, Q_E, M_E, E, B)
+        else:
+            for _ in range((cp - done) // 100):
+                tool.push_steps(pos, mom, Q_E, M_E, E, B, 100)
+        done = cp
+        hp, hm = pos.cpu().numpy(), mom.cpu().numpy()
+        assert np.array_equal(_sha(hp), g[f"sha_pos_{cp}"]), f"position differs from the reference at step {cp}"
+        assert np.array_equal(_sha(hm), g[f"sha_mom_{cp}"]), f"momentum differs from the reference at step {cp}"
+    assert done == steps
+    assert_bits_equal(hp[::16], g["pos_final_16"])
+    assert_bits_equal(hm[::16], g["mom_final_16"])
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 100_001, 1 << 20])
 @pytest.mark.parametrize("layout", ["soa", "aos"])
 def test_ragged_sizes_vs_oracle(tp, n, layout):
