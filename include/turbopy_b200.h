@@ -152,6 +152,25 @@ int tp_gather_push_f64(const tp_particles* p, const tp_push_consts* k,
  * have done: leave it untouched). */
 int tp_gather_push_steps_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g,
                              int axis, int formula, int nsteps, uint64_t* status, tp_stream_t stream);
+/* The same single step for grids TOO LARGE for shared memory, with a per-tile WINDOW of the node records staged
+ * next to every 960-particle tile (one cp.async.bulk per tile) -- the fast path once the particles are ordered by
+ * cell (tp_sort_by_cell), when a tile only touches a short run of consecutive cells.  tile_bounds: DEVICE array
+ * of tp_gather_windows_len() int32 words, two per full tile {first cell, number of cells}; it is read by this
+ * call to size the windows and REWRITTEN by it with the cells the particles moved into, i.e. the windows of the
+ * next call.  It is a hint: particles whose cell is not covered (zeroed or stale bounds, particles in random
+ * order) take their records from L2 like tp_gather_push_f64 -- identical results either way.  With a NULL
+ * tile_bounds, or when tp_gather_windows_len() is 0, this IS tp_gather_push_f64.  records_scratch: where the
+ * 64-byte node records {r, E, B, 0} are packed each call; caller-owned memory makes the call capturable in a
+ * CUDA graph on any stream without a warm-up call (the library-owned scratch is allocated per stream). */
+int tp_gather_push_windows_f64(const tp_particles* p, const tp_push_consts* k,
+                               const tp_grid_fields* g, int axis, int formula,
+                               int32_t* tile_bounds, int64_t tile_bounds_len,
+                               double* records_scratch /* DEVICE, 8*ng doubles, or NULL: library-owned scratch */,
+                               uint64_t* status, tp_stream_t stream);
+int64_t tp_gather_windows_len(const tp_particles* p, const tp_grid_fields* g);
+/* prime tile_bounds from the particles' current coordinates (8 B read per particle); a zeroed array is valid too */
+int tp_gather_windows_init(const tp_particles* p, const tp_grid_fields* g, int axis,
+                           int32_t* tile_bounds, int64_t tile_bounds_len, tp_stream_t stream);
 int tp_status_reset(uint64_t* status, tp_stream_t stream);
 /* shared-memory bytes the staged variant would need; *staged = 1 if it fits */
 int tp_gather_smem_bytes(const tp_grid_fields* g, int64_t* bytes, int* staged);

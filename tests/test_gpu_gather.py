@@ -62,8 +62,9 @@ def test_interpolate1d_reference_test(tp):
     assert np.allclose(f1(x), y)
     ref, _ = ogather.interp_b(xnew, x, y)
     assert_bits_equal(f1(xnew), ref)
-    with pytest.raises(NotImplementedError):
-        tool.interpolate1D(x, y, 'quadratic')
+    if tp.stock_tools.get("Interpolators") is None:      # no turboPy to hand spline kinds to
+        with pytest.raises(NotImplementedError):
+            tool.interpolate1D(x, y, 'quadratic')
 
 
 def test_interpolate1d_bounds_error(tp):

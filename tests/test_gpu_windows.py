@@ -1,0 +1,180 @@
+"""The windowed large-grid gather (tp_gather_push_windows_f64, csrc/tma_ring_window.cuh): node records staged per
+960-particle tile for grids too large for shared memory.  The per-tile bounds are a hint -- every case below must
+be bit-identical to the oracle whether the windows cover the particles (cell-ordered), cover nothing (random order,
+zeroed bounds), are stale, garbage, or too wide for the stage."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import M_E, Q_E, assert_bits_equal, make_grid, make_owner, thermal_ensemble
+from test_gpu_gather import fused_reference, smooth_fields
+
+pytestmark = pytest.mark.gpu
+
+TILE = 960
+NAME = {"A": "create_interpolator", "B": "interp", "C": "interp1d_nd"}
+
+
+@pytest.fixture(scope="module")
+def tp():
+    import turbopy_b200
+    return turbopy_b200
+
+
+def ensemble(n, ng, seed, ordered):
+    pos0, mom0 = thermal_ensemble(n, seed=seed)
+    x = np.random.default_rng(seed + 1).uniform(0.02, 0.98, n)
+    pos0[:, 0] = np.sort(x) if ordered else x
+    return pos0, mom0
+
+
+def fields_on(grid):
+    comps = smooth_fields(grid)
+    E = torch.from_numpy(np.stack(comps[:3], axis=1)).cuda()
+    B = torch.from_numpy(np.stack(comps[3:], axis=1)).cuda()
+    return comps, E, B
+
+
+def windows_of(tool):
+    bufs = [w[0] for w in tool._windows.values() if w[0] is not None]
+    assert len(bufs) == 1, "the windowed kernel was not selected"
+    return bufs[0]
+
+
+def expected_bounds(x, grid, ntiles):
+    j = np.clip(((x - grid.r[0]) * (1.0 / grid.dr)).astype(np.int64), 0, grid.num_points - 2)
+    j = j[:ntiles * TILE].reshape(ntiles, TILE)
+    return np.stack([j.min(1), j.max(1) - j.min(1) + 1], axis=1).astype(np.int32)
+
+
+@pytest.mark.parametrize("formula", ["A", "B", "C"])
+@pytest.mark.parametrize("ng", [20_001, (1 << 20) + 1])
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("ordered", [True, False])
+def test_windowed_gather_vs_oracle(tp, formula, ng, layout, ordered):
+    if layout == "aos" and (ng > 100_000 or not ordered):
+        pytest.skip("AoS covered by the ordered mid-size case")
+    grid = make_grid(ng)
+    dt = 0.5 * grid.dr / 2.9979e8                                  # config 3: half a cell per step at most
+    tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+    n = 148 * TILE * 2 + 333
+    pos0, mom0 = ensemble(n, ng, ng % 1000 + 17, ordered)
+    node = np.arange(11, n, 7919)                                   # exactly on nodes, inside full tiles
+    pos0[node, 0] = grid.r[np.clip(np.searchsorted(grid.r, pos0[node, 0]), 1, ng - 2)]
+    comps, E, B = fields_on(grid)
+    if layout == "soa":
+        pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    else:
+        pos, mom = torch.from_numpy(pos0).cuda(), torch.from_numpy(mom0).cuda()
+    steps = 3
+    for _ in range(steps):
+        tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, axis=0, formula=NAME[formula])
+    tool.check_status()
+    rp, rm = fused_reference(formula, pos0, mom0, grid, comps, 0, dt, steps)
+    assert_bits_equal(pos.cpu().numpy(), rp, "position")
+    assert_bits_equal(mom.cpu().numpy(), rm, "momentum")
+    # the bounds the last call left behind describe the cells the particles are in NOW
+    ntiles = n // TILE
+    got = windows_of(tool).cpu().numpy().reshape(-1, 2)[:ntiles]
+    want = expected_bounds(rp[:, 0], grid, ntiles)
+    skip = np.zeros(ntiles, dtype=bool)
+    skip[node[node < ntiles * TILE] // TILE] = True                 # on-node particles leave the fast path: not counted
+    assert np.array_equal(got[~skip], want[~skip])
+    if ordered:
+        assert got[:, 1].max() < 400                                # a cell-ordered tile spans a short run of cells
+
+
+def test_bounds_are_only_a_hint(tp, monkeypatch):
+    """Zeroed, stale (another ensemble's), garbage and too-narrow windows: same bits."""
+    ng = 50_001
+    grid = make_grid(ng)
+    dt = 0.5 * grid.dr / 2.9979e8
+    n = 148 * TILE * 3 + 5
+    pos0, mom0 = ensemble(n, ng, 5, True)
+    comps, E, B = fields_on(grid)
+    rp, rm = fused_reference("B", pos0, mom0, grid, comps, 0, dt, 1)
+    rng = np.random.default_rng(0)
+
+    def run(spoil, env=None):
+        if env:
+            monkeypatch.setenv(*env)
+        tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+        pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+        tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B)               # primes the windows (and moves on)
+        pos.copy_(torch.from_numpy(pos0).cuda()); mom.copy_(torch.from_numpy(mom0).cuda())   # same storage, start state
+        w = windows_of(tool)
+        spoil(w)
+        tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B)
+        tool.check_status()
+        if env:
+            monkeypatch.delenv(env[0])
+        assert_bits_equal(pos.cpu().numpy(), rp, "position")
+        assert_bits_equal(mom.cpu().numpy(), rm, "momentum")
+        return w.cpu().numpy().reshape(-1, 2)
+
+    good = run(lambda w: None)
+    run(lambda w: w.zero_())
+    run(lambda w: w.copy_(w.roll(2 * 37)))                                      # every tile gets another tile's cells
+    run(lambda w: w.copy_(torch.from_numpy(rng.integers(-2**31, 2**31 - 1, w.shape[0], dtype=np.int64)
+                                           .astype(np.int32)).cuda()))
+    narrow = run(lambda w: None, env=("TURBOPY_B200_WINDOW_BYTES", "1024"))     # 16 records: most tiles do not fit
+    ntiles = n // TILE
+    assert np.array_equal(good[:ntiles], narrow[:ntiles])
+
+
+def test_sort_every_policy_and_external_sort(tp):
+    """input_data['sort_every'] = K: the tool re-orders the ensemble itself; the result is the oracle's for the
+    permuted particles (physics does not depend on particle order).  An external tp.sort_by_cell re-primes the
+    windows through the order generation counter."""
+    ng = 30_001
+    grid = make_grid(ng)
+    dt = 0.5 * grid.dr / 2.9979e8
+    n = 148 * TILE * 2 + 100
+    pos0, mom0 = ensemble(n, ng, 23, False)
+    comps, E, B = fields_on(grid)
+    tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush", "sort_every": 2})
+    pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    tag = torch.arange(n, dtype=torch.float64, device="cuda")       # rides in momentum's z to recover the permutation
+    steps = 4
+    for _ in range(steps):
+        tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B)
+    tool.check_status()
+    rp, rm = fused_reference("B", pos0, mom0, grid, comps, 0, dt, steps)
+    gp, gm = pos.cpu().numpy(), mom.cpu().numpy()
+    # match particles by their (unique) y coordinate, which the x-only field dependence still moves deterministically
+    order_g, order_r = np.lexsort((gp[:, 2], gp[:, 1], gp[:, 0])), np.lexsort((rp[:, 2], rp[:, 1], rp[:, 0]))
+    assert_bits_equal(gp[order_g], rp[order_r], "position (as a set)")
+    assert_bits_equal(gm[order_g], rm[order_r], "momentum (as a set)")
+    w = windows_of(tool).cpu().numpy().reshape(-1, 2)[:n // TILE]
+    assert w[:, 1].max() < 400                                       # the ensemble is cell-ordered now
+    # external re-ordering: windows are re-primed, results stay exact
+    tool2 = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+    pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    tool2.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B)
+    perm = tp.sort_by_cell(pos, mom, grid, return_perm=True).cpu().numpy()
+    tool2.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B)
+    tool2.check_status()
+    rp, rm = fused_reference("B", pos0, mom0, grid, comps, 0, dt, 2)
+    assert_bits_equal(pos.cpu().numpy(), rp[perm]); assert_bits_equal(mom.cpu().numpy(), rm[perm])
+
+
+def test_windowed_gather_in_a_cuda_graph(tp):
+    ng = 20_001
+    grid = make_grid(ng)
+    dt = 0.5 * grid.dr / 2.9979e8
+    n = 148 * TILE * 2
+    pos0, mom0 = ensemble(n, ng, 31, True)
+    comps, E, B = fields_on(grid)
+    tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+    pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B)         # eager: allocates records + windows
+    with tp.StepGraph(pos.device) as graph:
+        for _ in range(3):
+            tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B)
+    graph.replay(); graph.replay()
+    torch.cuda.synchronize()
+    tool.check_status()
+    rp, rm = fused_reference("B", pos0, mom0, grid, comps, 0, dt, 7)
+    assert_bits_equal(pos.cpu().numpy(), rp); assert_bits_equal(mom.cpu().numpy(), rm)

@@ -128,11 +128,20 @@ def test_product_never_imports_the_oracle():
             assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), (name, mods)
 
 
-def test_interpolate1d_rejects_splines_without_device():
+def test_interpolate1d_hands_splines_to_the_stock_tool():
+    """Spline kinds are outside the GPU path: host arrays go to the stock tool the import displaced
+    (the reference's own tests/test_computetools.py:82-86 call pattern), device tensors raise."""
     import turbopy_b200 as tp
     tool = tp.Interpolators(make_owner(), {"type": "Interpolators"})
-    with pytest.raises(NotImplementedError):
-        tool.interpolate1D(np.arange(4.0), np.arange(4.0), "cubic")
+    x, y = np.arange(6.0), np.exp(-np.arange(6.0) / 3.0)
+    if tp.HAVE_TURBOPY:
+        from scipy import interpolate
+        assert tp.stock_tools["Interpolators"].__module__ == "turbopy.computetools"
+        xq = np.arange(0, 5, 0.1)
+        assert np.allclose(tool.interpolate1D(x, y, "cubic")(xq), interpolate.interp1d(x, y, kind="cubic")(xq))
+    else:
+        with pytest.raises(NotImplementedError):
+            tool.interpolate1D(x, y, "cubic")
 
 
 def test_additive_apis_validate_before_touching_the_device():

@@ -1,7 +1,12 @@
 #!/usr/bin/env python
-"""Small driver for profiling: N steps of the 6-component fused gather+push
-(ng = 1025 staged in shared memory, or a larger grid through L2)."""
+"""Driver for profiling / sweeping the 6-component fused gather+push: a grid staged whole in shared memory
+(ng <= ~1.5 k), or a larger grid through per-tile record windows / L2.
+
+    python tools/run_gather6.py --ng 1048577 --n 16777216 --order sorted --formula interp
+    python tools/run_gather6.py --sweep          # the table of profiles/r2_gather6.json
+"""
 import argparse
+import json
 import os
 import sys
 from types import SimpleNamespace
@@ -11,31 +16,82 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import turbopy_b200 as tp  # noqa: E402
-from oracle import grid as ogrid  # noqa: E402
+from oracle import grid as ogrid  # noqa: E402  (Grid.r restatement, setup only)
 
-ap = argparse.ArgumentParser()
-ap.add_argument("--ng", type=int, default=1025)
-ap.add_argument("--n", type=int, default=16 << 20)
-ap.add_argument("--steps", type=int, default=8)
-ap.add_argument("--formula", default="interp")
-args = ap.parse_args()
-r = ogrid.grid_points(0.0, 1.0, args.ng)
-owner = SimpleNamespace(clock=SimpleNamespace(dt=1e-13),
-                        grid=SimpleNamespace(r=r, dr=ogrid.grid_dr(0.0, 1.0, args.ng), num_points=args.ng, r_min=0.0, r_max=1.0))
-tool = tp.BorisPush(owner, {"type": "BorisPush"})
-rd = torch.from_numpy(r).cuda()
-E = torch.stack([1e3 * torch.cos(6.28 * (k + 1) * rd) for k in range(3)], dim=1).contiguous()
-B = torch.stack([torch.sin(6.28 * (k + 1) * rd) for k in range(3)], dim=1).contiguous()
-pos, mom = tp.soa_particles(args.n), tp.soa_particles(args.n, fill=0.0)
-pos.copy_(0.05 + 0.9 * torch.rand((args.n, 3), dtype=torch.float64, device="cuda"))
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for _ in range(3):
-    tool.gather_push(pos, mom, -1.6022e-19, 9.1094e-31, E_grid=E, B_grid=B, formula=args.formula)
-e0.record()
-for _ in range(args.steps):
-    tool.gather_push(pos, mom, -1.6022e-19, 9.1094e-31, E_grid=E, B_grid=B, formula=args.formula)
-e1.record()
-torch.cuda.synchronize()
-tool.check_status()
-ms = e0.elapsed_time(e1) / args.steps
-print(f"ng={args.ng} 6 comps {args.formula}: {ms:.4f} ms/step  {args.n / ms / 1e6:.2f} G pushes/s")
+Q_E, M_E, C = -1.6022e-19, 9.1094e-31, 2.9979e8
+
+
+def peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def run(ng, n, order, formula, steps, comps=6, quiet=False):
+    r = ogrid.grid_points(0.0, 1.0, ng)
+    dr = ogrid.grid_dr(0.0, 1.0, ng)
+    owner = SimpleNamespace(clock=SimpleNamespace(dt=0.5 * dr / C),           # config 3: at most half a cell per step
+                            grid=SimpleNamespace(r=r, dr=dr, num_points=ng, r_min=0.0, r_max=1.0))
+    tool = tp.BorisPush(owner, {"type": "BorisPush"})
+    rd = torch.from_numpy(r).cuda()
+    E = torch.stack([1e3 * torch.cos(6.28 * (k + 1) * rd) for k in range(3)], dim=1).contiguous()
+    B = torch.stack([torch.sin(6.28 * (k + 1) * rd) for k in range(3)], dim=1).contiguous() if comps == 6 else None
+    g = torch.Generator(device="cuda").manual_seed(7)
+    pos, mom = tp.soa_particles(n), tp.soa_particles(n)
+    pos.copy_(0.05 + 0.9 * torch.rand((n, 3), dtype=torch.float64, device="cuda", generator=g))
+    mom.copy_(torch.randn((n, 3), dtype=torch.float64, device="cuda", generator=g) * (M_E * C * 0.1))
+    if order == "sorted":
+        tp.sort_by_cell(pos, mom, owner.grid)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, formula=formula)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, formula=formula)
+    e1.record()
+    torch.cuda.synchronize()
+    tool.check_status()
+    ms = e0.elapsed_time(e1) / steps
+    row = {"ng": ng, "particles": n, "order": order, "formula": formula, "components": comps, "ms_per_step": ms,
+           "g_pushes_per_s": n / ms / 1e6, "frac_of_hbm_peak": 96.0 * n / (ms * 1e-3) / 1e9 / peak(),
+           "windows": os.environ.get("TURBOPY_B200_WINDOWS", "1") != "0"}
+    wins = [w[0] for w in tool._windows.values() if w[0] is not None]
+    if wins:
+        b = wins[0].view(-1, 2)[: n // 960, 1].float()
+        row["cells_per_tile_mean_max"] = [float(b.mean()), float(b.max())]
+    if not quiet:
+        print(json.dumps(row), flush=True)
+    return row
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ng", type=int, default=1025)
+    ap.add_argument("--n", type=int, default=16 << 20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--formula", default="interp")
+    ap.add_argument("--order", default="random", choices=["random", "sorted"])
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--json")
+    a = ap.parse_args()
+    if not a.sweep:
+        run(a.ng, a.n, a.order, a.formula, a.steps)
+        return
+    rows = []
+    for ng in (1025, (1 << 20) + 1):
+        for order in ("random", "sorted"):
+            for formula in ("interp", "create_interpolator", "interp1d_nd"):
+                rows.append(run(ng, a.n, order, formula, a.steps))
+    rows.append(run((1 << 20) + 1, 64 << 20, "sorted", "interp", a.steps))
+    rows.append(run((1 << 20) + 1, 125_000_000, "sorted", "interp", a.steps))
+    rows.append(run((1 << 20) + 1, 125_000_000, "random", "interp", a.steps))
+    if a.json:
+        with open(a.json, "w") as f:
+            json.dump(rows, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

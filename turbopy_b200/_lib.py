@@ -56,6 +56,12 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tp_gather_push_steps_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts), C.POINTER(GridFields),
                                            C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "tp_gather_push_windows_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts), C.POINTER(GridFields),
+                                             C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]),
+    "tp_gather_windows_len": (C.c_int64, [C.POINTER(Particles), C.POINTER(GridFields)]),
+    "tp_gather_windows_init": (C.c_int, [C.POINTER(Particles), C.POINTER(GridFields), C.c_int, C.c_void_p, C.c_int64,
+                                         C.c_void_p]),
     "tp_status_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tp_gather_smem_bytes": (C.c_int, [C.POINTER(GridFields), c_i64_p, C.POINTER(C.c_int)]),
     "tp_interp1d_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,

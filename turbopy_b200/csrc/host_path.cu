@@ -14,7 +14,8 @@
 namespace tp {
 
 int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
-                       int formula, uint64_t* status, cudaStream_t s, int nsteps);
+                       int formula, uint64_t* status, cudaStream_t s, int nsteps, int32_t* bounds, int64_t bounds_len,
+                       double* rec_scratch);
 
 namespace {
 
@@ -205,7 +206,7 @@ extern "C" int tp_gather_push_host_f64(const tp_particles* p, const tp_push_cons
     if (p->n > 0) {
         rc = run_chunks(p, nullptr, false, nullptr, false,
                         [&](const tp_particles& dp, double*, int64_t, cudaStream_t s) {
-                            return gather_push_device(&dp, k, &dg, axis, formula, c.status_dev, s, 1);
+                            return gather_push_device(&dp, k, &dg, axis, formula, c.status_dev, s, 1, nullptr, 0, nullptr);
                         });
         if (rc) return rc;
     }

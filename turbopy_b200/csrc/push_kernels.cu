@@ -19,6 +19,7 @@
 #include "grid_stage.cuh"
 #include "tma_ring.cuh"
 #include "tma_ring_fields.cuh"
+#include "tma_ring_window.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -276,6 +277,80 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const _
             if (gather_step_fast<FORMULA>(a, g, x, p)) store_one(a.p, i, x, p);
             else gather_step_exact<FORMULA, STAGED>(a, smem, i);
         }
+    }
+}
+
+// ---- fused gather + push, node records staged per tile (large grids, cell-ordered particles) ----------
+struct TmaWinArgs {
+    GatherArgs g;
+    RingArgs ring;
+    WindowArgs win;
+};
+
+template <int FORMULA>
+__device__ __forceinline__ bool gather_step_fast_window(const GatherArgs& a, const RecView& rv, const WinView& w,
+                                                        Vec3& x, Vec3& p) {
+    double F[6];
+    Guard gd;
+    NodePair np;
+    const double xa = axis_of(x, a.axis);
+    fetch_records_window<FORMULA>(rv, w, xa, np);
+    bool ok = interp_nodes<FORMULA>(np, xa, rv.dr, rv.ng, rv.present, F, gd);
+    Vec3 E, B;
+    E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
+    boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
+    return ok && guard_ok(gd) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+}
+
+template <int FORMULA, bool AOS>
+__global__ void __launch_bounds__(kTmaThreads, 1) gather_push_win_kernel(const __grid_constant__ TmaWinArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const GatherArgs& a = ta.g;
+    ring_init(ta.ring, smem);
+    __syncthreads();
+    const RecView rv = make_rec_view(a, ta.ring.stream_hint);
+    tma_ring_window<AOS>(
+        a.p, ta.ring, ta.win, rv, a.axis, smem,
+        [&](Vec3& x, Vec3& p, const WinView& w) { return gather_step_fast_window<FORMULA>(a, rv, w, x, p); },
+        [&](int64_t i, double* xs, double* ps, int pitch) {
+            gather_step_exact_slot<FORMULA, false>(a, smem, i, xs, ps, pitch);
+        });
+    // ragged tail (< kTile particles) on the last CTA, scalar path over the original arrays
+    if (blockIdx.x == gridDim.x - 1) {
+        const GridView g = make_view<false>(a, smem);
+        for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
+            Vec3 x, p;
+            load_one(a.p, i, x, p);
+            if (gather_step_fast<FORMULA>(a, g, x, p)) store_one(a.p, i, x, p);
+            else gather_step_exact<FORMULA, false>(a, smem, i);
+        }
+    }
+}
+
+// Cell range of every full tile from the particles' CURRENT coordinates: primes the per-tile windows on the
+// first call for an ensemble and after a re-ordering (tp_sort_by_cell).  Reads 8 B per particle.
+__global__ void __launch_bounds__(256) tile_bounds_kernel(const double* __restrict__ coord, int64_t stride, int64_t ntiles,
+                                                          double r_first, double inv_dr, int ng, int2* __restrict__ bounds) {
+    __shared__ int smin[8], smax[8];
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int lo = 0x7fffffff, hi = static_cast<int>(0x80000000u);
+        for (int i = threadIdx.x; i < kTile; i += 256) {
+            const double x = coord[(t * kTile + i) * stride];
+            const bool in = x >= r_first && (x - r_first) * inv_dr < static_cast<double>(ng);     // false for NaN
+            if (in) {
+                const int j = guess_cell(x, r_first, inv_dr, ng);
+                lo = min(lo, j); hi = max(hi, j);
+            }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) { lo = min(lo, smin[w]); hi = max(hi, smax[w]); }
+            bounds[t] = hi >= lo ? make_int2(lo, hi - lo + 1) : make_int2(0, 0);
+        }
+        __syncthreads();
     }
 }
 
@@ -700,9 +775,20 @@ static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int
     return true;
 }
 
+static int pack_records(const GatherArgs& a, cudaStream_t s, double* caller_scratch, double** rec) {
+    int rc;
+    if (caller_scratch) *rec = caller_scratch;               // ng * 64 bytes owned by the caller (stream-ordered by it)
+    else if ((rc = records_scratch(a.ng, s, rec))) return rc;
+    const DeviceProps& d = device_props();
+    const int pblocks = static_cast<int>(std::min<int64_t>((a.ng + 255) / 256, static_cast<int64_t>(d.sm_count) * 8));
+    pack_nodes_kernel<<<pblocks, 256, 0, s>>>(a, *rec);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
 // Returns TP_OK and sets `launched` when the TMA kernel took the call.
 static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_smem, bool staged, bool aos,
-                               cudaStream_t s, bool& launched) {
+                               double* rec_scratch, cudaStream_t s, bool& launched) {
     launched = false;
     TmaArgs ta;
     ta.g = a;
@@ -713,12 +799,7 @@ static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_sme
     if (!staged && records_enabled()) {
         // the grid lives in L2: pack {r, E, B} into 64-byte node records first (ng * 64 B, a few us)
         double* rec = nullptr;
-        if ((rc = records_scratch(a.ng, s, &rec))) return rc;
-        const DeviceProps& d = device_props();
-        const int pblocks = static_cast<int>(std::min<int64_t>((a.ng + 255) / 256, static_cast<int64_t>(d.sm_count) * 8));
-        pack_nodes_kernel<<<pblocks, 256, 0, s>>>(a, rec);
-        count_launch();
-        if ((rc = static_cast<int>(cudaGetLastError()))) return rc;
+        if ((rc = pack_records(a, s, rec_scratch, &rec))) return rc;
         ta.g.records = rec;
         gmode = 2;
         ta.ring.stream_hint = l2_hints_enabled() ? 1 : 0;
@@ -727,6 +808,68 @@ static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_sme
         case TP_INTERP_A: rc = launch_gather_push_tma_v<TP_INTERP_A>(ta, smem, blocks, gmode, aos, s); break;
         case TP_INTERP_B: rc = launch_gather_push_tma_v<TP_INTERP_B>(ta, smem, blocks, gmode, aos, s); break;
         case TP_INTERP_C: rc = launch_gather_push_tma_v<TP_INTERP_C>(ta, smem, blocks, gmode, aos, s); break;
+        default: return TP_E_MODE;
+    }
+    launched = (rc == TP_OK);
+    return rc;
+}
+
+static bool windows_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("TURBOPY_B200_WINDOWS");      // tuning / A-B switch, default on
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+// Ring + per-stage record windows for `n` particles; false if the windowed kernel is not applicable.
+static bool plan_window_ring(int64_t n, RingArgs& ring, WindowArgs& win, size_t& smem, int& blocks) {
+    const DeviceProps& d = device_props();
+    if (!windows_enabled() || !records_enabled()) return false;
+    if (!plan_ring(n, kWinFront, ring, smem, blocks)) return false;
+    const int64_t left = d.smem_optin - 1024 - static_cast<int64_t>(smem);
+    int64_t per_stage = (left / ring.nstages) & ~int64_t(127);
+    if (const char* cap = std::getenv("TURBOPY_B200_WINDOW_BYTES"))
+        per_stage = std::min<int64_t>(per_stage, std::max(0, std::atoi(cap)) & ~127);
+    if (per_stage < 16 * kRecBytes) return false;
+    win.win_off = static_cast<uint32_t>(smem);                 // tiles_off and kTileBytes are multiples of 128
+    win.win_bytes = static_cast<uint32_t>(per_stage);
+    smem += static_cast<size_t>(ring.nstages) * per_stage;
+    return true;
+}
+
+template <int FORMULA>
+static int launch_gather_push_win(const TmaWinArgs& ta, size_t smem, int blocks, bool aos, cudaStream_t s) {
+    auto go = [&](auto kern) {
+        int rc = set_smem(kern, smem);
+        if (rc) return rc;
+        kern<<<blocks, kTmaThreads, smem, s>>>(ta);
+        count_launch();
+        return static_cast<int>(cudaGetLastError());
+    };
+    return aos ? go(gather_push_win_kernel<FORMULA, true>) : go(gather_push_win_kernel<FORMULA, false>);
+}
+
+// Returns TP_OK and sets `launched` when the windowed kernel took the call.
+static int try_gather_push_windows(const GatherArgs& a, int formula, bool aos, int32_t* bounds, int64_t bounds_len,
+                                   double* rec_scratch, cudaStream_t s, bool& launched) {
+    launched = false;
+    if (!bounds) return TP_OK;
+    TmaWinArgs ta;
+    ta.g = a;
+    size_t smem = 0; int blocks = 0;
+    if (!plan_window_ring(a.p.n, ta.ring, ta.win, smem, blocks)) return TP_OK;
+    if (bounds_len < 2 * ta.ring.ntiles) return TP_E_ARG;
+    ta.win.bounds = reinterpret_cast<int2*>(bounds);
+    int rc;
+    double* rec = nullptr;
+    if ((rc = pack_records(a, s, rec_scratch, &rec))) return rc;
+    ta.g.records = rec;
+    ta.ring.stream_hint = l2_hints_enabled() ? 1 : 0;
+    switch (formula) {
+        case TP_INTERP_A: rc = launch_gather_push_win<TP_INTERP_A>(ta, smem, blocks, aos, s); break;
+        case TP_INTERP_B: rc = launch_gather_push_win<TP_INTERP_B>(ta, smem, blocks, aos, s); break;
+        case TP_INTERP_C: rc = launch_gather_push_win<TP_INTERP_C>(ta, smem, blocks, aos, s); break;
         default: return TP_E_MODE;
     }
     launched = (rc == TP_OK);
@@ -756,7 +899,8 @@ static int launch_interp_nc(const InterpArgs& a, size_t smem, cudaStream_t s) {
 
 // Entry point shared with host_path.cu
 int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
-                       int formula, uint64_t* status, cudaStream_t s, int nsteps) {
+                       int formula, uint64_t* status, cudaStream_t s, int nsteps, int32_t* bounds, int64_t bounds_len,
+                       double* rec_scratch) {
     const DeviceProps& d = device_props();
     if (d.status != TP_OK) return d.status;
     if (nsteps < 0) return TP_E_ARG;
@@ -781,7 +925,11 @@ int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_
     // costs it 3 % (measured: 66.6 -> 64.2 G pushes/s on the headline configuration).
     if ((vec2 || aos16) && a.nsteps == 1) {
         bool launched = false;
-        if ((rc = try_gather_push_tma(a, formula, smem, staged, aos16, s, launched))) return rc;
+        if (!staged) {          // grid too large for shared memory: per-tile record windows (cell-ordered particles)
+            if ((rc = try_gather_push_windows(a, formula, aos16, bounds, bounds_len, rec_scratch, s, launched))) return rc;
+            if (launched) return TP_OK;
+        }
+        if ((rc = try_gather_push_tma(a, formula, smem, staged, aos16, rec_scratch, s, launched))) return rc;
         if (launched) return TP_OK;
     }
     return vec2 ? launch_gather_push_f<true>(a, formula, smem, staged, s)
@@ -879,12 +1027,55 @@ extern "C" int tp_boris_push_steps_f64(const tp_particles* p, const tp_push_cons
 
 extern "C" int tp_gather_push_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
                                   int formula, uint64_t* status, tp_stream_t stream) {
-    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), 1);
+    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), 1, nullptr, 0, nullptr);
 }
 
 extern "C" int tp_gather_push_steps_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
                                         int formula, int nsteps, uint64_t* status, tp_stream_t stream) {
-    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), nsteps);
+    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), nsteps, nullptr, 0, nullptr);
+}
+
+extern "C" int tp_gather_push_windows_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g,
+                                          int axis, int formula, int32_t* tile_bounds, int64_t tile_bounds_len,
+                                          double* records_scratch, uint64_t* status, tp_stream_t stream) {
+    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), 1, tile_bounds,
+                              tile_bounds_len, records_scratch);
+}
+
+// int32 words of tile bounds tp_gather_push_windows_f64 wants for this ensemble and grid; 0 = the call would not use
+// per-tile windows (grid staged whole in shared memory, layout not streamable, too few particles, switched off).
+extern "C" int64_t tp_gather_windows_len(const tp_particles* p, const tp_grid_fields* g) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return 0;
+    GatherArgs a;
+    std::memset(&a, 0, sizeof(a));
+    bool vec2 = false, aos16 = false;
+    if (fill_particles(p, a.p, vec2, &aos16) || !(vec2 || aos16)) return 0;
+    size_t smem = 0; bool staged = false;
+    if (fill_grid(g, a, smem, staged) || staged) return 0;
+    RingArgs ring; WindowArgs win; int blocks = 0;
+    if (!plan_window_ring(a.p.n, ring, win, smem, blocks)) return 0;
+    return 2 * ring.ntiles;
+}
+
+// Prime the tile bounds from the particles' current coordinates along `axis` (first call for an ensemble, or after
+// the caller re-ordered it); a zeroed buffer is also valid (the first step then gathers through L2 and primes it).
+extern "C" int tp_gather_windows_init(const tp_particles* p, const tp_grid_fields* g, int axis, int32_t* tile_bounds,
+                                      int64_t tile_bounds_len, tp_stream_t stream) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    if (!p || !g || !tile_bounds || axis < 0 || axis > 2) return TP_E_ARG;
+    if (g->ng < 2 || g->ng > (1ll << 31) - 8 || !(g->dr > 0.0)) return TP_E_GRID;
+    const int64_t ntiles = p->n / kTile;
+    if (tile_bounds_len < 2 * ntiles) return TP_E_ARG;
+    if (ntiles == 0) return TP_OK;
+    if (p->pos_stride_n <= 0 || p->pos_stride_c <= 0) return TP_E_LAYOUT;
+    const int blocks = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(d.sm_count) * 8));
+    tile_bounds_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p->pos + axis * p->pos_stride_c, p->pos_stride_n, ntiles, g->r_first, 1.0 / g->dr, static_cast<int>(g->ng),
+        reinterpret_cast<int2*>(tile_bounds));
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
 }
 
 extern "C" int tp_status_reset(uint64_t* status, tp_stream_t stream) {

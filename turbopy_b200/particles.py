@@ -6,6 +6,11 @@ import numpy as np
 import torch
 
 
+#: bumped by every sort_by_cell: tools that keep per-tile state about an ensemble (the windowed large-grid gather)
+#: re-derive it when the particle order changed under them
+order_generation = 0
+
+
 def soa_particles(n, device="cuda", fill=None):
     """An ``(n,3)`` float64 view whose memory is three contiguous component
     arrays (strides ``(1, ld)``, ``ld`` = ``n`` rounded up to even so every
@@ -69,6 +74,8 @@ def sort_by_cell(position, momentum, grid, axis=0, cells_per_bin_log2=0, extra=(
     need = int(lib.tp_sort_scratch_bytes(n, ncells, int(cells_per_bin_log2)))
     if need < 0:
         raise ValueError("sort_by_cell: need 0 <= n < 2**32, at least one cell and 0 <= cells_per_bin_log2 <= 40")
+    global order_generation
+    order_generation += 1
     with _on_device(dev):
         scratch = torch.empty(max(need, 8), dtype=torch.uint8, device=dev)
         perm = torch.empty(n, dtype=torch.int64, device=dev) if (return_perm or len(extra)) else None

@@ -30,7 +30,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._host import ComputeTool
+from ._host import ComputeTool, stock_tools
 
 _FORMULAS = {
     "A": _lib.TP_INTERP_A, "create_interpolator": _lib.TP_INTERP_A,
@@ -425,6 +425,13 @@ class BorisPush(ComputeTool):
         self.c2 = 2.9979e8 ** 2             # computetools.py:405 (pinned by tests/test_computetools.py:12)
         self._status = {}
         self._grid_cache = {}
+        self._windows = {}                  # per ensemble: tile bounds of the windowed large-grid gather
+        self._records = {}                  # per (grid size, device): scratch for the packed node records
+        # additive option: re-order the particles by cell every K gather_push calls (0 = never).  The reference
+        # never reorders particles and its physics does not depend on their order, but callers that index
+        # particles by position in the array would notice, hence opt-in.
+        self.sort_every = int(input_data.get("sort_every", 0) or 0)
+        self._sort_calls = {}
 
     # -- the reference method ------------------------------------------------
     def push(self, position, momentum, charge, mass, E, B):
@@ -549,10 +556,27 @@ class BorisPush(ComputeTool):
             status = self._status.get(dev)
             if status is None:
                 status = self._status[dev] = GatherStatus(dev)
+            if self.sort_every > 0:
+                from . import particles
+                ck = (position.data_ptr(), int(p.n), axis)
+                calls = self._sort_calls.get(ck, 0)
+                if calls % self.sort_every == 0:
+                    particles.sort_by_cell(position, momentum, grid, axis=axis)
+                self._sort_calls[ck] = calls + 1
             with _on_device(dev):
                 if _steps is None:
-                    _lib.check(lib.tp_gather_push_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
-                                                      C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
+                    win = self._tile_windows(p, g, position, momentum, axis, grid, dev)
+                    if win is not None:
+                        rec = self._records.get((ng, dev))
+                        if rec is None:
+                            rec = self._records[(ng, dev)] = torch.empty(8 * ng, dtype=torch.float64, device=dev)
+                        _lib.check(lib.tp_gather_push_windows_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
+                                                                  C.c_void_p(win.data_ptr()), win.shape[0],
+                                                                  C.c_void_p(rec.data_ptr()),
+                                                                  C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
+                    else:
+                        _lib.check(lib.tp_gather_push_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
+                                                          C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
                 else:
                     _lib.check(lib.tp_gather_push_steps_f64(C.byref(p), C.byref(k), C.byref(g), axis, code, _steps,
                                                             C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
@@ -578,6 +602,29 @@ class BorisPush(ComputeTool):
                 raise exc(GatherStatus.message(int(words[0]), int(words[1]), int(words[2])))
             return None
         raise TypeError("position/momentum must both be CUDA float64 tensors or both numpy float64 arrays")
+
+    def _tile_windows(self, p, g, position, momentum, axis, grid, dev):
+        """The int32 tile-bounds tensor of this ensemble for tp_gather_push_windows_f64 (None when the library would
+        not use per-tile windows: grid staged whole in shared memory, small ensemble, odd layout).  Primed from the
+        current coordinates the first time an ensemble is seen and whenever the particles were re-ordered
+        (``sort_every``, or a ``tp.sort_by_cell`` call by anyone); afterwards each call leaves the next call's
+        windows behind.  Stale bounds cost speed for one step, never correctness (include/turbopy_b200.h)."""
+        from . import particles
+        key = (position.data_ptr(), int(p.n), axis, id(grid), dev)
+        hit = self._windows.get(key)
+        if hit is None:
+            need = int(_lib.lib().tp_gather_windows_len(C.byref(p), C.byref(g)))
+            if len(self._windows) > 8:
+                self._windows.clear()
+            hit = self._windows[key] = [torch.zeros(need, dtype=torch.int32, device=dev) if need else None, -1]
+        buf, generation = hit
+        if buf is None:
+            return None
+        if generation != particles.order_generation:
+            _lib.check(_lib.lib().tp_gather_windows_init(C.byref(p), C.byref(g), axis, C.c_void_p(buf.data_ptr()),
+                                                         buf.shape[0], _stream_ptr(dev)))
+            hit[1] = particles.order_generation
+        return buf
 
     def check_status(self):
         """Poll the device error flags of :meth:`gather_push` (one small D2H
@@ -615,6 +662,14 @@ class _Interp1D:
             raise ValueError("x and y arrays must be equal in length along interpolation axis.")
         if x.shape[0] < 2:
             raise ValueError("x and y arrays must have at least 2 entries")
+        x_host = np.ascontiguousarray(x.cpu().numpy())
+        if x_host.shape[0] > 1 and not bool(np.all(x_host[1:] >= x_host[:-1])):
+            # interp1d(assume_sorted=False), scipy's default: ``ind = np.argsort(x, kind="mergesort")``,
+            # ``x = x[ind]``, ``y = np.take(y, ind, axis=axis)`` -- the same stable sort, on the device
+            ind = torch.sort(x, stable=True).indices
+            x = x[ind]
+            y = y.index_select(-1, ind)
+            x_host = np.ascontiguousarray(x.cpu().numpy())
         self.x = x.contiguous()
         self.y = y
         self._y2 = y.reshape(-1, y.shape[-1]).contiguous()
@@ -624,7 +679,7 @@ class _Interp1D:
         self.formula = _lib.TP_INTERP_B if y.ndim == 1 else _lib.TP_INTERP_C
         self._status = GatherStatus(x.device)
         # abscissas that are exactly turboPy's linspace grid (Grid.r): the kernel rebuilds them in registers
-        self._lin = GridOnDevice.probe_linspace(np.ascontiguousarray(self.x.cpu().numpy()), bounds)
+        self._lin = GridOnDevice.probe_linspace(x_host, bounds)
 
     #: interp1d raises its bounds error inside the call, which costs one device
     #: sync per evaluation; set ``f.deferred_check = True`` to keep evaluations
@@ -684,9 +739,16 @@ class Interpolators(ComputeTool):
         Only ``kind='linear'`` is on the particle hot path and implemented here;
         spline kinds raise (they are scipy/LAPACK code, not a B200 kernel)."""
         if kind != 'linear':
+            # Spline kinds are scipy / LAPACK set-up code on a handful of nodes, not part of the particle hot
+            # path (SURVEY 8a-4): host arrays go to the stock tool this class displaced in the registry, so a
+            # Simulation that used them keeps working after ``import turbopy_b200``.  This is a hand-off of an
+            # out-of-scope call, not a fallback of the linear path: that one has no CPU implementation here.
+            stock = stock_tools.get("Interpolators")
+            if stock is not None and not isinstance(x, torch.Tensor) and not isinstance(y, torch.Tensor):
+                return stock.interpolate1D(self, x, y, kind)
             raise NotImplementedError(
-                f"interpolate1D(kind={kind!r}): only 'linear' is implemented by turbopy_b200 "
-                "(the field gather of the particle hot path); use the stock turboPy tool for splines")
+                f"interpolate1D(kind={kind!r}): only 'linear' runs on the GPU (the field gather of the particle "
+                "hot path); spline kinds need numpy arrays and the stock turboPy tool")
         grid = getattr(self.owner, "grid", None)
         return _Interp1D(x, y, (getattr(grid, "r_min", None), getattr(grid, "r_max", None)))
 
@@ -706,6 +768,7 @@ class BandedOperator:
         self._apply = apply_fn
         self._device = device
         self._dense = None
+        self._diag = None
         self._stored = stored            # callable -> (ndiag, n) numpy array of the stored diagonals, if known
 
     # ---- constructors for the two stored forms --------------------------------
@@ -748,6 +811,9 @@ class BandedOperator:
         data = data.contiguous()
         nd, n = data.shape
         offsets = [int(o) for o in offsets]
+        if nd > 5 or any(abs(o) > 2 for o in offsets):
+            raise NotImplementedError("banded operators are applied up to bandwidth 5 (offsets -2 .. 2); "
+                                      f"got offsets {offsets}")
         c_off = (C.c_int * nd)(*offsets)
 
         def apply(f):
@@ -758,7 +824,10 @@ class BandedOperator:
                     C.c_void_p(out.data_ptr()), n, _stream_ptr(f.device)))
             return out
 
-        return cls(n, offsets, apply, device, lambda: data.cpu().numpy())
+        op = cls(n, offsets, apply, device, lambda: data.cpu().numpy())
+        if offsets == list(range(offsets[0], offsets[-1] + 1)):
+            op._diag = (offsets, data)
+        return op
 
     def _compose(self, other):
         """``self @ other``: apply ``other`` first (operator product, lazily)."""
@@ -776,23 +845,148 @@ class BandedOperator:
             if not _is_cuda(f):
                 raise TypeError("operand must be a CUDA tensor (or a numpy array)")
             _require_f64(f, "operand")
-            if f.ndim != 1 or f.shape[0] != self.shape[0]:
+            if f.ndim not in (1, 2) or f.shape[0] != self.shape[0]:
                 raise ValueError("dimension mismatch")
+            if f.ndim == 2:                         # a block of column vectors, like scipy's A @ X
+                return torch.stack([self._apply(f[:, c].contiguous()) for c in range(f.shape[1])], dim=1)
             return self._apply(f.contiguous())
+        if hasattr(f, "todia") and getattr(f, "shape", None) == self.shape:     # a scipy sparse matrix
+            return self._compose(self._coerce(f))
         a = np.asarray(f, dtype=np.float64)
-        if a.ndim != 1 or a.shape[0] != self.shape[0]:
+        if a.ndim not in (1, 2) or a.shape[0] != self.shape[0]:
             raise ValueError("dimension mismatch")
-        out = self._apply(torch.from_numpy(np.ascontiguousarray(a)).to(self._device))
+        out = self.dot(torch.from_numpy(np.ascontiguousarray(a)).to(self._device))
         return out.cpu().numpy()
 
     __matmul__ = dot
 
+    # ---- the stored diagonals of ANY banded operator, without forming it ------
+    def diagonals(self):
+        """``(offsets, data)``: every diagonal between the lowest and the highest offset, as an ``(nd, n)`` CUDA
+        tensor in scipy's dia layout (``data[k, j] = A[j - offsets[k], j]``).  Extracted exactly by applying the
+        operator to ``nd`` comb vectors (ones at the columns ``j = c mod nd``): a row of a matrix of bandwidth
+        ``nd`` meets exactly one column of each comb, so each output element IS one matrix entry (times 1.0, plus
+        zeros).  ``nd`` kernel launches, O(nd * n) work, no dense matrix."""
+        if self._diag is None:
+            n = self.shape[0]
+            lo, hi = int(self.offsets.min()), int(self.offsets.max())
+            w = hi - lo + 1
+            dev = self._device
+            i = torch.arange(n, device=dev)
+            data = torch.zeros((w, n), dtype=torch.float64, device=dev)
+            for c in range(w):
+                col = self._apply((i % w == c).to(torch.float64))
+                j = i + lo + ((c - (i + lo)) % w)          # the comb's only column inside row i's band
+                ok = (j >= 0) & (j < n)
+                data[(j - i - lo)[ok], j[ok]] = col[ok]
+            self._diag = (list(range(lo, hi + 1)), data)
+        return self._diag
+
     def toarray(self):
         if self._dense is None:
+            offsets, data = self.diagonals()
             n = self.shape[0]
-            eye = torch.eye(n, dtype=torch.float64, device=self._device)
-            self._dense = torch.stack([self._apply(eye[j].contiguous()) for j in range(n)], dim=1).cpu().numpy()
+            dense = torch.zeros((n, n), dtype=torch.float64, device=self._device)
+            j = torch.arange(n, device=self._device)
+            for k, off in enumerate(offsets):
+                ok = (j - off >= 0) & (j - off < n)
+                dense[(j - off)[ok], j[ok]] = data[k][ok]
+            self._dense = dense.cpu().numpy()
         return self._dense
+
+    # ---- sparse-matrix arithmetic (what scipy's dia_matrix gives the reference's callers) ----
+    # computetools.py:221 itself forms ``D1 + D2``; user modules scale and combine operators the same way
+    # (``1 - dt * D``-style updates).  Results are new BandedOperators with merged diagonals, applied by
+    # tp_fd_dia_apply_f64 in ascending-offset (= column) order, the order scipy's csr result sums in.
+    def _coerce(self, other):
+        if isinstance(other, BandedOperator):
+            return other
+        if hasattr(other, "todia"):
+            m = other.todia()
+            if m.shape != self.shape:
+                raise ValueError("inconsistent shapes")
+            order = np.argsort(m.offsets)
+            data = torch.from_numpy(np.ascontiguousarray(m.data[order], dtype=np.float64)).to(self._device)
+            if data.shape[1] < self.shape[0]:
+                data = torch.nn.functional.pad(data, (0, self.shape[0] - data.shape[1]))
+            return BandedOperator.from_diagonals(data, m.offsets[order], self._device)
+        return None
+
+    def _merged(self, other, sign):
+        other = self._coerce(other)
+        if other is None:
+            return NotImplemented
+        if other.shape != self.shape:
+            raise ValueError("inconsistent shapes")
+        (oa, da), (ob, db) = self.diagonals(), other.diagonals()
+        lo, hi = min(oa[0], ob[0]), max(oa[-1], ob[-1])
+        n = self.shape[0]
+        data = torch.zeros((hi - lo + 1, n), dtype=torch.float64, device=self._device)
+        data[oa[0] - lo:oa[-1] - lo + 1] = da
+        rows = data[ob[0] - lo:ob[-1] - lo + 1]
+        rows += db.to(self._device) if sign > 0 else -db.to(self._device)
+        return BandedOperator.from_diagonals(data, list(range(lo, hi + 1)), self._device)
+
+    def __add__(self, other):
+        return self._merged(other, +1)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self._merged(other, -1)
+
+    def __rsub__(self, other):
+        return (-self).__add__(other)
+
+    def _scaled(self, c):
+        if not np.isscalar(c):
+            return NotImplemented
+        offsets, data = self.diagonals()
+        return BandedOperator.from_diagonals(data * float(c), offsets, self._device)
+
+    def __mul__(self, c):
+        return self._scaled(c)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, c):
+        if not np.isscalar(c):
+            return NotImplemented
+        return self._scaled(1.0 / float(c))         # scipy's sparse true-divide is a multiplication by 1/c
+
+    def __neg__(self):
+        return self._scaled(-1.0)
+
+    def transpose(self):
+        offsets, data = self.diagonals()
+        n = self.shape[0]
+        out = torch.zeros_like(data)
+        for k, off in enumerate(offsets):           # A^T[j, j - off] = A[j - off, j]: diagonal -off, re-indexed by column
+            src = data[k]
+            if off >= 0:
+                out[k, :n - off] = src[off:]
+            else:
+                out[k, -off:] = src[:n + off]
+        # the diagonals keep their stored order (offsets now descending), as scipy's dia transpose does: the
+        # apply kernel sums in stored order, so (A.T @ f) rounds like scipy's
+        return BandedOperator.from_diagonals(out, [-o for o in offsets], self._device)
+
+    T = property(transpose)
+
+    def todia(self):
+        """A host ``scipy.sparse.dia_matrix`` with the same diagonals (for spsolve & co.)."""
+        from scipy import sparse
+        offsets, data = self.diagonals()
+        return sparse.dia_matrix((data.cpu().numpy(), offsets), shape=self.shape)
+
+    def tocsr(self):
+        return self.todia().tocsr()
+
+    def tocsc(self):
+        return self.todia().tocsc()
+
+    def tocoo(self):
+        return self.todia().tocoo()
 
     @property
     def data(self):
@@ -801,13 +995,9 @@ class BandedOperator:
         was built from them)."""
         if self._stored is not None:
             return self._stored()
-        A = self.toarray()
-        n = self.shape[0]
-        out = np.zeros((len(self.offsets), n))
-        for k, off in enumerate(self.offsets):
-            j = np.arange(max(0, off), min(n, n + off))
-            out[k, j] = A[j - off, j]
-        return out
+        offsets, data = self.diagonals()
+        data = data.cpu().numpy()
+        return np.stack([data[offsets.index(int(o))] for o in self.offsets])
 
 
 class FiniteDifference(ComputeTool):
