@@ -268,6 +268,10 @@ int tp_host_pin(void* ptr, int64_t bytes);
 int tp_host_unpin(void* ptr);
 int tp_host_last_transfer(int64_t* h2d_bytes, int64_t* d2h_bytes);
 int tp_host_release(void);        /* free the internal staging buffers/streams */
+/* What the host link of the current device sustains right now: pinned host <-> device cudaMemcpyAsync of `bytes`
+ * per direction, `iters` times -- H2D alone, D2H alone, both at once (GB/s per direction).  The ceiling of the
+ * host entry points above (48 B in + 48 B out per push); bench.py reports e2e against it. */
+int tp_host_link_probe(int64_t bytes, int iters, double* h2d_gbs, double* d2h_gbs, double* duplex_gbs);
 
 /* ---- on-device field update + clock for multi-step graphs ----
  * tp_plane_wave_f64: EMWave.update of the particle_in_field example

@@ -100,6 +100,7 @@ SIGNATURES = {
     "tp_host_pin": (C.c_int, [C.c_void_p, C.c_int64]),
     "tp_host_unpin": (C.c_int, [C.c_void_p]),
     "tp_host_release": (C.c_int, []),
+    "tp_host_link_probe": (C.c_int, [C.c_int64, C.c_int, c_double_p, c_double_p, c_double_p]),
     "tp_plane_wave_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tp_clock_advance_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p]),

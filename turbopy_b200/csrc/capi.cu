@@ -67,6 +67,12 @@ __global__ void selftest_division_kernel(int64_t n, uint64_t seed, unsigned long
         if (mode == 9) a = __longlong_as_double(0x7ff0000000000000ll);   // inf numerator
         if (mode == 10) b = __longlong_as_double(0x7ff0000000000000ll);  // inf denominator
         if (mode == 11) b = 0.0;
+        if (mode == 12 || mode == 13) {                                  // subnormal numerators; 12: high word zero (< 2^-1042)
+            uint64_t m = (mode == 12) ? (ma & 0xFFFFFFFFull) : ma;
+            if (m == 0) m = 1;
+            a = __longlong_as_double(static_cast<long long>(m | ((sel & (1ull << 60)) ? 0x8000000000000000ull : 0ull)));
+            b = __longlong_as_double(static_cast<long long>((static_cast<uint64_t>(1023 + static_cast<int>((sel >> 24) % 3)) << 52) | mb));
+        }
         // The contract of the FAST policy: whenever the guard and the finiteness
         // test pass (b > 0 as for every denominator of the hot path), the quotient
         // has the bits of IEEE a/b; otherwise the caller recomputes with a/b.

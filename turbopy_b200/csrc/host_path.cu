@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace tp {
 
@@ -49,10 +50,22 @@ struct HostCtx {
     int64_t h2d = 0, d2h = 0;
     bool init = false;
 };
-HostCtx g_ctx;
+// One context (streams + staging buffers) per device, created on the device that is current at the first host
+// call on it; g_host_mutex serialises the host entry points (ctypes releases the GIL around them).
+constexpr int kMaxDevices = 16;
+HostCtx g_ctxs[kMaxDevices];
+std::mutex g_host_mutex;
+int g_last_device = 0;
+
+HostCtx& current_ctx() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    g_last_device = dev;
+    return g_ctxs[dev];
+}
 
 int ensure_ctx(int64_t chunk, int64_t grid_doubles) {
-    HostCtx& c = g_ctx;
+    HostCtx& c = current_ctx();
     if (!c.init) {
         for (int b = 0; b < kBufs; ++b) TP_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream[b], cudaStreamNonBlocking));
         TP_CUDA_TRY(cudaMalloc(&c.status_dev, 4 * sizeof(uint64_t)));
@@ -107,9 +120,28 @@ int check_host_layout(const tp_particles* p) {
 
 // Shared driver: `launch(chunk particles, buffer index, first particle, stream)` runs the kernel.
 template <typename Launch>
+int run_chunks_unsafe(const tp_particles* p, const double* E_host, bool e_pp, const double* B_host, bool b_pp,
+                      Launch launch);
+
+// On ANY error the three streams are drained before returning: asynchronous copies issued earlier may still be
+// targeting the caller's arrays, which the caller is free to release as soon as the call has failed.
+template <typename Launch>
 int run_chunks(const tp_particles* p, const double* E_host, bool e_pp, const double* B_host, bool b_pp,
                Launch launch) {
-    HostCtx& c = g_ctx;
+    const int rc = run_chunks_unsafe(p, E_host, e_pp, B_host, b_pp, launch);
+    if (rc != TP_OK) {
+        HostCtx& c = current_ctx();
+        for (int b = 0; b < kBufs; ++b)
+            if (c.stream[b]) cudaStreamSynchronize(c.stream[b]);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+template <typename Launch>
+int run_chunks_unsafe(const tp_particles* p, const double* E_host, bool e_pp, const double* B_host, bool b_pp,
+                      Launch launch) {
+    HostCtx& c = current_ctx();
     const int64_t n = p->n;
     const int64_t chunk = chunk_for(n);
     int rc = TP_OK;
@@ -153,9 +185,10 @@ extern "C" int tp_boris_push_host_f64(const tp_particles* p, const tp_push_const
     if (rc) return rc;
     if (!k || !E_host || !B_host) return TP_E_ARG;
     if (p->n == 0) return TP_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
     const int64_t chunk = chunk_for(p->n);
     if ((rc = ensure_ctx(chunk, 0))) return rc;
-    g_ctx.h2d = g_ctx.d2h = 0;
+    current_ctx().h2d = current_ctx().d2h = 0;
     return run_chunks(p, E_host, e_per_particle != 0, B_host, b_per_particle != 0,
                       [&](const tp_particles& dp, double* base, int64_t ch, cudaStream_t s) {
                           const double* E = e_per_particle ? base + 6 * ch : E_host;
@@ -178,9 +211,10 @@ extern "C" int tp_gather_push_host_f64(const tp_particles* p, const tp_push_cons
     int ncomp = 0;
     for (int c = 0; c < 6; ++c) ncomp += g->comp[c] ? 1 : 0;
     const int64_t ngp = (g->ng + 1) & ~1ll;                        // keep every block 16-byte aligned
+    std::lock_guard<std::mutex> lock(g_host_mutex);
     const int64_t chunk = chunk_for(p->n);
     if ((rc = ensure_ctx(chunk, ngp * (1 + ncomp)))) return rc;
-    HostCtx& c = g_ctx;
+    HostCtx& c = current_ctx();
     c.h2d = c.d2h = 0;
     cudaStream_t s0 = c.stream[0];
     tp_grid_fields dg = *g;
@@ -240,21 +274,83 @@ extern "C" int tp_host_unpin(void* ptr) {
 }
 
 extern "C" int tp_host_last_transfer(int64_t* h2d_bytes, int64_t* d2h_bytes) {
-    if (h2d_bytes) *h2d_bytes = g_ctx.h2d;
-    if (d2h_bytes) *d2h_bytes = g_ctx.d2h;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    if (h2d_bytes) *h2d_bytes = g_ctxs[g_last_device].h2d;
+    if (d2h_bytes) *d2h_bytes = g_ctxs[g_last_device].d2h;
     return TP_OK;
 }
 
 extern "C" int tp_host_release(void) {
-    HostCtx& c = g_ctx;
-    for (int b = 0; b < kBufs; ++b) {
-        if (c.dev[b]) cudaFree(c.dev[b]);
-        c.dev[b] = nullptr;
-        if (c.stream[b]) cudaStreamDestroy(c.stream[b]);
-        c.stream[b] = nullptr;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    int keep = 0;
+    cudaGetDevice(&keep);
+    for (int dev = 0; dev < kMaxDevices; ++dev) {
+        HostCtx& c = g_ctxs[dev];
+        if (!c.init) continue;
+        cudaSetDevice(dev);
+        for (int b = 0; b < kBufs; ++b) {
+            if (c.dev[b]) cudaFree(c.dev[b]);
+            c.dev[b] = nullptr;
+            if (c.stream[b]) cudaStreamDestroy(c.stream[b]);
+            c.stream[b] = nullptr;
+        }
+        if (c.grid_dev) cudaFree(c.grid_dev);
+        if (c.status_dev) cudaFree(c.status_dev);
+        c.grid_dev = nullptr; c.status_dev = nullptr; c.cap = 0; c.grid_cap = 0; c.init = false;
     }
-    if (c.grid_dev) cudaFree(c.grid_dev);
-    if (c.status_dev) cudaFree(c.status_dev);
-    c.grid_dev = nullptr; c.status_dev = nullptr; c.cap = 0; c.grid_cap = 0; c.init = false;
+    cudaSetDevice(keep);
     return TP_OK;
+}
+
+// What the host link of THIS device sustains right now: pinned host <-> device cudaMemcpyAsync of `bytes` per
+// direction, `iters` times, H2D alone, D2H alone and both at once on two streams (GB/s each, CUDA events).  It is
+// the ceiling of the end-to-end host path (48 B in + 48 B out per push); run on all ranks at once it shows what the
+// box's host memory / PCIe fabric gives each GPU under that load.
+extern "C" int tp_host_link_probe(int64_t bytes, int iters, double* h2d_gbs, double* d2h_gbs, double* duplex_gbs) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    if (bytes <= 0 || iters <= 0) return TP_E_ARG;
+    void *h0 = nullptr, *h1 = nullptr, *d0 = nullptr, *d1 = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    auto cleanup = [&](int rc) {
+        if (h0) cudaFreeHost(h0); if (h1) cudaFreeHost(h1);
+        if (d0) cudaFree(d0); if (d1) cudaFree(d1);
+        if (s0) cudaStreamDestroy(s0); if (s1) cudaStreamDestroy(s1);
+        if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2);
+        return rc;
+    };
+#define TP_PROBE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return cleanup(static_cast<int>(_e)); } while (0)
+    TP_PROBE_TRY(cudaHostAlloc(&h0, bytes, cudaHostAllocDefault));
+    TP_PROBE_TRY(cudaHostAlloc(&h1, bytes, cudaHostAllocDefault));
+    std::memset(h0, 1, bytes); std::memset(h1, 2, bytes);          // first touch on the calling thread's NUMA node
+    TP_PROBE_TRY(cudaMalloc(&d0, bytes));
+    TP_PROBE_TRY(cudaMalloc(&d1, bytes));
+    TP_PROBE_TRY(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking));
+    TP_PROBE_TRY(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    TP_PROBE_TRY(cudaEventCreate(&e0)); TP_PROBE_TRY(cudaEventCreate(&e1)); TP_PROBE_TRY(cudaEventCreate(&e2));
+    auto timed = [&](bool up, bool down, double* out) -> int {
+        for (int pass = 0; pass < 2; ++pass) {                      // pass 0 warms up
+            cudaEventRecord(e0, s0);
+            cudaStreamWaitEvent(s1, e0, 0);
+            for (int i = 0; i < iters; ++i) {
+                if (up) cudaMemcpyAsync(d0, h0, bytes, cudaMemcpyHostToDevice, s0);
+                if (down) cudaMemcpyAsync(h1, d1, bytes, cudaMemcpyDeviceToHost, s1);
+            }
+            cudaEventRecord(e2, s1);
+            cudaStreamWaitEvent(s0, e2, 0);
+            cudaEventRecord(e1, s0);
+            const cudaError_t e = cudaEventSynchronize(e1);
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (out) *out = static_cast<double>(bytes) * iters / (ms * 1e-3) / 1e9;     // per direction
+        return TP_OK;
+    };
+    int rc;
+    if ((rc = timed(true, false, h2d_gbs)) || (rc = timed(false, true, d2h_gbs)) || (rc = timed(true, true, duplex_gbs)))
+        return cleanup(rc);
+#undef TP_PROBE_TRY
+    return cleanup(TP_OK);
 }

@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace tp {
 
@@ -697,7 +698,9 @@ static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, 
     }
 }
 
-// Scratch for the packed node records, one buffer per stream (calls on one
+// Library-owned scratch for the packed node records when the caller passes none (tp_gather_push_f64 on a grid
+// too large for shared memory; tp_gather_push_windows_f64 takes caller-owned scratch, which is what the Python
+// tool uses): one buffer per stream (calls on one
 // stream are ordered, so the buffer is free again when the next call runs).
 // Allocation is synchronous: a call that would have to (re)allocate while its
 // stream is being captured into a graph fails with TP_E_GRAPH -- run one eager
@@ -708,6 +711,8 @@ static int records_scratch(int64_t ng, cudaStream_t s, double** out) {
     struct Slot { cudaStream_t stream; double* buf; int64_t cap; int device; };
     static Slot slots[16];
     static int used = 0;
+    static std::mutex guard;                                // callers may come from several host threads
+    std::lock_guard<std::mutex> lock(guard);
     int dev = 0;
     TP_CUDA_TRY(cudaGetDevice(&dev));
     Slot* hit = nullptr;

@@ -322,13 +322,13 @@ class GridOnDevice:
     def of(cls, grid, device):
         device = torch.device(device)
         key = (id(grid), device.type, device.index if device.index is not None else torch.cuda.current_device())
-        hit = cls._cache.get(key)
+        hit = cls._cache.pop(key, None)
         if hit is None or hit[0] is not grid:
-            if len(cls._cache) >= 32:       # grids are few and long-lived; do not let a churn of them pile up device copies
-                cls._cache.clear()
+            while len(cls._cache) >= 32:    # grids are few and long-lived: drop the least recently used one only
+                cls._cache.pop(next(iter(cls._cache)))
             hit = (grid, cls(grid.r, grid.dr, device))
             hit[1]._bounds = (getattr(grid, "r_min", None), getattr(grid, "r_max", None))
-            cls._cache[key] = hit
+        cls._cache[key] = hit               # (re-)inserted last = most recently used
         return hit[1]
 
 
@@ -552,7 +552,9 @@ class BorisPush(ComputeTool):
                 if None not in key[2:]:
                     if len(self._grid_cache) > 16:
                         self._grid_cache.clear()
-                    self._grid_cache[key] = (grid, g)
+                    # gd rides along: the struct holds gd.r's device pointer, which must outlive the cached struct
+                    # even if GridOnDevice's own cache lets go of it
+                    self._grid_cache[key] = (grid, g, gd)
             status = self._status.get(dev)
             if status is None:
                 status = self._status[dev] = GatherStatus(dev)
