@@ -42,6 +42,7 @@ extern "C" {
 #define TP_E_GRID       -4        /* fewer than 2 grid nodes, dr <= 0, ...      */
 #define TP_E_MODE       -5        /* unknown field mode / formula / axis        */
 #define TP_E_GRAPH      -6        /* graph capture misuse                       */
+#define TP_E_NCCL       -100      /* libnccl not loadable; -100 - k = NCCL returned ncclResult_t k */
 
 /* ---- how E / B are given to tp_boris_push_f64 ---------------------------- */
 #define TP_FIELD_UNIFORM_HOST 0   /* ptr -> 3 doubles in HOST memory, read at call time   */
@@ -246,6 +247,19 @@ int64_t tp_reduce_scratch_doubles(void);
 int tp_reduce_moments_f64(const double* mom, int64_t stride_n, int64_t stride_c, int64_t n,
                           double mass, double mass_sq, double c2,
                           double* out8, double* scratch, tp_stream_t stream);
+
+/* ---- the path's only collective: SUM all-reduce of the diagnostic's <= 8 doubles --------------
+ * One rank per GPU.  tp_nccl_unique_id on rank 0 -> ship the 128 bytes to every rank by any means (the Python
+ * layer uses torch.distributed's store) -> tp_nccl_comm_init on every rank (collective) -> per diagnose step
+ * tp_nccl_allreduce_sum_f64(comm, out8, 8, stream), IN PLACE on the reduction's output buffer and ON THE SAME
+ * STREAM as tp_reduce_moments_f64, so reduction + all-reduce are stream-ordered without events and can be
+ * captured in a CUDA graph together with the push steps.  libnccl.so.2 is resolved at run time (the copy the
+ * process already has loaded, normally torch's); TP_E_NCCL if there is none. */
+int tp_nccl_version(int* version);
+int tp_nccl_unique_id(void* id128 /* 128 bytes out */);
+int tp_nccl_comm_init(const void* id128, int world, int rank, void** comm);
+int tp_nccl_allreduce_sum_f64(void* comm, double* buf, int64_t n, tp_stream_t stream);
+int tp_nccl_comm_destroy(void* comm);
 
 /* ---- end-to-end call on HOST buffers --------------------------------------
  * Same contract as tp_boris_push_f64 / tp_gather_push_f64 but pos/mom (and

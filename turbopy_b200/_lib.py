@@ -92,6 +92,11 @@ SIGNATURES = {
     "tp_reduce_moments_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_double, C.c_double, C.c_double,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tp_nccl_version": (C.c_int, [C.POINTER(C.c_int)]),
+    "tp_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "tp_nccl_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "tp_nccl_allreduce_sum_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tp_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
     "tp_boris_push_host_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts),
                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "tp_gather_push_host_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts), C.POINTER(GridFields),

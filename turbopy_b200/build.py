@@ -18,7 +18,7 @@ OBJ_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(HERE, "libturbopy_b200.so")
 
 SOURCES = ["capi.cu", "push_kernels.cu", "fd_kernels.cu", "reduce_kernels.cu", "scan_kernels.cu", "field_kernels.cu",
-           "sort_kernels.cu", "host_path.cu"]
+           "sort_kernels.cu", "host_path.cu", "nccl_link.cu"]
 
 # -fmad=false is part of the arithmetic contract (no FMA contraction: results
 # are bit-identical to the reference's numpy); -lineinfo maps ncu's source page
@@ -80,7 +80,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB_PATH, *objs,
+    r = subprocess.run([nvcc, "-shared", "-o", LIB_PATH, *objs, "-ldl",
                         "-gencode", "arch=compute_100a,code=sm_100a"],
                        capture_output=True, text=True)
     if r.returncode != 0:

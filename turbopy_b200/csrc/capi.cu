@@ -171,8 +171,10 @@ extern "C" const char* tp_error_string(int code) {
         case TP_E_GRID: return "turbopy_b200: invalid grid (need >= 2 nodes, dr > 0)";
         case TP_E_MODE: return "turbopy_b200: unknown field mode / formula / axis";
         case TP_E_GRAPH: return "turbopy_b200: CUDA graph capture misuse";
+        case TP_E_NCCL: return "turbopy_b200: libnccl.so.2 could not be loaded";
         default: break;
     }
+    if (code < TP_E_NCCL && code > TP_E_NCCL - 64) return "turbopy_b200: NCCL call failed (ncclResult_t = -100 - code)";
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
     return "turbopy_b200: unknown error";
 }

@@ -289,18 +289,29 @@ struct TmaWinArgs {
 };
 
 template <int FORMULA>
-__device__ __forceinline__ bool gather_step_fast_window(const GatherArgs& a, const RecView& rv, const WinView& w,
-                                                        Vec3& x, Vec3& p) {
-    double F[6];
-    Guard gd;
-    NodePair np;
-    const double xa = axis_of(x, a.axis);
-    fetch_records_window<FORMULA>(rv, w, xa, np);
-    bool ok = interp_nodes<FORMULA>(np, xa, rv.dr, rv.ng, rv.present, F, gd);
-    Vec3 E, B;
-    E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
-    boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
-    return ok && guard_ok(gd) && finite3(x.x, x.y, x.z) && a.k.fast_ok;
+__device__ __forceinline__ void gather_pair_fast_window(const GatherArgs& a, const RecView& rv, const WinView& w,
+                                                        Vec3 (&x)[2], Vec3 (&p)[2], bool& ok0, bool& ok1) {
+    NodePair n0, n1;
+    const double xa = axis_of(x[0], a.axis), xb = axis_of(x[1], a.axis);
+    fetch_pair_window<FORMULA>(rv, w, xa, xb, n0, n1);
+    {
+        double F[6];
+        Guard gd;
+        const bool ok = interp_nodes<FORMULA>(n0, xa, rv.dr, rv.ng, rv.present, F, gd);
+        Vec3 E, B;
+        E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
+        boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x[0], p[0], gd);
+        ok0 = ok && guard_ok(gd) && finite3(x[0].x, x[0].y, x[0].z) && a.k.fast_ok;
+    }
+    {
+        double F[6];
+        Guard gd;
+        const bool ok = interp_nodes<FORMULA>(n1, xb, rv.dr, rv.ng, rv.present, F, gd);
+        Vec3 E, B;
+        E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
+        boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x[1], p[1], gd);
+        ok1 = ok && guard_ok(gd) && finite3(x[1].x, x[1].y, x[1].z) && a.k.fast_ok;
+    }
 }
 
 template <int FORMULA, bool AOS>
@@ -312,7 +323,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_win_kernel(const _
     const RecView rv = make_rec_view(a, ta.ring.stream_hint);
     tma_ring_window<AOS>(
         a.p, ta.ring, ta.win, rv, a.axis, smem,
-        [&](Vec3& x, Vec3& p, const WinView& w) { return gather_step_fast_window<FORMULA>(a, rv, w, x, p); },
+        [&](Vec3 (&x)[2], Vec3 (&p)[2], const WinView& w, bool& ok0, bool& ok1) {
+            gather_pair_fast_window<FORMULA>(a, rv, w, x, p, ok0, ok1);
+        },
         [&](int64_t i, double* xs, double* ps, int pitch) {
             gather_step_exact_slot<FORMULA, false>(a, smem, i, xs, ps, pitch);
         });
@@ -832,10 +845,17 @@ static bool plan_window_ring(int64_t n, RingArgs& ring, WindowArgs& win, size_t&
     const DeviceProps& d = device_props();
     if (!windows_enabled() || !records_enabled()) return false;
     if (!plan_ring(n, kWinFront, ring, smem, blocks)) return false;
-    const int64_t left = d.smem_optin - 1024 - static_cast<int64_t>(smem);
+    // Default: what is left of the 164 KB shared-memory carve-out the 3-stage ring needs anyway (the next
+    // configurable sizes are 196 and 228 KB, and every step up takes 32 KB from the L1 that the random-order
+    // fallback lives on: measured 31 -> 19 G pushes/s in random order with 228 KB).  ~9 KB per stage = 148 node
+    // records = 145 cells per tile; a cell-ordered 960-particle tile of config 3 spans 14-67 cells.
+    const int64_t carve = std::min<int64_t>(164 * 1024, d.smem_optin);
+    const int64_t left = carve - 1024 - static_cast<int64_t>(smem);
     int64_t per_stage = (left / ring.nstages) & ~int64_t(127);
-    if (const char* cap = std::getenv("TURBOPY_B200_WINDOW_BYTES"))
-        per_stage = std::min<int64_t>(per_stage, std::max(0, std::atoi(cap)) & ~127);
+    if (const char* cap = std::getenv("TURBOPY_B200_WINDOW_BYTES")) {          // tuning knob
+        const int64_t most = ((d.smem_optin - 1024 - static_cast<int64_t>(smem)) / ring.nstages) & ~int64_t(127);
+        per_stage = std::min<int64_t>(most, std::max(0, std::atoi(cap)) & ~127);
+    }
     if (per_stage < 16 * kRecBytes) return false;
     win.win_off = static_cast<uint32_t>(smem);                 // tiles_off and kTileBytes are multiples of 128
     win.win_bytes = static_cast<uint32_t>(per_stage);

@@ -57,26 +57,39 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 
-// The two nodes of the particle's cell from the staged window when it covers the cell, else from the global
-// record table (fetch_records).  Returns whether the window served it (statistics only).
+// The two nodes of the cells of BOTH particles of a thread: from the staged window when the window covers every
+// particle of the warp (the cell-ordered case: one uniform branch per warp and tile, broadcast-friendly LDS), else
+// from the global record table with all eight 256-bit loads of the thread issued back to back (the round-1 access
+// pattern: the loads of the two particles overlap each other's latency).  Same values either way.
 template <int FORMULA>
-__device__ __forceinline__ void fetch_records_window(const RecView& rv, const WinView& w, double x, NodePair& np) {
-    const int j = guess_cell(x, rv.r_first, rv.inv_dr, rv.ng);
-    if (static_cast<unsigned>(j - w.jlo) < static_cast<unsigned>(w.ncells)) {
-        np.j = j;
-        const uint32_t a0 = w.base + static_cast<uint32_t>(j - w.wlo) * kRecBytes;
-        double a[8], b[8];
-        lds_record(a0, a);
-        lds_record(a0 + kRecBytes, b);
-        np.x0 = a[0]; np.x1 = b[0];
-        if (FORMULA == TP_INTERP_A) {       // the window holds records jlo-1 .. jhi+2 (clamped to the grid)
-            np.xm = lds_f64(w.base + static_cast<uint32_t>(max(j - 1, 0) - w.wlo) * kRecBytes);
-            np.xp = lds_f64(w.base + static_cast<uint32_t>(min(j + 2, rv.ng - 1) - w.wlo) * kRecBytes);
-        }
+__device__ __forceinline__ void fetch_records_smem(const RecView& rv, const WinView& w, int j, NodePair& np) {
+    np.j = j;
+    const uint32_t a0 = w.base + static_cast<uint32_t>(j - w.wlo) * kRecBytes;
+    double a[8], b[8];
+    lds_record(a0, a);
+    lds_record(a0 + kRecBytes, b);
+    np.x0 = a[0]; np.x1 = b[0];
+    if (FORMULA == TP_INTERP_A) {           // the window holds records jlo-1 .. jhi+2 (clamped to the grid)
+        np.xm = lds_f64(w.base + static_cast<uint32_t>(max(j - 1, 0) - w.wlo) * kRecBytes);
+        np.xp = lds_f64(w.base + static_cast<uint32_t>(min(j + 2, rv.ng - 1) - w.wlo) * kRecBytes);
+    }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { np.y0[k] = a[1 + k]; np.y1[k] = b[1 + k]; }
+    for (int k = 0; k < 6; ++k) { np.y0[k] = a[1 + k]; np.y1[k] = b[1 + k]; }
+}
+
+template <int FORMULA>
+__device__ __forceinline__ void fetch_pair_window(const RecView& rv, const WinView& w, double xa, double xb,
+                                                  NodePair& na, NodePair& nb) {
+    const int ja = guess_cell(xa, rv.r_first, rv.inv_dr, rv.ng);
+    const int jb = guess_cell(xb, rv.r_first, rv.inv_dr, rv.ng);
+    const bool in = static_cast<unsigned>(ja - w.jlo) < static_cast<unsigned>(w.ncells) &&
+                    static_cast<unsigned>(jb - w.jlo) < static_cast<unsigned>(w.ncells);
+    if (__all_sync(0xffffffffu, in)) {
+        fetch_records_smem<FORMULA>(rv, w, ja, na);
+        fetch_records_smem<FORMULA>(rv, w, jb, nb);
     } else {
-        fetch_records<FORMULA>(rv, x, np);
+        fetch_records<FORMULA>(rv, xa, na);
+        fetch_records<FORMULA>(rv, xb, nb);
     }
 }
 
@@ -84,7 +97,7 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t byte
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-// Ring driver.  fast(x, p, win) -> bool updates one particle in registers; recover as in tma_ring.
+// Ring driver.  fast(x[2], p[2], win, ok0, ok1) updates the thread's two particles in registers; recover as in tma_ring.
 template <bool AOS, typename Fast, typename Recover>
 __device__ __forceinline__ void tma_ring_window(const ParticleArgs& P, const RingArgs& ra, const WindowArgs& wa,
                                                 const RecView& rv, int axis, unsigned char* smem, Fast fast,
@@ -156,8 +169,8 @@ __device__ __forceinline__ void tma_ring_window(const ParticleArgs& P, const Rin
         w.base = smem_u32(wins + static_cast<size_t>(s) * wa.win_bytes);
         Vec3 x[2], p[2];
         stage_read<AOS>(stage, x, p);
-        const bool ok0 = fast(x[0], p[0], w);
-        const bool ok1 = fast(x[1], p[1], w);
+        bool ok0, ok1;
+        fast(x, p, w, ok0, ok1);
         stage_write<AOS>(stage, x, p);
         // the cells this warp's particles moved into: next call's window (particles that left the fast path are
         // served from global memory next time, whatever the window)

@@ -43,11 +43,65 @@ def init_process_group(backend=None):
     return rank, world, local
 
 
+class DiagnosticComm:
+    """The path's own NCCL communicator (one rank per GPU), used for exactly one thing: the in-place SUM all-reduce
+    of the diagnostic's 8 doubles, enqueued on the CURRENT (compute) stream through the C ABI
+    (tp_nccl_allreduce_sum_f64).  That keeps ``reduce_moments`` -> all-reduce stream-ordered with the push kernels
+    and capturable in a ``StepGraph``; ``torch.distributed.all_reduce`` runs on the process group's
+    own stream behind event waits instead.  torch.distributed is only the bootstrap: it carries the 128-byte
+    NCCL unique id from rank 0 to the other ranks."""
+
+    _instance = None
+
+    def __init__(self):
+        import ctypes as C
+
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        lib = _lib.lib()
+        ident = (C.c_char * 128)()
+        if self.rank == 0:
+            _lib.check(lib.tp_nccl_unique_id(ident))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0)                # pickled through the process group (CPU or GPU backend)
+        ident = (C.c_char * 128).from_buffer_copy(box[0])
+        self._comm = C.c_void_p()
+        _lib.check(lib.tp_nccl_comm_init(ident, self.world, self.rank, C.byref(self._comm)))
+
+    @classmethod
+    def get(cls):
+        """The process-wide communicator, created collectively on first use (every rank must get here)."""
+        if cls._instance is None:
+            cls._instance = cls()
+        return cls._instance
+
+    def allreduce_sum_(self, t):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise TypeError("DiagnosticComm reduces contiguous CUDA float64 tensors")
+        C = self._C
+        self._lib.check(self._lib.lib().tp_nccl_allreduce_sum_f64(
+            self._comm, C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+        return t
+
+    def close(self):
+        if self._comm:
+            self._lib.lib().tp_nccl_comm_destroy(self._comm)
+            self._comm = self._C.c_void_p()
+        if DiagnosticComm._instance is self:
+            DiagnosticComm._instance = None
+
+
 def allreduce_sum_(t):
-    """In-place SUM all-reduce of the diagnostic scalars (NCCL over NVLink on
-    GPUs); a no-op in a single-process run."""
+    """In-place SUM all-reduce of the diagnostic scalars; a no-op in a single-process run.  CUDA tensors go
+    through the path's own NCCL communicator on the current stream (:class:`DiagnosticComm`, NVLink / NVSwitch);
+    host tensors (the gloo tests) through ``torch.distributed``.  ``TURBOPY_B200_TORCH_ALLREDUCE=1`` forces the
+    latter for CUDA tensors too (A-B switch)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if t.is_cuda and os.environ.get("TURBOPY_B200_TORCH_ALLREDUCE", "0") != "1":
+            DiagnosticComm.get().allreduce_sum_(t)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
 
 
