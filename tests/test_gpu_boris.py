@@ -40,7 +40,7 @@ def test_division_selftest(tp):
     n = 200_000_000
     _lib.check(_lib.lib().tp_selftest_division(n, 12345, C.byref(bad), C.byref(taken), None))
     assert bad.value == 0
-    assert taken.value > n // 2          # the fast path is the common case, not a dead branch
+    assert taken.value > 0.45 * n        # the fast path is the common case, not a dead branch
 
 
 def test_roots_selftest(tp):

@@ -131,6 +131,32 @@ __device__ __forceinline__ void fetch_records(const RecView& rv, double x, NodeP
     for (int k = 0; k < 6; ++k) { np.y0[k] = a[1 + k]; np.y1[k] = b[1 + k]; }
 }
 
+// CELL records for formula B (numpy.interp: out = slope*(x - x0) + y0 with slope = (y1-y0)/(x1-x0)): the slope
+// belongs to the cell, not to the particle, so pack_cells_kernel forms it once per cell and step with the plain IEEE
+// division numpy uses, and a particle needs ONE 128-byte record
+//     cell j = {r[j], r[j+1], y[j] (6 components), slope_j (6 components), 0, 0}
+// (one cache line; the two 64-byte node records it replaces are the same number of bytes) and, per component, one
+// multiply and one add -- no reciprocal, no quotient, no guard.  Absent components are stored as y = slope = +0.0.
+constexpr int kCellDoubles = 16;
+
+__device__ __forceinline__ void ld_cell(const double* p, double (&c)[16], uint64_t policy) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=d"(c[4 * q]), "=d"(c[4 * q + 1]), "=d"(c[4 * q + 2]), "=d"(c[4 * q + 3]) : "l"(p + 4 * q), "l"(policy));
+}
+
+__device__ __forceinline__ bool interp_cell_b(const double (&c)[16], double x, unsigned present, double (&F)[6]) {
+    const double x0 = c[0], x1 = c[1];
+    const double dx0 = x - x0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        F[k] = 0.0;
+        if (present & (1u << k)) F[k] = c[8 + k] * dx0 + c[2 + k];
+    }
+    return (x0 < x) && (x < x1);                    // strictly inside the cell (false for NaN): else the exact path
+}
+
 // Interpolate the present components from a NodePair.  `present` bit k = 0 means
 // the component is identically zero (F[k] = +0.0 without touching the data).
 template <int FORMULA>

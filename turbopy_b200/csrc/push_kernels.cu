@@ -152,6 +152,30 @@ __global__ void __launch_bounds__(256) pack_nodes_kernel(const __grid_constant__
     }
 }
 
+// cell j = {r[j], r[j+1], y[j][0..5], slope_j[0..5], 0, 0} with slope = (y[j+1]-y[j])/(r[j+1]-r[j]) by IEEE division,
+// exactly numpy.interp's per-cell quantity (gather_math.cuh: interp_cell_b); absent components as +0.0.
+__global__ void __launch_bounds__(256) pack_cells_kernel(const __grid_constant__ GatherArgs a, double* __restrict__ rec) {
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < a.ng - 1; j += gstride) {
+        double v[16];
+        v[0] = a.r[j]; v[1] = a.r[j + 1];
+        const double dx = v[1] - v[0];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            v[2 + k] = 0.0; v[8 + k] = 0.0;
+            if (a.comp[k]) {
+                const double y0 = a.comp[k][j * a.stride[k]], y1 = a.comp[k][(j + 1) * a.stride[k]];
+                v[2 + k] = y0;
+                v[8 + k] = (y1 - y0) / dx;
+            }
+        }
+        v[14] = 0.0; v[15] = 0.0;
+        double* dst = rec + j * kCellDoubles;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st2(dst + 2 * q, make_double2(v[2 * q], v[2 * q + 1]));
+    }
+}
+
 // Recovery path: reload the particle (nothing has been stored yet), complete
 // gather semantics, IEEE divisions; out-of-grid particles are flagged and left
 // untouched.  The out-of-line entry points below take only the grid-constant
@@ -314,17 +338,45 @@ __device__ __forceinline__ void gather_pair_fast_window(const GatherArgs& a, con
     }
 }
 
+// formula B on cell records: no division in the gather at all
+__device__ __forceinline__ void gather_pair_fast_cells(const GatherArgs& a, const RecView& rv, const WinView& w,
+                                                       Vec3 (&x)[2], Vec3 (&p)[2], bool& ok0, bool& ok1) {
+    double c0[16], c1[16];
+    const double xa = axis_of(x[0], a.axis), xb = axis_of(x[1], a.axis);
+    fetch_pair_cells(rv, w, xa, xb, c0, c1);
+    {
+        double F[6];
+        Guard gd;
+        const bool ok = interp_cell_b(c0, xa, rv.present, F);
+        Vec3 E, B;
+        E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
+        boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x[0], p[0], gd);
+        ok0 = ok && guard_ok(gd) && finite3(x[0].x, x[0].y, x[0].z) && a.k.fast_ok;
+    }
+    {
+        double F[6];
+        Guard gd;
+        const bool ok = interp_cell_b(c1, xb, rv.present, F);
+        Vec3 E, B;
+        E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
+        boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x[1], p[1], gd);
+        ok1 = ok && guard_ok(gd) && finite3(x[1].x, x[1].y, x[1].z) && a.k.fast_ok;
+    }
+}
+
 template <int FORMULA, bool AOS>
 __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_win_kernel(const __grid_constant__ TmaWinArgs ta) {
+    constexpr bool CELLS = FORMULA == TP_INTERP_B;          // (the host packs the matching record table)
     extern __shared__ __align__(128) unsigned char smem[];
     const GatherArgs& a = ta.g;
     ring_init(ta.ring, smem);
     __syncthreads();
     const RecView rv = make_rec_view(a, ta.ring.stream_hint);
-    tma_ring_window<AOS>(
+    tma_ring_window<AOS, CELLS>(
         a.p, ta.ring, ta.win, rv, a.axis, smem,
         [&](Vec3 (&x)[2], Vec3 (&p)[2], const WinView& w, bool& ok0, bool& ok1) {
-            gather_pair_fast_window<FORMULA>(a, rv, w, x, p, ok0, ok1);
+            if (CELLS) gather_pair_fast_cells(a, rv, w, x, p, ok0, ok1);
+            else gather_pair_fast_window<FORMULA>(a, rv, w, x, p, ok0, ok1);
         },
         [&](int64_t i, double* xs, double* ps, int pitch) {
             gather_step_exact_slot<FORMULA, false>(a, smem, i, xs, ps, pitch);
@@ -793,13 +845,14 @@ static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int
     return true;
 }
 
-static int pack_records(const GatherArgs& a, cudaStream_t s, double* caller_scratch, double** rec) {
+static int pack_records(const GatherArgs& a, cudaStream_t s, double* caller_scratch, double** rec, bool cells = false) {
     int rc;
-    if (caller_scratch) *rec = caller_scratch;               // ng * 64 bytes owned by the caller (stream-ordered by it)
-    else if ((rc = records_scratch(a.ng, s, rec))) return rc;
+    if (caller_scratch) *rec = caller_scratch;               // 16 * ng doubles owned by the caller (stream-ordered by it)
+    else if ((rc = records_scratch(cells ? 2 * static_cast<int64_t>(a.ng) : a.ng, s, rec))) return rc;
     const DeviceProps& d = device_props();
     const int pblocks = static_cast<int>(std::min<int64_t>((a.ng + 255) / 256, static_cast<int64_t>(d.sm_count) * 8));
-    pack_nodes_kernel<<<pblocks, 256, 0, s>>>(a, *rec);
+    if (cells) pack_cells_kernel<<<pblocks, 256, 0, s>>>(a, *rec);
+    else pack_nodes_kernel<<<pblocks, 256, 0, s>>>(a, *rec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -888,7 +941,7 @@ static int try_gather_push_windows(const GatherArgs& a, int formula, bool aos, i
     ta.win.bounds = reinterpret_cast<int2*>(bounds);
     int rc;
     double* rec = nullptr;
-    if ((rc = pack_records(a, s, rec_scratch, &rec))) return rc;
+    if ((rc = pack_records(a, s, rec_scratch, &rec, formula == TP_INTERP_B))) return rc;
     ta.g.records = rec;
     ta.ring.stream_hint = l2_hints_enabled() ? 1 : 0;
     switch (formula) {

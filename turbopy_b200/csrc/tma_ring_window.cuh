@@ -30,7 +30,8 @@ namespace tp {
 
 constexpr uint32_t kWinMetaOff = kSmemHeader;          // per stage: {jlo, ncells, next_min, next_max}, 16 B each
 constexpr uint32_t kWinFront = 2 * kSmemHeader;        // barriers + meta
-constexpr uint32_t kRecBytes = 64;
+constexpr uint32_t kRecBytes = 64;                     // node records {r, E, B, 0}: formulas A and C
+constexpr uint32_t kCellBytes = 128;                   // cell records {x0, x1, y0[6], slope[6], 0, 0}: formula B
 
 struct WindowArgs {
     int2* bounds;               // per tile {first cell, number of cells} the tile's particles sit in; {*, 0} = unknown
@@ -93,12 +94,38 @@ __device__ __forceinline__ void fetch_pair_window(const RecView& rv, const WinVi
     }
 }
 
+// The same for cell records (formula B): one 128-byte record per particle, seven LDS.128 from the window or four
+// 256-bit loads of one cache line from the global table.
+__device__ __forceinline__ void lds_cell(uint32_t addr, double (&c)[16]) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q)
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c[2 * q]), "=d"(c[2 * q + 1]) : "r"(addr + 16 * q));
+    c[14] = 0.0; c[15] = 0.0;
+}
+
+__device__ __forceinline__ void fetch_pair_cells(const RecView& rv, const WinView& w, double xa, double xb,
+                                                 double (&ca)[16], double (&cb)[16]) {
+    const int ja = guess_cell(xa, rv.r_first, rv.inv_dr, rv.ng);
+    const int jb = guess_cell(xb, rv.r_first, rv.inv_dr, rv.ng);
+    const bool in = static_cast<unsigned>(ja - w.jlo) < static_cast<unsigned>(w.ncells) &&
+                    static_cast<unsigned>(jb - w.jlo) < static_cast<unsigned>(w.ncells);
+    if (__all_sync(0xffffffffu, in)) {
+        lds_cell(w.base + static_cast<uint32_t>(ja - w.wlo) * kCellBytes, ca);
+        lds_cell(w.base + static_cast<uint32_t>(jb - w.wlo) * kCellBytes, cb);
+    } else {
+        ld_cell(rv.rec + static_cast<int64_t>(ja) * kCellDoubles, ca, rv.policy);
+        ld_cell(rv.rec + static_cast<int64_t>(jb) * kCellDoubles, cb, rv.policy);
+    }
+}
+
 __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
 // Ring driver.  fast(x[2], p[2], win, ok0, ok1) updates the thread's two particles in registers; recover as in tma_ring.
-template <bool AOS, typename Fast, typename Recover>
+// CELLS: the record table holds 128-byte cell records (cells jlo .. jhi are staged) instead of 64-byte node records
+// (nodes jlo-1 .. jhi+2, clamped: formula A also looks at the outer neighbours).
+template <bool AOS, bool CELLS, typename Fast, typename Recover>
 __device__ __forceinline__ void tma_ring_window(const ParticleArgs& P, const RingArgs& ra, const WindowArgs& wa,
                                                 const RecView& rv, int axis, unsigned char* smem, Fast fast,
                                                 Recover recover) {
@@ -108,7 +135,8 @@ __device__ __forceinline__ void tma_ring_window(const ParticleArgs& P, const Rin
     unsigned char* tiles = smem + ra.tiles_off;
     unsigned char* wins = smem + wa.win_off;
     const int nst = ra.nstages;
-    const int cap_records = static_cast<int>(wa.win_bytes / kRecBytes);
+    constexpr uint32_t kRec = CELLS ? kCellBytes : kRecBytes;
+    const int cap_records = static_cast<int>(wa.win_bytes / kRec);
     const int64_t t0 = blockIdx.x, tstep = gridDim.x;
     int s = 0;
     uint32_t parity = 0;
@@ -122,16 +150,17 @@ __device__ __forceinline__ void tma_ring_window(const ParticleArgs& P, const Rin
                 int wlo = 0, nrec = 0;
                 const int64_t jhi = static_cast<int64_t>(b.x) + b.y - 1;       // (64-bit: the words may be garbage)
                 if (b.y > 0 && b.x >= 0 && jhi <= rv.ng - 2) {
-                    wlo = max(b.x - 1, 0);
-                    const int whi = min(static_cast<int>(jhi) + 2, rv.ng - 1);  // records jlo-1 .. jhi+2, clamped
+                    wlo = CELLS ? b.x : max(b.x - 1, 0);
+                    const int whi = CELLS ? static_cast<int>(jhi) : min(static_cast<int>(jhi) + 2, rv.ng - 1);
                     nrec = whi - wlo + 1;
                     if (nrec > cap_records) nrec = 0;                           // too wide for the stage
                 }
                 meta[st] = make_int4(b.x, nrec ? b.y : 0, 0x7fffffff, static_cast<int>(0x80000000u));
                 if (nrec) {
-                    mbar_expect_tx_only(&full[st], static_cast<uint32_t>(nrec) * kRecBytes);
-                    tma_bulk_g2s_hint(wins + static_cast<size_t>(st) * wa.win_bytes, rv.rec + static_cast<int64_t>(wlo) * 8,
-                                      static_cast<uint32_t>(nrec) * kRecBytes, &full[st], pol_keep);
+                    mbar_expect_tx_only(&full[st], static_cast<uint32_t>(nrec) * kRec);
+                    tma_bulk_g2s_hint(wins + static_cast<size_t>(st) * wa.win_bytes,
+                                      rv.rec + static_cast<int64_t>(wlo) * (kRec / 8),
+                                      static_cast<uint32_t>(nrec) * kRec, &full[st], pol_keep);
                 }
                 if (hint) tile_load_hint(P, t, tiles + st * kTileBytes, &full[st], pol_stream);
                 else tile_load<AOS>(P, t, tiles + st * kTileBytes, &full[st]);
@@ -165,7 +194,7 @@ __device__ __forceinline__ void tma_ring_window(const ParticleArgs& P, const Rin
         double* stage = reinterpret_cast<double*>(tiles + s * kTileBytes);
         const int4 m = meta[s];
         WinView w;
-        w.jlo = m.x; w.ncells = m.y; w.wlo = max(m.x - 1, 0);
+        w.jlo = m.x; w.ncells = m.y; w.wlo = CELLS ? m.x : max(m.x - 1, 0);
         w.base = smem_u32(wins + static_cast<size_t>(s) * wa.win_bytes);
         Vec3 x[2], p[2];
         stage_read<AOS>(stage, x, p);
