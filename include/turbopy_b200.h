@@ -42,6 +42,7 @@ extern "C" {
 #define TP_E_GRID       -4        /* fewer than 2 grid nodes, dr <= 0, ...      */
 #define TP_E_MODE       -5        /* unknown field mode / formula / axis        */
 #define TP_E_GRAPH      -6        /* graph capture misuse                       */
+#define TP_RECORDS_DOUBLES_PER_NODE 18   /* caller-owned record scratch of tp_gather_push_windows_f64 */
 #define TP_E_NCCL       -100      /* libnccl not loadable; -100 - k = NCCL returned ncclResult_t k */
 
 /* ---- how E / B are given to tp_boris_push_f64 ---------------------------- */
@@ -161,13 +162,13 @@ int tp_gather_push_steps_f64(const tp_particles* p, const tp_push_consts* k, con
  * next call.  It is a hint: particles whose cell is not covered (zeroed or stale bounds, particles in random
  * order) take their records from L2 like tp_gather_push_f64 -- identical results either way.  With a NULL
  * tile_bounds, or when tp_gather_windows_len() is 0, this IS tp_gather_push_f64.  records_scratch: where the
- * per-step record table is packed each call (formula B: 128-byte cell records {r[j], r[j+1], y[j], slope_j} with
- * numpy.interp's per-cell slopes; formulas A, C: 64-byte node records {r, E, B, 0}); caller-owned memory makes the call capturable in a
+ * per-step record table is packed each call (formula B: cell records {r[j], r[j+1], y[j], slope_j} with
+ * numpy.interp's per-cell slopes, 144-byte pitch; formulas A, C: node records {r, E, B, 0}, 80-byte pitch); caller-owned memory makes the call capturable in a
  * CUDA graph on any stream without a warm-up call (the library-owned scratch is allocated per stream). */
 int tp_gather_push_windows_f64(const tp_particles* p, const tp_push_consts* k,
                                const tp_grid_fields* g, int axis, int formula,
                                int32_t* tile_bounds, int64_t tile_bounds_len,
-                               double* records_scratch /* DEVICE, 16*ng doubles, or NULL: library-owned scratch */,
+                               double* records_scratch /* DEVICE, TP_RECORDS_DOUBLES_PER_NODE*ng doubles, or NULL: library-owned */,
                                uint64_t* status, tp_stream_t stream);
 int64_t tp_gather_windows_len(const tp_particles* p, const tp_grid_fields* g);
 /* prime tile_bounds from the particles' current coordinates (8 B read per particle); a zeroed array is valid too */

@@ -119,7 +119,7 @@ def test_bounds_are_only_a_hint(tp, monkeypatch):
     run(lambda w: w.copy_(w.roll(2 * 37)))                                      # every tile gets another tile's cells
     run(lambda w: w.copy_(torch.from_numpy(rng.integers(-2**31, 2**31 - 1, w.shape[0], dtype=np.int64)
                                            .astype(np.int32)).cuda()))
-    narrow = run(lambda w: None, env=("TURBOPY_B200_WINDOW_BYTES", "1024"))     # 16 records: most tiles do not fit
+    narrow = run(lambda w: None, env=("TURBOPY_B200_WINDOW_BYTES", "4096"))     # 28 cells: the tiles do not fit
     ntiles = n // TILE
     assert np.array_equal(good[:ntiles], narrow[:ntiles])
 

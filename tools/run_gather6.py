@@ -67,8 +67,47 @@ def run(ng, n, order, formula, steps, comps=6, quiet=False):
     return row
 
 
+def decay(ng, n, formula, blocks, steps_per_block):
+    """Throughput block by block after ONE sort: how long a cell order lasts (dt = dr/(2c), thermal 0.1c momenta)."""
+    r = ogrid.grid_points(0.0, 1.0, ng)
+    dr = ogrid.grid_dr(0.0, 1.0, ng)
+    owner = SimpleNamespace(clock=SimpleNamespace(dt=0.5 * dr / C),
+                            grid=SimpleNamespace(r=r, dr=dr, num_points=ng, r_min=0.0, r_max=1.0))
+    tool = tp.BorisPush(owner, {"type": "BorisPush"})
+    rd = torch.from_numpy(r).cuda()
+    E = torch.stack([1e3 * torch.cos(6.28 * (k + 1) * rd) for k in range(3)], dim=1).contiguous()
+    B = torch.stack([torch.sin(6.28 * (k + 1) * rd) for k in range(3)], dim=1).contiguous()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    pos, mom = tp.soa_particles(n), tp.soa_particles(n)
+    pos.copy_(0.05 + 0.9 * torch.rand((n, 3), dtype=torch.float64, device="cuda", generator=g))
+    mom.copy_(torch.randn((n, 3), dtype=torch.float64, device="cuda", generator=g) * (M_E * C * 0.1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tp.sort_by_cell(pos, mom, owner.grid)
+    e1.record()
+    torch.cuda.synchronize()
+    sort_ms = e0.elapsed_time(e1)
+    rows = []
+    for b in range(blocks):
+        e0.record()
+        for _ in range(steps_per_block):
+            tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, formula=formula)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps_per_block
+        wins = [w[0] for w in tool._windows.values() if w[0] is not None]
+        cells = float(wins[0].view(-1, 2)[: n // 960, 1].float().mean()) if wins else None
+        rows.append({"steps_since_sort": (b + 1) * steps_per_block, "ms_per_step": ms,
+                     "frac_of_hbm_peak": 96.0 * n / (ms * 1e-3) / 1e9 / peak(), "cells_per_tile_mean": cells})
+        print(json.dumps(rows[-1]), flush=True)
+    tool.check_status()
+    return {"ng": ng, "particles": n, "formula": formula, "sort_ms": sort_ms, "blocks": rows,
+            "windows": os.environ.get("TURBOPY_B200_WINDOWS", "1") != "0"}
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--decay", type=int, default=0, help="blocks of 50 steps to time after one sort")
     ap.add_argument("--ng", type=int, default=1025)
     ap.add_argument("--n", type=int, default=16 << 20)
     ap.add_argument("--steps", type=int, default=20)
@@ -77,6 +116,12 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--json")
     a = ap.parse_args()
+    if a.decay:
+        out = decay(a.ng, a.n, a.formula, a.decay, 50)
+        if a.json:
+            with open(a.json, "w") as f:
+                json.dump(out, f, indent=1)
+        return
     if not a.sweep:
         run(a.ng, a.n, a.order, a.formula, a.steps)
         return

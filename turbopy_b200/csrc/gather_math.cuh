@@ -114,18 +114,35 @@ __device__ __forceinline__ void fetch_nodes_lin(const GridView& g, const LinGrid
     }
 }
 
-template <int FORMULA>
+// 16-byte aligned variant (record pitches that are not multiples of 32 bytes): four 128-bit loads
+__device__ __forceinline__ void ld_record16(const double* p, double (&v)[8], uint64_t policy) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                     : "=d"(v[2 * q]), "=d"(v[2 * q + 1]) : "l"(p + 2 * q), "l"(policy));
+}
+
+// PITCH: doubles between consecutive node records -- 8 (packed, 256-bit loads) or kNodePitchWin (the windowed
+// kernel's table, padded so that records of neighbouring nodes start in different shared-memory bank groups).
+constexpr int kNodePitchWin = 10;
+
+template <int FORMULA, int PITCH = 8>
 __device__ __forceinline__ void fetch_records(const RecView& rv, double x, NodePair& np) {
     const int j = guess_cell(x, rv.r_first, rv.inv_dr, rv.ng);
     np.j = j;
     double a[8], b[8];
-    const double* base = rv.rec + static_cast<int64_t>(j) * 8;
-    ld_record(base, a, rv.policy);
-    ld_record(base + 8, b, rv.policy);
+    const double* base = rv.rec + static_cast<int64_t>(j) * PITCH;
+    if (PITCH % 4 == 0) {
+        ld_record(base, a, rv.policy);
+        ld_record(base + PITCH, b, rv.policy);
+    } else {
+        ld_record16(base, a, rv.policy);
+        ld_record16(base + PITCH, b, rv.policy);
+    }
     np.x0 = a[0]; np.x1 = b[0];
     if (FORMULA == TP_INTERP_A) {
-        np.xm = rv.rec[static_cast<int64_t>(max(j - 1, 0)) * 8];
-        np.xp = rv.rec[static_cast<int64_t>(min(j + 2, rv.ng - 1)) * 8];
+        np.xm = rv.rec[static_cast<int64_t>(max(j - 1, 0)) * PITCH];
+        np.xp = rv.rec[static_cast<int64_t>(min(j + 2, rv.ng - 1)) * PITCH];
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) { np.y0[k] = a[1 + k]; np.y1[k] = b[1 + k]; }
@@ -134,16 +151,21 @@ __device__ __forceinline__ void fetch_records(const RecView& rv, double x, NodeP
 // CELL records for formula B (numpy.interp: out = slope*(x - x0) + y0 with slope = (y1-y0)/(x1-x0)): the slope
 // belongs to the cell, not to the particle, so pack_cells_kernel forms it once per cell and step with the plain IEEE
 // division numpy uses, and a particle needs ONE 128-byte record
-//     cell j = {r[j], r[j+1], y[j] (6 components), slope_j (6 components), 0, 0}
-// (one cache line; the two 64-byte node records it replaces are the same number of bytes) and, per component, one
+//     cell j = {r[j], r[j+1], y[j] (6 components), slope_j (6 components)} + 4 pad doubles
+// (112 payload bytes; the two 64-byte node records it replaces are the same number of bytes) and, per component, one
 // multiply and one add -- no reciprocal, no quotient, no guard.  Absent components are stored as y = slope = +0.0.
-constexpr int kCellDoubles = 16;
+// The table's pitch is 18 doubles (144 B), not 16: in the shared-memory window, lanes that read the same 16-byte
+// chunk of DIFFERENT cells then fall into different bank groups (144/16 = 9 is odd), where a 128-byte pitch puts
+// all of them on the same four banks (8-way conflicts as soon as the particle order has decayed a little:
+// measured 92 % -> 61 % of the HBM peak 100 steps after a sort with the 128-byte pitch).
+constexpr int kCellDoubles = 18;
 
 __device__ __forceinline__ void ld_cell(const double* p, double (&c)[16], uint64_t policy) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-        asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
-                     : "=d"(c[4 * q]), "=d"(c[4 * q + 1]), "=d"(c[4 * q + 2]), "=d"(c[4 * q + 3]) : "l"(p + 4 * q), "l"(policy));
+    for (int q = 0; q < 7; ++q)
+        asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                     : "=d"(c[2 * q]), "=d"(c[2 * q + 1]) : "l"(p + 2 * q), "l"(policy));
+    c[14] = 0.0; c[15] = 0.0;
 }
 
 __device__ __forceinline__ bool interp_cell_b(const double (&c)[16], double x, unsigned present, double (&F)[6]) {

@@ -138,6 +138,7 @@ __device__ __forceinline__ RecView make_rec_view(const GatherArgs& a, int keep_i
 }
 
 // record j = {r[j], Ex[j], Ey[j], Ez[j], Bx[j], By[j], Bz[j], 0}; absent components are stored as +0.0
+template <int PITCH>
 __global__ void __launch_bounds__(256) pack_nodes_kernel(const __grid_constant__ GatherArgs a, double* __restrict__ rec) {
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < a.ng; j += gstride) {
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) pack_nodes_kernel(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 6; ++k) v[1 + k] = a.comp[k] ? a.comp[k][j * a.stride[k]] : 0.0;
         v[7] = 0.0;
-        double* dst = rec + j * 8;
+        double* dst = rec + j * PITCH;
 #pragma unroll
         for (int q = 0; q < 4; ++q) st2(dst + 2 * q, make_double2(v[2 * q], v[2 * q + 1]));
     }
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) pack_nodes_kernel(const __grid_constant__
 __global__ void __launch_bounds__(256) pack_cells_kernel(const __grid_constant__ GatherArgs a, double* __restrict__ rec) {
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < a.ng - 1; j += gstride) {
-        double v[16];
+        double v[14];
         v[0] = a.r[j]; v[1] = a.r[j + 1];
         const double dx = v[1] - v[0];
 #pragma unroll
@@ -169,10 +170,9 @@ __global__ void __launch_bounds__(256) pack_cells_kernel(const __grid_constant__
                 v[8 + k] = (y1 - y0) / dx;
             }
         }
-        v[14] = 0.0; v[15] = 0.0;
         double* dst = rec + j * kCellDoubles;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) st2(dst + 2 * q, make_double2(v[2 * q], v[2 * q + 1]));
+        for (int q = 0; q < 7; ++q) st2(dst + 2 * q, make_double2(v[2 * q], v[2 * q + 1]));
     }
 }
 
@@ -845,14 +845,17 @@ static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int
     return true;
 }
 
-static int pack_records(const GatherArgs& a, cudaStream_t s, double* caller_scratch, double** rec, bool cells = false) {
+// kind: 0 = packed 64-byte node records (the L2 kernel), 1 = 80-byte-pitch node records (windowed, formulas A / C),
+// 2 = 144-byte-pitch cell records (windowed, formula B)
+static int pack_records(const GatherArgs& a, cudaStream_t s, double* caller_scratch, double** rec, int kind = 0) {
     int rc;
-    if (caller_scratch) *rec = caller_scratch;               // 16 * ng doubles owned by the caller (stream-ordered by it)
-    else if ((rc = records_scratch(cells ? 2 * static_cast<int64_t>(a.ng) : a.ng, s, rec))) return rc;
+    if (caller_scratch) *rec = caller_scratch;               // TP_RECORDS_DOUBLES_PER_NODE * ng doubles owned by the caller
+    else if ((rc = records_scratch(kind == 0 ? a.ng : 3 * static_cast<int64_t>(a.ng), s, rec))) return rc;
     const DeviceProps& d = device_props();
     const int pblocks = static_cast<int>(std::min<int64_t>((a.ng + 255) / 256, static_cast<int64_t>(d.sm_count) * 8));
-    if (cells) pack_cells_kernel<<<pblocks, 256, 0, s>>>(a, *rec);
-    else pack_nodes_kernel<<<pblocks, 256, 0, s>>>(a, *rec);
+    if (kind == 2) pack_cells_kernel<<<pblocks, 256, 0, s>>>(a, *rec);
+    else if (kind == 1) pack_nodes_kernel<kNodePitchWin><<<pblocks, 256, 0, s>>>(a, *rec);
+    else pack_nodes_kernel<8><<<pblocks, 256, 0, s>>>(a, *rec);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
@@ -909,7 +912,7 @@ static bool plan_window_ring(int64_t n, RingArgs& ring, WindowArgs& win, size_t&
         const int64_t most = ((d.smem_optin - 1024 - static_cast<int64_t>(smem)) / ring.nstages) & ~int64_t(127);
         per_stage = std::min<int64_t>(most, std::max(0, std::atoi(cap)) & ~127);
     }
-    if (per_stage < 16 * kRecBytes) return false;
+    if (per_stage < 16 * kCellBytes) return false;
     win.win_off = static_cast<uint32_t>(smem);                 // tiles_off and kTileBytes are multiples of 128
     win.win_bytes = static_cast<uint32_t>(per_stage);
     smem += static_cast<size_t>(ring.nstages) * per_stage;
@@ -941,7 +944,7 @@ static int try_gather_push_windows(const GatherArgs& a, int formula, bool aos, i
     ta.win.bounds = reinterpret_cast<int2*>(bounds);
     int rc;
     double* rec = nullptr;
-    if ((rc = pack_records(a, s, rec_scratch, &rec, formula == TP_INTERP_B))) return rc;
+    if ((rc = pack_records(a, s, rec_scratch, &rec, formula == TP_INTERP_B ? 2 : 1))) return rc;
     ta.g.records = rec;
     ta.ring.stream_hint = l2_hints_enabled() ? 1 : 0;
     switch (formula) {

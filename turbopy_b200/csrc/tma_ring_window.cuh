@@ -30,8 +30,9 @@ namespace tp {
 
 constexpr uint32_t kWinMetaOff = kSmemHeader;          // per stage: {jlo, ncells, next_min, next_max}, 16 B each
 constexpr uint32_t kWinFront = 2 * kSmemHeader;        // barriers + meta
-constexpr uint32_t kRecBytes = 64;                     // node records {r, E, B, 0}: formulas A and C
-constexpr uint32_t kCellBytes = 128;                   // cell records {x0, x1, y0[6], slope[6], 0, 0}: formula B
+constexpr uint32_t kRecBytes = kNodePitchWin * 8;      // node records {r, E, B, 0} + pad, 80 B: formulas A and C
+constexpr uint32_t kCellBytes = kCellDoubles * 8;      // cell records {x0, x1, y0[6], slope[6]} + pad, 144 B: formula B
+static_assert((kRecBytes / 16) % 2 == 1 && (kCellBytes / 16) % 2 == 1, "odd pitch in 16-byte chunks: bank-conflict-free");
 
 struct WindowArgs {
     int2* bounds;               // per tile {first cell, number of cells} the tile's particles sit in; {*, 0} = unknown
@@ -89,8 +90,8 @@ __device__ __forceinline__ void fetch_pair_window(const RecView& rv, const WinVi
         fetch_records_smem<FORMULA>(rv, w, ja, na);
         fetch_records_smem<FORMULA>(rv, w, jb, nb);
     } else {
-        fetch_records<FORMULA>(rv, xa, na);
-        fetch_records<FORMULA>(rv, xb, nb);
+        fetch_records<FORMULA, kNodePitchWin>(rv, xa, na);
+        fetch_records<FORMULA, kNodePitchWin>(rv, xb, nb);
     }
 }
 

@@ -571,7 +571,7 @@ class BorisPush(ComputeTool):
                     if win is not None:
                         rec = self._records.get((ng, dev))
                         if rec is None:
-                            rec = self._records[(ng, dev)] = torch.empty(16 * ng, dtype=torch.float64, device=dev)
+                            rec = self._records[(ng, dev)] = torch.empty(18 * ng, dtype=torch.float64, device=dev)
                         _lib.check(lib.tp_gather_push_windows_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
                                                                   C.c_void_p(win.data_ptr()), win.shape[0],
                                                                   C.c_void_p(rec.data_ptr()),
