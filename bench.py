@@ -594,12 +594,17 @@ def run_b200(args):
         sampler.start(); time.sleep(0.05)
         ms, launches, window = b.timed(lambda k: [step(W + s) for s in range(k)], K, sampler)
         pusher.check_status()
-        kernel = ("gather_push_win_kernel<interp(B)> (TMA particle ring + per-tile node-record windows; "
-                  "pack_nodes_kernel before it, moments_* + ncclAllReduce every 10th step)")
+        kernel = ("gather_push_win_kernel<interp(B)> (TMA particle ring + per-tile windows of cell records; "
+                  "pack_cells_kernel before it, moments_* + ncclAllReduce every 10th step)")
         layout_note = "SoA fp64 resident, cell-ordered once before the timed region (tp.sort_by_cell)"
         order_note = {"sort_ms_per_gpu": st["sort_ms"], "sorted_before_timed_region": True,
-                      "order_lifetime": "dt = dr/(2c): a 0.1c thermal particle drifts 0.05 cells per step; the "
-                                        "per-tile windows hold ~480 cells, so one sort lasts > 1000 steps"}
+                      "steps_since_sort_in_timed_region": [W, W + K],
+                      "order_lifetime": "dt = dr/(2c), thermal 0.1c momenta: a 960-particle tile spans ~10 cells "
+                                        "right after the sort and ~0.3 cells more per step; the per-tile windows "
+                                        "hold 65 cells.  Measured decay at 125 M particles "
+                                        "(profiles/r2_order_decay.md): 92 % of the HBM peak in the first steps, "
+                                        "83 % at step 100, 78 % at 200, 66-68 % from step 300 on (L2 path); a "
+                                        "re-sort every ~200 steps keeps the average incl. the sort at ~74 %"}
         if not args.no_parity:
             parity = b.parity_config3(st)
         ke_rows = st["diag"].values()

@@ -207,13 +207,34 @@ extern "C" int tp_gather_push_host_f64(const tp_particles* p, const tp_push_cons
     if (rc) return rc;
     if (!k || !g || !g->r) return TP_E_ARG;
     if (g->ng < 2) return TP_E_GRID;
-    // upload the grid: r, then each present component densely (stride 1)
-    int ncomp = 0;
-    for (int c = 0; c < 6; ++c) ncomp += g->comp[c] ? 1 : 0;
+    // Upload the grid: r, then the field components.  A component with node stride 1 is one contiguous copy.
+    // Strided components (the columns of a Grid.generate_field(3) array: stride 3) are NOT copied row by row (a 2-D
+    // copy of 8-byte rows runs at a few hundred MB/s): the memory ranges they live in are merged (columns of one
+    // (ng,3) array share a range) and each range is uploaded once, contiguously; the device reads it with the same
+    // stride.  Ranges whose stride is so large that the gaps dominate fall back to the 2-D copy.
+    struct Range { uintptr_t lo, hi; };
+    Range rng[6]; int nr = 0;
+    for (int cc = 0; cc < 6; ++cc) {
+        if (!g->comp[cc] || g->comp_stride[cc] == 1) continue;
+        if (g->comp_stride[cc] < 1 || g->comp_stride[cc] > 8) continue;          // sparse: 2-D copy below
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(g->comp[cc]);
+        rng[nr++] = {lo, lo + (static_cast<uintptr_t>(g->ng - 1) * g->comp_stride[cc] + 1) * sizeof(double)};
+    }
+    std::sort(rng, rng + nr, [](const Range& x, const Range& y) { return x.lo < y.lo; });
+    Range seg[6]; int ns = 0;
+    for (int i = 0; i < nr; ++i) {
+        if (ns && rng[i].lo <= seg[ns - 1].hi) seg[ns - 1].hi = std::max(seg[ns - 1].hi, rng[i].hi);
+        else seg[ns++] = rng[i];
+    }
+    int ndense = 0;
+    for (int cc = 0; cc < 6; ++cc)
+        ndense += (g->comp[cc] && (g->comp_stride[cc] == 1 || g->comp_stride[cc] > 8)) ? 1 : 0;
     const int64_t ngp = (g->ng + 1) & ~1ll;                        // keep every block 16-byte aligned
+    int64_t seg_doubles = 0;
+    for (int i = 0; i < ns; ++i) seg_doubles += ((static_cast<int64_t>(seg[i].hi - seg[i].lo) / 8) + 2) & ~1ll;
     std::lock_guard<std::mutex> lock(g_host_mutex);
     const int64_t chunk = chunk_for(p->n);
-    if ((rc = ensure_ctx(chunk, ngp * (1 + ncomp)))) return rc;
+    if ((rc = ensure_ctx(chunk, ngp * (1 + ndense) + seg_doubles))) return rc;
     HostCtx& c = current_ctx();
     c.h2d = c.d2h = 0;
     cudaStream_t s0 = c.stream[0];
@@ -221,14 +242,32 @@ extern "C" int tp_gather_push_host_f64(const tp_particles* p, const tp_push_cons
     dg.r = c.grid_dev;
     TP_CUDA_TRY(cudaMemcpyAsync(c.grid_dev, g->r, sizeof(double) * g->ng, cudaMemcpyHostToDevice, s0));
     c.h2d += sizeof(double) * g->ng;
-    int slot = 1;
+    double* next = c.grid_dev + ngp;
+    double* seg_dev[6];
+    for (int i = 0; i < ns; ++i) {
+        const int64_t nd = static_cast<int64_t>(seg[i].hi - seg[i].lo) / 8;
+        seg_dev[i] = next;
+        TP_CUDA_TRY(cudaMemcpyAsync(next, reinterpret_cast<const void*>(seg[i].lo), sizeof(double) * nd,
+                                    cudaMemcpyHostToDevice, s0));
+        c.h2d += sizeof(double) * nd;
+        next += (nd + 2) & ~1ll;
+    }
     for (int cc = 0; cc < 6; ++cc) {
         if (!g->comp[cc]) continue;
-        double* dst = c.grid_dev + ngp * slot++;
-        if (g->comp_stride[cc] == 1) {
+        const int64_t st = g->comp_stride[cc];
+        if (st != 1 && st >= 1 && st <= 8) {                        // lives in one of the uploaded ranges
+            const uintptr_t u = reinterpret_cast<uintptr_t>(g->comp[cc]);
+            for (int i = 0; i < ns; ++i)
+                if (u >= seg[i].lo && u < seg[i].hi) dg.comp[cc] = seg_dev[i] + (u - seg[i].lo) / 8;
+            dg.comp_stride[cc] = st;
+            continue;
+        }
+        double* dst = next;
+        next += ngp;
+        if (st == 1) {
             TP_CUDA_TRY(cudaMemcpyAsync(dst, g->comp[cc], sizeof(double) * g->ng, cudaMemcpyHostToDevice, s0));
         } else {
-            TP_CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(double), g->comp[cc], sizeof(double) * g->comp_stride[cc],
+            TP_CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(double), g->comp[cc], sizeof(double) * st,
                                           sizeof(double), g->ng, cudaMemcpyHostToDevice, s0));
         }
         c.h2d += sizeof(double) * g->ng;
