@@ -314,6 +314,16 @@ int tp_clock_advance_f64(double* clock_dev, double start_time, double dt, tp_str
 int64_t tp_sort_scratch_bytes(int64_t n, int64_t ncells, int cells_per_bin_log2);
 int tp_sort_by_cell_f64(const tp_particles* p, int axis, double r_first, double dr, int64_t ncells,
                         int cells_per_bin_log2, void* scratch, int64_t* perm_out, tp_stream_t stream);
+/* Local re-sort of an ALREADY nearly cell-ordered ensemble: the same stable order by cell, applied independently
+ * inside blocks of tp_resort_block_particles() (1920) consecutive particles -- block 0 = [0, block_offset), block b =
+ * [block_offset + (b-1)*1920, block_offset + b*1920) -- in one read and one write of the particle state (the cost
+ * of a push step; the global sort above gathers every component through a random permutation and costs ~18 of
+ * them).  Alternate block_offset = 0 / 960 between calls so that particles migrate across block boundaries.  Per
+ * block the result equals numpy.argsort(min(key - min(key), 2^20-1), kind="stable").  SoA layout only
+ * (stride_n = 1, even stride_c, 16-byte aligned arrays), else TP_E_LAYOUT; block_offset even, < 1920. */
+int tp_resort_blocks_f64(const tp_particles* p, int axis, double r_first, double dr, int64_t ncells,
+                         int64_t block_offset, tp_stream_t stream);
+int64_t tp_resort_block_particles(void);
 /* array[i*stride_n] <- array[perm[i]*stride_n] for i < n; tmp: n doubles of device scratch */
 int tp_permute_f64(double* array, int64_t stride_n, int64_t n, const int64_t* perm, double* tmp, tp_stream_t stream);
 

@@ -23,3 +23,18 @@ def keys(x, r_first, dr, ncells, cells_per_bin_log2=0):
 def permutation(x, r_first, dr, ncells, cells_per_bin_log2=0):
     """new[i] = old[perm[i]]"""
     return np.argsort(keys(x, r_first, dr, ncells, cells_per_bin_log2), kind="stable")
+
+
+def resort_blocks_permutation(x, r_first, dr, ncells, offset=0, block=1920):
+    """tp_resort_blocks_f64: the stable order by cell applied independently inside blocks of ``block`` consecutive
+    particles (block 0 = [0, offset), then [offset + k*block, offset + (k+1)*block)); inside a block the key is
+    ``min(cell - lowest cell of the block, 2**20 - 1)``.  new[i] = old[perm[i]]."""
+    k = keys(x, r_first, dr, ncells)
+    n = len(k)
+    perm = np.arange(n)
+    edges = ([0] if offset > 0 else []) + list(range(min(offset, n), n, block)) + [n]
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        if hi > lo:
+            kb = np.minimum(k[lo:hi] - k[lo:hi].min(), (1 << 20) - 1)
+            perm[lo:hi] = lo + np.argsort(kb, kind="stable")
+    return perm

@@ -19,7 +19,7 @@ from .diagnostics import (DeviceFieldDiagnostic, DeviceParticleDiagnostic, Devic
                           KineticEnergyDiagnostic, reduce_moments)
 from .cycle import DeviceClock, PlaneWave
 from .graph import StepGraph
-from .particles import soa_particles, sort_by_cell, to_soa
+from .particles import resort_local, soa_particles, sort_by_cell, to_soa
 from .tools import (BandedOperator, BorisPush, FiniteDifference, GridOnDevice, Interpolators,
                     PoissonSolver1DRadial)
 

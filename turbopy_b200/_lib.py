@@ -112,6 +112,8 @@ SIGNATURES = {
     "tp_sort_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int]),
     "tp_sort_by_cell_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tp_resort_blocks_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_void_p]),
+    "tp_resort_block_particles": (C.c_int64, []),
     "tp_permute_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tp_graph_begin": (C.c_int, [C.c_void_p]),
     "tp_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

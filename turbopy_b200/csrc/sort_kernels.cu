@@ -307,3 +307,194 @@ extern "C" int tp_permute_f64(double* array, int64_t stride_n, int64_t n, const 
     count_launch(2);
     return static_cast<int>(cudaGetLastError());
 }
+
+// ---------------------------------------------------------------------------
+// Local re-sort: restore the cell order of an ALREADY nearly ordered ensemble
+// ---------------------------------------------------------------------------
+// A cell-ordered ensemble decays slowly (config 3: a 960-particle tile spans ~10 cells after the sort and ~0.3
+// cells more per step), but the windowed gather feels it quickly: once the 64 particles of a warp sit in 20
+// different cells its window loads stop being broadcasts (measured: 92 % of the HBM peak right after a sort, 83 %
+// 100 steps later, 66 % from step 300 on).  The global radix sort above costs 39 ms per 125 M particles -- 18 push
+// steps -- because it gathers every component through a random permutation.  This kernel re-orders the particles
+// INSIDE blocks of 1920 consecutive particles (two ring tiles) instead: one read and one write of the state, like a
+// push step (~2.5 ms per 125 M particles).  Block b covers [offset + (b-1)*1920, offset + b*1920) (block 0 is the
+// head [0, offset)); callers alternate offset = 0 / 960 from call to call, so particles also migrate across block
+// boundaries over successive calls.
+//
+// Per block: TMA bulk loads of the six component slices into shared memory (double-buffered: the next block loads
+// while this one is sorted), key = (cell - block's lowest cell, capped at 2^20-1) << 12 | index-in-block, a bitonic
+// sort of the 2048 padded 32-bit keys -- the index in the low bits makes the order STABLE and unique, so the result
+// equals numpy.argsort(key, kind="stable") per block (oracle/sort.py: resort_blocks) -- and a gather from shared
+// memory straight into coalesced 128-bit global stores.
+namespace tp {
+
+constexpr int kRsBlock = 1920;
+constexpr int kRsPad = 2048;
+constexpr int kRsThreads = 512;
+constexpr uint32_t kRsSlice = kRsBlock * sizeof(double);            // 15 360 B
+constexpr uint32_t kRsBuf = 6 * kRsSlice;                           // 92 160 B
+constexpr uint32_t kRsSmem = 128 + 2 * kRsBuf + kRsPad * sizeof(uint32_t);
+
+struct ResortArgs {
+    double* comp[6];            // x, y, z, px, py, pz component arrays (contiguous, 16-byte aligned)
+    int axis;
+    int64_t n, offset, nblocks;
+    double r_first, inv_dr;
+    int64_t ncells;
+};
+
+__device__ __forceinline__ uint32_t rs_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void rs_block_range(const ResortArgs& a, int64_t q, int64_t& first, int& count) {
+    int64_t lo, hi;
+    if (a.offset > 0) {
+        lo = q == 0 ? 0 : a.offset + (q - 1) * kRsBlock;
+        hi = q == 0 ? a.offset : lo + kRsBlock;
+    } else {
+        lo = q * kRsBlock; hi = lo + kRsBlock;
+    }
+    hi = min(hi, a.n);
+    first = lo; count = static_cast<int>(hi - lo);
+}
+
+__global__ void __launch_bounds__(kRsThreads, 1) resort_blocks_kernel(const __grid_constant__ ResortArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // two mbarriers
+    double* bufs = reinterpret_cast<double*>(smem + 128);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem + 128 + 2 * kRsBuf);
+    __shared__ int s_min[kRsThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rs_smem_u32(&full[s])) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // one elected thread streams a block's six slices into buffer s (the even part by the TMA; an odd last
+    // element is copied by the same thread with a plain load, visible after the barrier below)
+    auto issue = [&](int64_t q, int s) {
+        int64_t first; int count;
+        rs_block_range(a, q, first, count);
+        const uint32_t bytes = static_cast<uint32_t>(count & ~1) * sizeof(double);
+        double* dst = bufs + static_cast<size_t>(s) * 6 * kRsBlock;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_smem_u32(&full[s])), "r"(6 * bytes) : "memory");
+        for (int c = 0; c < 6; ++c) {
+            if (bytes)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 rs_smem_u32(dst + c * kRsBlock)),
+                             "l"(a.comp[c] + first), "r"(bytes), "r"(rs_smem_u32(&full[s]))
+                             : "memory");
+            if (count & 1) dst[c * kRsBlock + count - 1] = a.comp[c][first + count - 1];
+        }
+    };
+    int s = 0;
+    uint32_t parity = 0u;                                              // bit s: phase parity of full[s]
+    int64_t q = blockIdx.x;
+    if (tid == 0 && q < a.nblocks) issue(q, 0);
+    for (; q < a.nblocks; q += gridDim.x) {
+        const int64_t qn = q + gridDim.x;
+        if (tid == 0 && qn < a.nblocks) issue(qn, s ^ 1);              // buffer s^1 was released by the barrier that ended the last iteration
+        // wait for this block's data
+        asm volatile(
+            "{\n.reg .pred P1;\nRS_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra.uni RS_DONE;\nbra.uni RS_WAIT;\nRS_DONE:\n}\n" ::"r"(
+                rs_smem_u32(&full[s])),
+            "r"((parity >> s) & 1u)
+            : "memory");
+        parity ^= 1u << s;
+        __syncthreads();                                               // (the odd tail element, written by thread 0)
+        int64_t first; int count;
+        rs_block_range(a, q, first, count);
+        const double* buf = bufs + static_cast<size_t>(s) * 6 * kRsBlock;
+        const double* xs = buf + a.axis * kRsBlock;
+        // cells and the block's lowest cell
+        int cell[kRsPad / kRsThreads];
+        int lo = 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < kRsPad / kRsThreads; ++u) {
+            const int i = tid + u * kRsThreads;
+            cell[u] = 0x7fffffff;
+            if (i < count) {
+                const double t = (xs[i] - a.r_first) * a.inv_dr;
+                int64_t c = t >= 0.0 ? static_cast<int64_t>(fmin(t, 9.0e18)) : 0;     // the key of tp_sort_by_cell_f64
+                c = min(c, a.ncells - 1);
+                cell[u] = static_cast<int>(min(c, static_cast<int64_t>(0x7ffffffe)));
+                lo = min(lo, cell[u]);
+            }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        if (lane == 0) s_min[warp] = lo;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kRsThreads / 32; ++w) lo = min(lo, s_min[w]);
+#pragma unroll
+        for (int u = 0; u < kRsPad / kRsThreads; ++u) {
+            const int i = tid + u * kRsThreads;
+            keys[i] = i < count ? (static_cast<uint32_t>(min(cell[u] - lo, (1 << 20) - 1)) << 12) | static_cast<uint32_t>(i)
+                                : 0xffffffffu;
+        }
+        __syncthreads();
+        // bitonic sort of the 2048 keys, ascending
+        for (int k = 2; k <= kRsPad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (int u = 0; u < kRsPad / 2 / kRsThreads; ++u) {
+                    const int t = tid + u * kRsThreads;                 // compare-exchange number t of this stage
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); // the lower index of the pair
+                    const int p = i | j;
+                    const uint32_t x = keys[i], y = keys[p];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { keys[i] = y; keys[p] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        // gather from shared memory into coalesced global stores (two outputs per thread and component)
+        for (int i2 = tid; 2 * i2 < count; i2 += kRsThreads) {
+            const int i = 2 * i2;
+            const int s0 = static_cast<int>(keys[i] & 0xfffu);
+            if (i + 1 < count) {
+                const int s1 = static_cast<int>(keys[i + 1] & 0xfffu);
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    st2(a.comp[c] + first + i, make_double2(buf[c * kRsBlock + s0], buf[c * kRsBlock + s1]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) a.comp[c][first + i] = buf[c * kRsBlock + s0];
+            }
+        }
+        __syncthreads();                                               // buffer s and the keys are free again
+        s ^= 1;
+    }
+}
+
+}  // namespace tp
+
+extern "C" int tp_resort_blocks_f64(const tp_particles* p, int axis, double r_first, double dr, int64_t ncells,
+                                    int64_t block_offset, tp_stream_t stream) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return d.status;
+    if (!p || p->n < 0 || axis < 0 || axis > 2 || !(dr > 0.0) || ncells < 1) return TP_E_ARG;
+    if (block_offset < 0 || block_offset >= kRsBlock || (block_offset & 1)) return TP_E_ARG;
+    if (p->n == 0) return TP_OK;
+    if (!p->pos || !p->mom) return TP_E_ARG;
+    // component arrays: contiguous (SoA) and 16-byte aligned, like the TMA particle ring
+    if (p->pos_stride_n != 1 || p->mom_stride_n != 1 || (p->pos_stride_c & 1) || (p->mom_stride_c & 1) ||
+        p->pos_stride_c < p->n || p->mom_stride_c < p->n || !aligned16(p->pos) || !aligned16(p->mom))
+        return TP_E_LAYOUT;
+    ResortArgs a;
+    for (int c = 0; c < 3; ++c) { a.comp[c] = p->pos + c * p->pos_stride_c; a.comp[3 + c] = p->mom + c * p->mom_stride_c; }
+    a.axis = axis; a.n = p->n; a.offset = std::min<int64_t>(block_offset, p->n);
+    a.r_first = r_first; a.inv_dr = 1.0 / dr; a.ncells = ncells;
+    const int64_t rest = p->n - a.offset;
+    a.nblocks = (a.offset > 0 ? 1 : 0) + (rest + kRsBlock - 1) / kRsBlock;
+    int rc = static_cast<int>(cudaFuncSetAttribute(resort_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(kRsSmem)));
+    if (rc) return rc;
+    const int blocks = static_cast<int>(std::min<int64_t>(a.nblocks, d.sm_count));
+    resort_blocks_kernel<<<blocks, kRsThreads, kRsSmem, static_cast<cudaStream_t>(stream)>>>(a);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int64_t tp_resort_block_particles(void) { return kRsBlock; }

@@ -93,3 +93,29 @@ def sort_by_cell(position, momentum, grid, axis=0, cells_per_bin_log2=0, extra=(
                     _lib.check(lib.tp_permute_f64(C.c_void_p(col.data_ptr()), int(col.stride(0)) if n > 1 else 1, n,
                                                   C.c_void_p(perm.data_ptr()), C.c_void_p(tmp.data_ptr()), _stream_ptr(dev)))
     return perm if return_perm else None
+
+
+def resort_local(position, momentum, grid, axis=0, phase=0):
+    """Restore the cell order of an ALREADY nearly ordered ensemble in place, at the cost of one push step: a stable
+    sort by cell inside blocks of 1920 consecutive particles (tp_resort_blocks_f64; the global :func:`sort_by_cell`
+    costs ~18 push steps).  ``phase`` alternates the block boundaries (even: blocks start at particle 0, odd: at
+    particle 960) so that repeated calls let particles migrate between blocks.  SoA ensembles
+    (:func:`soa_particles`) only.  Additive helper, asynchronous on the current stream."""
+    import ctypes as C
+
+    from . import _lib
+    from .tools import _is_cuda, _on_device, _particles_struct, _stream_ptr
+
+    if not (_is_cuda(position) and _is_cuda(momentum)) or position.device != momentum.device:
+        raise TypeError("position and momentum must be CUDA float64 tensors on one device")
+    if axis not in (0, 1, 2):
+        raise ValueError("axis must be 0, 1 or 2")
+    p = _particles_struct(position, momentum)
+    ng = int(grid.num_points) if hasattr(grid, "num_points") else int(len(grid.r))
+    lib = _lib.lib()
+    offset = (int(lib.tp_resort_block_particles()) // 2) if (int(phase) & 1) else 0
+    global order_generation
+    order_generation += 1
+    with _on_device(position.device):
+        _lib.check(lib.tp_resort_blocks_f64(C.byref(p), int(axis), float(grid.r[0]), float(grid.dr), ng - 1, offset,
+                                            _stream_ptr(position.device)))

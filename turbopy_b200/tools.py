@@ -431,6 +431,8 @@ class BorisPush(ComputeTool):
         # never reorders particles and its physics does not depend on their order, but callers that index
         # particles by position in the array would notice, hence opt-in.
         self.sort_every = int(input_data.get("sort_every", 0) or 0)
+        # every full_sort_every-th of those re-orderings is a global sort again (0 = only the first one)
+        self.full_sort_every = int(input_data.get("full_sort_every", 0) or 0)
         self._sort_calls = {}
 
     # -- the reference method ------------------------------------------------
@@ -563,7 +565,14 @@ class BorisPush(ComputeTool):
                 ck = (position.data_ptr(), int(p.n), axis)
                 calls = self._sort_calls.get(ck, 0)
                 if calls % self.sort_every == 0:
-                    particles.sort_by_cell(position, momentum, grid, axis=axis)
+                    # the first time (and every full_sort_every-th time) a global sort; in between the cheap
+                    # block-local re-sort, which is all a slowly decaying order needs (SoA ensembles)
+                    k = calls // self.sort_every
+                    soa = p.pos_stride_n == 1 and p.mom_stride_n == 1
+                    if k == 0 or not soa or (self.full_sort_every > 0 and k % self.full_sort_every == 0):
+                        particles.sort_by_cell(position, momentum, grid, axis=axis)
+                    else:
+                        particles.resort_local(position, momentum, grid, axis=axis, phase=k)
                 self._sort_calls[ck] = calls + 1
             with _on_device(dev):
                 if _steps is None:
