@@ -648,6 +648,14 @@ def run_b200(args):
             shape("config3_random_order", st)
             del st
             torch.cuda.empty_cache()
+        # the same shape over 500 steps with the tool keeping the order itself (input_data sort_every = 100: one
+        # global sort, then a block-local re-sort every 100 steps, all inside the timed region) -- the sustained figure
+        st = b.setup_config3(125_000_000 if workload == "pif" else n, NG_CONFIG3, "random")
+        st["pusher"].sort_every = 100
+        shape("config3_sustained_500_steps_sort_every_100", st, steps=500)
+        del st
+        torch.cuda.empty_cache()
+        if workload != "pif":
             pusher1, step1 = b.setup_pif(16 << 20, 4097, 64)
             mx, _, _ = b.measure(step1, 100, 5)
             extras["pif_16Mi_per_gpu"] = {"value": (16 << 20) * b.world * 100 / (mx * 1e-3), "unit": UNIT,

@@ -567,12 +567,12 @@ class BorisPush(ComputeTool):
                 if calls % self.sort_every == 0:
                     # the first time (and every full_sort_every-th time) a global sort; in between the cheap
                     # block-local re-sort, which is all a slowly decaying order needs (SoA ensembles)
-                    k = calls // self.sort_every
+                    nth = calls // self.sort_every
                     soa = p.pos_stride_n == 1 and p.mom_stride_n == 1
-                    if k == 0 or not soa or (self.full_sort_every > 0 and k % self.full_sort_every == 0):
+                    if nth == 0 or not soa or (self.full_sort_every > 0 and nth % self.full_sort_every == 0):
                         particles.sort_by_cell(position, momentum, grid, axis=axis)
                     else:
-                        particles.resort_local(position, momentum, grid, axis=axis, phase=k)
+                        particles.resort_local(position, momentum, grid, axis=axis, phase=nth)
                 self._sort_calls[ck] = calls + 1
             with _on_device(dev):
                 if _steps is None:
