@@ -209,6 +209,11 @@ int tp_fd_upwind_left_f64(const double* y, const double* widths, double* d, int6
 int tp_fd_del2_radial_apply_f64(const double* f, const double* r, double* out, int64_t n,
                                 double g1 /* 1/(2.0*dr), :197 */, double g2 /* 1/(dr**2), :211 */,
                                 tp_stream_t stream);
+/* out = f + dtau * (del2_radial() @ f) in one pass (the explicit field update `f + dtau * (D @ f)`; numpy's three
+ * roundings per point, no contraction); r: Grid.r, or NULL with `grid` describing it as a tp_linspace (or the other
+ * way round).  out must not alias f (rows read their neighbours). */
+int tp_fd_del2_radial_axpy_f64(const double* f, const double* r, const tp_linspace* grid, double* out, int64_t n,
+                               double g1, double g2, double dtau, tp_stream_t stream);
 /* generic banded operator apply (the dia_matrix objects the other builders
  * return, :140-187,225-381): out[i] = sum_k data[k][i+off[k]] * x[i+off[k]] in
  * the given diagonal order; data is (ndiag, n) row-major DEVICE memory,

@@ -212,3 +212,33 @@ def test_linspace_grids_rebuild_r_in_registers_with_the_same_bits(tp, n, monkeyp
     tool, grid = fd_tool(tp, max(n, 4), 2.5)
     grid.r = grid.r ** 1.5
     assert tp.GridOnDevice.of(grid, yd.device).linspace is None
+
+
+@pytest.mark.parametrize("n,rmax", [(10, 1.0), (1025, 2.5), (100_003, 1.0)])
+def test_del2_radial_axpy_is_numpys_update(tp, n, rmax, monkeypatch):
+    """D.axpy(f, dtau) == f + dtau * (D @ f) with numpy's three roundings per point (the field update
+    of configs[4] without an eager axpy), on a linspace grid (r rebuilt in registers) and reading r."""
+    grid = make_grid(n, 0.0, rmax)
+    rng = np.random.default_rng(n)
+    f = rng.normal(size=n)
+    dtau = 0.37 * grid.dr ** 2
+    want = f + dtau * ofd.del2_radial_apply(f, grid.r, grid.dr)
+    fd_t = torch.from_numpy(f).cuda()
+    for lin in ("1", "0"):
+        monkeypatch.setenv("TURBOPY_B200_LINSPACE", lin)
+        tp.GridOnDevice._cache.clear()
+        tool = tp.FiniteDifference(make_owner(grid=grid), {"type": "FiniteDifference", "method": "centered"})
+        D = tool.del2_radial()
+        got = D.axpy(fd_t, dtau)
+        assert got.data_ptr() != fd_t.data_ptr()
+        assert_bits_equal(got.cpu().numpy(), want, f"linspace={lin}")
+        assert_bits_equal(D.axpy(f, dtau), want, "numpy operand")
+    assert_bits_equal(tool.ddx().axpy(fd_t, 0.5).cpu().numpy(), f + 0.5 * ofd_ddx(f, grid.dr), "generic operator")
+
+
+def ofd_ddx(f, dr):
+    g = 1 / (2.0 * dr)
+    out = np.zeros_like(f)
+    out[:-1] = out[:-1] + (0.0 + g) * f[1:]
+    out[1:] = (0.0 - g) * f[:-1] + out[1:]
+    return out

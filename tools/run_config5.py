@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """BASELINE configs[4] at full size: centered / upwind ddx and the radial del2 on a 256 Mi-point cylindrical grid
-driving a field update f += dt * (del2_radial @ f) for 100 iterations (the update itself is a torch axpy)."""
+driving a field update f <- f + dt * (del2_radial @ f) for 100 iterations: one iteration = three own kernels
+(centered, upwind, the fused del2_radial axpy of tp_fd_del2_radial_axpy_f64); the round-1 variant with a torch axpy
+is timed beside it."""
 import json
 import os
 import sys
@@ -38,16 +40,27 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
-def iteration():
+def iteration_torch_axpy():
     fd.centered_difference(f)
     fd.upwind_left(f)
     f.add_(D @ f, alpha=dtau)
 
 
+state = {"f": f}
+
+
+def iteration():
+    fd.centered_difference(state["f"])
+    fd.upwind_left(state["f"])
+    state["f"] = D.axpy(state["f"], dtau)                        # fresh array, like numpy's f + dtau * (D @ f)
+
+
 out = {"config": "configs[4]: FD centered / upwind ddx + radial del2 on a 256 Mi-point grid, 100 update iterations",
        "points": n, "linspace_grid_detected": lin,
        "centered_ms": timed(lambda: fd.centered_difference(f), 10), "upwind_ms": timed(lambda: fd.upwind_left(f), 10),
-       "del2_radial_ms": timed(lambda: D @ f, 10), "iteration_ms": timed(iteration, 100)}
+       "del2_radial_ms": timed(lambda: D @ f, 10), "del2_radial_axpy_ms": timed(lambda: D.axpy(f, dtau), 10),
+       "iteration_torch_axpy_ms": timed(iteration_torch_axpy, 50), "iteration_ms": timed(iteration, 100)}
+f = state["f"]
 out["points_per_s_per_operator"] = {k[:-3]: n / out[k] * 1e3 for k in ("centered_ms", "upwind_ms", "del2_radial_ms")}
 out["finite"] = bool(torch.isfinite(f[1:]).all())
 print(json.dumps(out))

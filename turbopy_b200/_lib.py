@@ -76,6 +76,8 @@ SIGNATURES = {
     "tp_fd_upwind_left_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tp_fd_del2_radial_apply_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                               C.c_double, C.c_double, C.c_void_p]),
+    "tp_fd_del2_radial_axpy_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Linspace), C.c_void_p, C.c_int64,
+                                             C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "tp_fd_dia_apply_f64": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_void_p]),
     "tp_fd_dia_const_apply_f64": (C.c_int, [c_double_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), c_i64_p,

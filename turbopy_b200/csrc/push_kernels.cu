@@ -598,6 +598,75 @@ __global__ void __launch_bounds__(kThreads, NC == 1 ? 3 : 2) interp_kernel(const
     }
 }
 
+// 1-D y, numpy.interp rounding (formula B), the common call (Interpolators.interpolate1D(grid.r, field)(x)):
+// every CTA builds a per-CELL table {y[j], slope_j} in shared memory (slope = (y[j+1]-y[j])/(x[j+1]-x[j]) by IEEE
+// division: numpy.interp's per-cell quantity, ng/256 divisions per thread, once per launch) and a point then costs
+// ONE 128-bit shared load, a multiply and an add -- no reciprocal, no quotient, no guard, half the random shared
+// loads of interp_kernel.  LIN: the abscissas are a tp_linspace grid, x[j] / x[j+1] are rebuilt in
+// registers; otherwise the table also holds {x[j], x[j+1]} (two 128-bit loads per point).  Points that are not
+// strictly inside the guessed cell (on a node, at the ends, outside, NaN, non-uniform x) take interp_point_exact.
+template <bool LIN>
+__global__ void __launch_bounds__(kThreads, 3) interp_cells_kernel(const __grid_constant__ InterpArgs a, bool vec) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double2* ys = reinterpret_cast<double2*>(smem);                          // {y0, slope} per cell
+    double2* xs = reinterpret_cast<double2*>(smem) + (a.g.ng - 1);           // {x0, x1} per cell (not LIN)
+    const int ncell = a.g.ng - 1;
+    const double* y = a.g.comp[0];
+    const int sn = a.g.stride[0];
+    for (int j = threadIdx.x; j < ncell; j += kThreads) {
+        const double x0 = LIN ? lin_r(a.lin, j) : a.g.r[j], x1 = LIN ? lin_r(a.lin, j + 1) : a.g.r[j + 1];
+        const double y0 = y[static_cast<int64_t>(j) * sn], y1 = y[static_cast<int64_t>(j + 1) * sn];
+        ys[j] = make_double2(y0, (y1 - y0) / (x1 - x0));
+        if (!LIN) xs[j] = make_double2(x0, x1);
+    }
+    __syncthreads();
+    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kThreads;
+    const int64_t nquads = (a.n + 3) >> 2;
+    for (int64_t qd = gtid; qd < nquads; qd += gstride) {
+        const int64_t i = qd * 4;
+        const bool full = vec && i + 4 <= a.n;
+        double x[4];
+        if (full) {
+            const double2 u = ld2(a.xq + i), v = ld2(a.xq + i + 2);
+            x[0] = u.x; x[1] = u.y; x[2] = v.x; x[3] = v.y;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = i + q < a.n ? a.xq[(i + q) * a.xq_stride] : 0.0;
+        }
+        double o[4];
+        unsigned bad = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = guess_cell(x[q], a.g.r_first, a.g.inv_dr, a.g.ng);
+            const double2 t = ys[j];
+            double x0, x1;
+            if (LIN) {
+                const double dj = static_cast<double>(j);
+                x0 = lin_r_at(a.lin, dj, 0, j); x1 = lin_r_at(a.lin, dj, 1, j + 1);
+            } else {
+                const double2 e = xs[j];
+                x0 = e.x; x1 = e.y;
+            }
+            o[q] = t.y * (x[q] - x0) + t.x;
+            const bool ok = (x0 < x[q]) && (x[q] < x1) && (o[q] == o[q]);     // NaN -> numpy's fallbacks (exact path)
+            if (!ok && i + q < a.n) bad |= 1u << q;
+        }
+        double* dst = a.out + i;
+        if (full) {
+            st2(dst, make_double2(o[0], o[1]));
+            st2(dst + 2, make_double2(o[2], o[3]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (i + q < a.n) dst[q] = o[q];
+        }
+        if (__builtin_expect(bad != 0u, 0))                  // recovery overwrites the point's output (reads the global arrays)
+            for (int q = 0; q < 4; ++q)
+                if (bad & (1u << q)) interp_point_exact<TP_INTERP_B, false>(a, smem, i + q, 0);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -1206,6 +1275,33 @@ static int interp1d_impl(const double* r, int64_t ng, double dr, double r_first,
     a.g.status = reinterpret_cast<unsigned long long*>(status);
     a.xq = xq; a.xq_stride = xq_stride; a.n = n; a.out = out; a.out_stride_c = out_stride_c; a.ncomp = ncomp;
     if (n == 0) return TP_OK;
+    static const bool cells_on = [] {
+        const char* e = std::getenv("TURBOPY_B200_INTERP_CELLS");     // tuning / A-B switch, default on
+        return !(e && e[0] == '0');
+    }();
+    if (cells_on && ncomp == 1 && formula == TP_INTERP_B && n >= 8 * ng) {
+        // per-cell {y0, slope} table in shared memory (worth building when there are many more points than cells)
+        const size_t need = static_cast<size_t>(ng - 1) * (lin ? 16 : 32);
+        if (need <= static_cast<size_t>(d.smem_optin) / 3 - 1024 && (!lin || lin->n == ng)) {
+            GatherArgs& ga = a.g;
+            ga.r = r; ga.comp[0] = y; ga.stride[0] = static_cast<int>(y_stride_n);          // the global view (no staging plan)
+            ga.nseg = 0;
+            const bool vec = xq_stride == 1 && aligned16(xq) && aligned16(out);
+            auto go = [&](auto kern) {
+                int rc2 = set_smem(kern, need);
+                if (rc2) return rc2;
+                const int blocks = grid_blocks(reinterpret_cast<const void*>(kern), need, (n + 3) / 4);
+                kern<<<blocks, kThreads, need, s>>>(a, vec);
+                count_launch();
+                return static_cast<int>(cudaGetLastError());
+            };
+            if (lin) {
+                a.lin = LinGrid{lin->start, lin->span, lin->step, lin->n};
+                return go(interp_cells_kernel<true>);
+            }
+            return go(interp_cells_kernel<false>);
+        }
+    }
     if (lin) {
         if (lin->n != ng) return TP_E_ARG;
         a.lin = LinGrid{lin->start, lin->span, lin->step, lin->n};

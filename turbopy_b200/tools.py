@@ -780,6 +780,7 @@ class BandedOperator:
         self._device = device
         self._dense = None
         self._diag = None
+        self._axpy = None                # fused `f + dtau * (self @ f)` kernel, if the operator has one
         self._stored = stored            # callable -> (ndiag, n) numpy array of the stored diagonals, if known
 
     # ---- constructors for the two stored forms --------------------------------
@@ -870,6 +871,17 @@ class BandedOperator:
         return out.cpu().numpy()
 
     __matmul__ = dot
+
+    def axpy(self, f, dtau):
+        """``f + dtau * (self @ f)`` as a fresh array -- the explicit update step of a field module
+        (``f += dtau * (D @ f)``), with numpy's rounding (matvec, scale, add).  ``del2_radial()`` does it in one
+        kernel pass (tp_fd_del2_radial_axpy_f64: 16 B per point); other operators apply, scale and add."""
+        if isinstance(f, torch.Tensor) and _is_cuda(f) and f.ndim == 1 and self._axpy is not None:
+            _require_f64(f, "operand")
+            if f.shape[0] != self.shape[0]:
+                raise ValueError("dimension mismatch")
+            return self._axpy(f.contiguous(), dtau)
+        return f + dtau * self.dot(f)
 
     # ---- the stored diagonals of ANY banded operator, without forming it ------
     def diagonals(self):
@@ -1097,7 +1109,18 @@ class FiniteDifference(ComputeTool):
                         n, g1, g2, _stream_ptr(f.device)))
             return out
 
-        return BandedOperator(n, [-1, 0, 1], apply, dev)
+        def axpy(f, dtau):
+            out = torch.empty_like(f)
+            with torch.cuda.device(f.device):
+                _lib.check(_lib.lib().tp_fd_del2_radial_axpy_f64(
+                    C.c_void_p(f.data_ptr()), None if lin is not None else C.c_void_p(gd.r.data_ptr()),
+                    C.byref(lin) if lin is not None else None, C.c_void_p(out.data_ptr()), n, g1, g2, float(dtau),
+                    _stream_ptr(f.device)))
+            return out
+
+        op = BandedOperator(n, [-1, 0, 1], apply, dev)
+        op._axpy = axpy
+        return op
 
     # ---- the remaining matrix builders -------------------------
     # Operators whose diagonals are constant apart from a few boundary entries
