@@ -681,6 +681,11 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "configs": extras, "parity": parity,
         }
+        if workload == "config3":
+            line["scaling_note"] = ("N = 1 runs configs[1] (one component, 4097-node grid, no collective); this line is "
+                                    "configs[2].  The single-GPU figure of THIS workload is `configs.config3_per_gpu_sorted` "
+                                    "of the N = 1 line; `configs.pif_16Mi_per_gpu` here is configs[1] on all N GPUs.")
+            line["value_per_gpu"] = value / b.world
         print(json.dumps(line), flush=True)
     if b.world > 1:
         from turbopy_b200.sharding import DiagnosticComm

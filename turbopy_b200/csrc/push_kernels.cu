@@ -623,47 +623,65 @@ __global__ void __launch_bounds__(kThreads, 3) interp_cells_kernel(const __grid_
     const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * kThreads;
     const int64_t nquads = (a.n + 3) >> 2;
-    for (int64_t qd = gtid; qd < nquads; qd += gstride) {
-        const int64_t i = qd * 4;
-        const bool full = vec && i + 4 <= a.n;
-        double x[4];
-        if (full) {
-            const double2 u = ld2(a.xq + i), v = ld2(a.xq + i + 2);
-            x[0] = u.x; x[1] = u.y; x[2] = v.x; x[3] = v.y;
-        } else {
+    // kUnroll quads (4 points each) per thread and iteration, all their x loads issued before the first use: the
+    // kernel moves only 16 B per point, so it needs ~45 KB of loads in flight per SM to cover the HBM latency
+#ifndef TP_INTERP_UNROLL
+#define TP_INTERP_UNROLL 2
+#endif
+    constexpr int kUnroll = TP_INTERP_UNROLL;
+    for (int64_t qd0 = gtid; qd0 < nquads; qd0 += kUnroll * gstride) {
+        double x[kUnroll][4];
+        bool full[kUnroll], live[kUnroll];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = i + q < a.n ? a.xq[(i + q) * a.xq_stride] : 0.0;
-        }
-        double o[4];
-        unsigned bad = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int j = guess_cell(x[q], a.g.r_first, a.g.inv_dr, a.g.ng);
-            const double2 t = ys[j];
-            double x0, x1;
-            if (LIN) {
-                const double dj = static_cast<double>(j);
-                x0 = lin_r_at(a.lin, dj, 0, j); x1 = lin_r_at(a.lin, dj, 1, j + 1);
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t qd = qd0 + u * gstride;
+            const int64_t i = qd * 4;
+            live[u] = qd < nquads;
+            full[u] = live[u] && vec && i + 4 <= a.n;
+            if (full[u]) {
+                const double2 p = ld2(a.xq + i), v = ld2(a.xq + i + 2);
+                x[u][0] = p.x; x[u][1] = p.y; x[u][2] = v.x; x[u][3] = v.y;
             } else {
-                const double2 e = xs[j];
-                x0 = e.x; x1 = e.y;
-            }
-            o[q] = t.y * (x[q] - x0) + t.x;
-            const bool ok = (x0 < x[q]) && (x[q] < x1) && (o[q] == o[q]);     // NaN -> numpy's fallbacks (exact path)
-            if (!ok && i + q < a.n) bad |= 1u << q;
-        }
-        double* dst = a.out + i;
-        if (full) {
-            st2(dst, make_double2(o[0], o[1]));
-            st2(dst + 2, make_double2(o[2], o[3]));
-        } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (i + q < a.n) dst[q] = o[q];
+                for (int q = 0; q < 4; ++q) x[u][q] = (live[u] && i + q < a.n) ? a.xq[(i + q) * a.xq_stride] : 0.0;
+            }
         }
-        if (__builtin_expect(bad != 0u, 0))                  // recovery overwrites the point's output (reads the global arrays)
-            for (int q = 0; q < 4; ++q)
-                if (bad & (1u << q)) interp_point_exact<TP_INTERP_B, false>(a, smem, i + q, 0);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!live[u]) continue;
+            const int64_t i = (qd0 + u * gstride) * 4;
+            double o[4];
+            unsigned bad = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double xv = x[u][q];
+                const int j = guess_cell(xv, a.g.r_first, a.g.inv_dr, a.g.ng);
+                const double2 t = ys[j];
+                double x0, x1;
+                if (LIN) {
+                    const double dj = static_cast<double>(j);
+                    x0 = lin_r_at(a.lin, dj, 0, j); x1 = lin_r_at(a.lin, dj, 1, j + 1);
+                } else {
+                    const double2 e = xs[j];
+                    x0 = e.x; x1 = e.y;
+                }
+                o[q] = t.y * (xv - x0) + t.x;
+                const bool ok = (x0 < xv) && (xv < x1) && (o[q] == o[q]);        // NaN -> numpy's fallbacks (exact path)
+                if (!ok && i + q < a.n) bad |= 1u << q;
+            }
+            double* dst = a.out + i;
+            if (full[u]) {
+                st2(dst, make_double2(o[0], o[1]));
+                st2(dst + 2, make_double2(o[2], o[3]));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (i + q < a.n) dst[q] = o[q];
+            }
+            if (__builtin_expect(bad != 0u, 0))              // recovery overwrites the point's output (reads the global arrays)
+                for (int q = 0; q < 4; ++q)
+                    if (bad & (1u << q)) interp_point_exact<TP_INTERP_B, false>(a, smem, i + q, 0);
+        }
     }
 }
 
