@@ -88,18 +88,39 @@ def decay(ng, n, formula, blocks, steps_per_block):
     torch.cuda.synchronize()
     sort_ms = e0.elapsed_time(e1)
     rows = []
+    import threading
+    import time
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    samples, stop = [], threading.Event()
+
+    def poll():
+        while not stop.is_set():
+            samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                            pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                            pynvml.nvmlDeviceGetCurrentClocksEventReasons(h),
+                            pynvml.nvmlDeviceGetTemperature(h, pynvml.NVML_TEMPERATURE_GPU)))
+            time.sleep(0.005)
+    threading.Thread(target=poll, daemon=True).start()
     for b in range(blocks):
+        mark = len(samples)
         e0.record()
         for _ in range(steps_per_block):
             tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, formula=formula)
         e1.record()
         torch.cuda.synchronize()
+        win = samples[mark:] or [(0, 0.0, 0, 0)]
+        clk = {"sm_mhz_median": sorted(c for c, _, _, _ in win)[len(win) // 2], "power_w_max": max(p for _, p, _, _ in win),
+               "reasons_or": hex(__import__("functools").reduce(lambda a, b: a | b, (r for _, _, r, _ in win), 0)),
+               "temp_c": max(t for _, _, _, t in win)}
         ms = e0.elapsed_time(e1) / steps_per_block
         wins = [w[0] for w in tool._windows.values() if w[0] is not None]
         cells = float(wins[0].view(-1, 2)[: n // 960, 1].float().mean()) if wins else None
         rows.append({"steps_since_sort": (b + 1) * steps_per_block, "ms_per_step": ms,
-                     "frac_of_hbm_peak": 96.0 * n / (ms * 1e-3) / 1e9 / peak(), "cells_per_tile_mean": cells})
+                     "frac_of_hbm_peak": 96.0 * n / (ms * 1e-3) / 1e9 / peak(), "cells_per_tile_mean": cells, **clk})
         print(json.dumps(rows[-1]), flush=True)
+    stop.set()
     tool.check_status()
     return {"ng": ng, "particles": n, "formula": formula, "sort_ms": sort_ms, "blocks": rows,
             "windows": os.environ.get("TURBOPY_B200_WINDOWS", "1") != "0"}
