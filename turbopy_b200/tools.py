@@ -578,9 +578,13 @@ class BorisPush(ComputeTool):
                 if _steps is None:
                     win = self._tile_windows(p, g, position, momentum, axis, grid, dev)
                     if win is not None:
-                        rec = self._records.get((ng, dev))
+                        stream = _stream_ptr(dev)
+                        rkey = (ng, dev, stream.value)       # one scratch per stream: calls on a stream are ordered
+                        rec = self._records.get(rkey)
                         if rec is None:
-                            rec = self._records[(ng, dev)] = torch.empty(18 * ng, dtype=torch.float64, device=dev)
+                            if len(self._records) > 8:
+                                self._records.clear()
+                            rec = self._records[rkey] = torch.empty(18 * ng, dtype=torch.float64, device=dev)
                         _lib.check(lib.tp_gather_push_windows_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
                                                                   C.c_void_p(win.data_ptr()), win.shape[0],
                                                                   C.c_void_p(rec.data_ptr()),
