@@ -431,8 +431,10 @@ class BorisPush(ComputeTool):
         # never reorders particles and its physics does not depend on their order, but callers that index
         # particles by position in the array would notice, hence opt-in.
         self.sort_every = int(input_data.get("sort_every", 0) or 0)
-        # every full_sort_every-th of those re-orderings is a global sort again (0 = only the first one)
-        self.full_sort_every = int(input_data.get("full_sort_every", 0) or 0)
+        # every full_sort_every-th of those re-orderings is a global sort again (0 = only the first one): a block-local
+        # re-sort moves a particle at most 960 positions, so over thousands of steps the tiles slowly widen
+        # (profiles/r2_window_kernel.md: 10 -> 54 cells per tile after 500 steps at K = 100)
+        self.full_sort_every = int(input_data.get("full_sort_every", 10) or 0)
         self._sort_calls = {}
 
     # -- the reference method ------------------------------------------------
