@@ -42,15 +42,16 @@ __device__ __forceinline__ void boris_step(const PushK& k, const Vec3& eq, const
     const double m1 = root<FAST>(k.mm + quot<FAST>(pp, rc2, g), g);
     // :433  t = dt*B*charge/m1/2
     const Recip<FAST> r1 = make_recip<FAST>(m1, g);
-    const double tx = quot<FAST>(bq.x, r1, g) * 0.5;
-    const double ty = quot<FAST>(bq.y, r1, g) * 0.5;
-    const double tz = quot<FAST>(bq.z, r1, g) * 0.5;
+    const double ux = quot<FAST>(bq.x, r1, g), uy = quot<FAST>(bq.y, r1, g), uz = quot<FAST>(bq.z, r1, g);
+    const double tx = ux * 0.5, ty = uy * 0.5, tz = uz * 0.5;
     // :434  s = 2*t/(1 + sum(t*t))
     const double den = 1.0 + ((tx * tx + ty * ty) + tz * tz);
     const Recip<FAST> rd = make_recip<FAST>(den, g);
-    const double sx = quot<FAST>(2.0 * tx, rd, g);
-    const double sy = quot<FAST>(2.0 * ty, rd, g);
-    const double sz = quot<FAST>(2.0 * tz, rd, g);
+    // 2*t: on the FAST path it is u itself -- halving and doubling are exact unless u*0.5 lost a bit to underflow
+    // (|u| < 2^-1021), and such a numerator trips the guard either way; the IEEE path forms 2*t literally.
+    const double sx = quot<FAST>(FAST ? ux : 2.0 * tx, rd, g);
+    const double sy = quot<FAST>(FAST ? uy : 2.0 * ty, rd, g);
+    const double sz = quot<FAST>(FAST ? uz : 2.0 * tz, rd, g);
     // :436  vprime = vminus + cross(vminus, t)
     const double vpx = vmx + (vmy * tz - vmz * ty);
     const double vpy = vmy + (vmz * tx - vmx * tz);
