@@ -49,7 +49,9 @@ __device__ __forceinline__ int guess_cell(double x, double r_first, double inv_d
     return max(0, min(j, ng - 2));
 }
 
-template <int FORMULA>
+// ALL: every one of the six components is on the grid (kernel-uniform, tested once by the caller): no null checks,
+// and interp_nodes() below is called with a literal mask so that its per-component selects fold away.
+template <int FORMULA, bool ALL = false>
 __device__ __forceinline__ void fetch_nodes(const GridView& g, double x, NodePair& np) {
     const int j = guess_cell(x, g.r_first, g.inv_dr, g.ng);
     np.j = j;
@@ -62,7 +64,7 @@ __device__ __forceinline__ void fetch_nodes(const GridView& g, double x, NodePai
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         np.y0[k] = 0.0; np.y1[k] = 0.0;
-        if (g.comp[k] != nullptr) {
+        if (ALL || g.comp[k] != nullptr) {
             const double* y = g.comp[k] + static_cast<int64_t>(j) * g.stride[k];
             np.y0[k] = y[0];
             np.y1[k] = y[g.stride[k]];
@@ -171,10 +173,15 @@ __device__ __forceinline__ void ld_cell(const double* p, double (&c)[16], uint64
 __device__ __forceinline__ bool interp_cell_b(const double (&c)[16], double x, unsigned present, double (&F)[6]) {
     const double x0 = c[0], x1 = c[1];
     const double dx0 = x - x0;
+    if (present == 0x3fu) {                         // all six components on the grid (kernel-uniform): no selects
+#pragma unroll                                      // (ncu: 24 FSEL + their predicates per pair of particles otherwise)
+        for (int k = 0; k < 6; ++k) F[k] = c[8 + k] * dx0 + c[2 + k];
+    } else {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        F[k] = 0.0;
-        if (present & (1u << k)) F[k] = c[8 + k] * dx0 + c[2 + k];
+        for (int k = 0; k < 6; ++k) {
+            F[k] = 0.0;
+            if (present & (1u << k)) F[k] = c[8 + k] * dx0 + c[2 + k];
+        }
     }
     return (x0 < x) && (x < x1);                    // strictly inside the cell (false for NaN): else the exact path
 }
@@ -231,8 +238,13 @@ __device__ __forceinline__ unsigned present_mask(const GridView& g) {
 template <int FORMULA>
 __device__ __forceinline__ bool gather6_fast(const GridView& g, double x, double (&F)[6], Guard& gd) {
     NodePair np;
+    const unsigned present = present_mask(g);
+    if (present == 0x3fu) {                          // kernel-uniform
+        fetch_nodes<FORMULA, true>(g, x, np);
+        return interp_nodes<FORMULA>(np, x, g.dr, g.ng, 0x3fu, F, gd);
+    }
     fetch_nodes<FORMULA>(g, x, np);
-    return interp_nodes<FORMULA>(np, x, g.dr, g.ng, present_mask(g), F, gd);
+    return interp_nodes<FORMULA>(np, x, g.dr, g.ng, present, F, gd);
 }
 
 template <int FORMULA>
@@ -246,6 +258,7 @@ template <int FORMULA>
 __device__ __forceinline__ bool gather6_fast_records(const RecView& rv, double x, double (&F)[6], Guard& gd) {
     NodePair np;
     fetch_records<FORMULA>(rv, x, np);
+    if (rv.present == 0x3fu) return interp_nodes<FORMULA>(np, x, rv.dr, rv.ng, 0x3fu, F, gd);
     return interp_nodes<FORMULA>(np, x, rv.dr, rv.ng, rv.present, F, gd);
 }
 

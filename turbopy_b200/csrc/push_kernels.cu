@@ -338,7 +338,8 @@ __device__ __forceinline__ void gather_pair_fast_window(const GatherArgs& a, con
     {
         double F[6];
         Guard gd;
-        const bool ok = interp_nodes<FORMULA>(n0, xa, rv.dr, rv.ng, rv.present, F, gd);
+        const bool ok = rv.present == 0x3fu ? interp_nodes<FORMULA>(n0, xa, rv.dr, rv.ng, 0x3fu, F, gd)
+                                            : interp_nodes<FORMULA>(n0, xa, rv.dr, rv.ng, rv.present, F, gd);
         Vec3 E, B;
         E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
         boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x[0], p[0], gd);
@@ -347,7 +348,8 @@ __device__ __forceinline__ void gather_pair_fast_window(const GatherArgs& a, con
     {
         double F[6];
         Guard gd;
-        const bool ok = interp_nodes<FORMULA>(n1, xb, rv.dr, rv.ng, rv.present, F, gd);
+        const bool ok = rv.present == 0x3fu ? interp_nodes<FORMULA>(n1, xb, rv.dr, rv.ng, 0x3fu, F, gd)
+                                            : interp_nodes<FORMULA>(n1, xb, rv.dr, rv.ng, rv.present, F, gd);
         Vec3 E, B;
         E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
         boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x[1], p[1], gd);
