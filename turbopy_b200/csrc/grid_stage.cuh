@@ -58,17 +58,23 @@ __device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* sr
         : "memory");
 }
 
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires)
+// instead of re-issuing try_wait + branch every few hundred cycles (ncu, round 2: ~33 of 620 warp instructions per
+// tile iteration were such spins -- issue slots and power that a power-capped kernel wants back).
+#ifndef TP_MBAR_SUSPEND_NS
+#define TP_MBAR_SUSPEND_NS 0x989680
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra.uni WAIT_DONE;\n"
         "bra.uni WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(static_cast<uint32_t>(TP_MBAR_SUSPEND_NS))
         : "memory");
 }
 
