@@ -20,7 +20,18 @@ int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_
 
 namespace {
 
-constexpr int kBufs = 3;
+constexpr int kBufs = 6;                       // most buffers / streams in flight; host_bufs() of them are used
+// Pipeline depth: chunks in flight, each on its own stream (H2D -> kernel -> D2H).  Three keep both copy directions
+// busy when the link is symmetric (one GPU: 95 % of the duplex ceiling); with several ranks on one host the two
+// directions run at different, fluctuating rates and a deeper pipeline absorbs it (tunable: TURBOPY_B200_HOST_BUFS).
+inline int host_bufs() {
+    static const int n = [] {
+        const char* e = std::getenv("TURBOPY_B200_HOST_BUFS");
+        const int v = e ? std::atoi(e) : 4;
+        return std::max(2, std::min(kBufs, v));
+    }();
+    return n;
+}
 constexpr int64_t kChunk = 4ll << 20;          // most particles per chunk (192 MB of state)
 constexpr int64_t kMinChunk = 256ll << 10;
 
@@ -42,8 +53,9 @@ inline int64_t chunk_for(int64_t n) {
 }
 
 struct HostCtx {
-    cudaStream_t stream[kBufs] = {nullptr, nullptr, nullptr};
-    double* dev[kBufs] = {nullptr, nullptr, nullptr};   // 12 * cap doubles each: pos, mom, E, B
+    cudaStream_t stream[kBufs] = {};
+    double* dev[kBufs] = {};                            // 12 * cap doubles each: pos, mom, E, B
+    cudaEvent_t grid_ready = nullptr;                   // the uploaded grid (stream 0) is complete
     int64_t cap = 0;
     double* grid_dev = nullptr; int64_t grid_cap = 0;   // uploaded grid (r + components)
     uint64_t* status_dev = nullptr;
@@ -69,13 +81,14 @@ int ensure_ctx(int64_t chunk, int64_t grid_doubles) {
     if (!c.init) {
         for (int b = 0; b < kBufs; ++b) TP_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream[b], cudaStreamNonBlocking));
         TP_CUDA_TRY(cudaMalloc(&c.status_dev, 4 * sizeof(uint64_t)));
+        TP_CUDA_TRY(cudaEventCreateWithFlags(&c.grid_ready, cudaEventDisableTiming));
         c.init = true;
     }
     if (chunk > c.cap) {
         for (int b = 0; b < kBufs; ++b) {
             if (c.dev[b]) cudaFree(c.dev[b]);
             c.dev[b] = nullptr;
-            TP_CUDA_TRY(cudaMalloc(&c.dev[b], sizeof(double) * 12 * chunk));
+            if (b < host_bufs()) TP_CUDA_TRY(cudaMalloc(&c.dev[b], sizeof(double) * 12 * chunk));
         }
         c.cap = chunk;
     }
@@ -147,7 +160,7 @@ int run_chunks_unsafe(const tp_particles* p, const double* E_host, bool e_pp, co
     int rc = TP_OK;
     int idx = 0;
     for (int64_t i0 = 0; i0 < n; i0 += chunk, ++idx) {
-        const int b = idx % kBufs;
+        const int b = idx % host_bufs();
         const int64_t m = std::min(chunk, n - i0);
         cudaStream_t s = c.stream[b];
         double* base = c.dev[b];
@@ -275,10 +288,12 @@ extern "C" int tp_gather_push_host_f64(const tp_particles* p, const tp_push_cons
         dg.comp_stride[cc] = 1;
     }
     if ((rc = tp_status_reset(c.status_dev, s0))) return rc;
-    TP_CUDA_TRY(cudaStreamSynchronize(s0));
+    // the chunk pipeline starts right away: its particle uploads overlap the grid upload, only the KERNELS wait for it
+    TP_CUDA_TRY(cudaEventRecord(c.grid_ready, s0));
     if (p->n > 0) {
         rc = run_chunks(p, nullptr, false, nullptr, false,
                         [&](const tp_particles& dp, double*, int64_t, cudaStream_t s) {
+                            if (s != s0) TP_CUDA_TRY(cudaStreamWaitEvent(s, c.grid_ready, 0));
                             return gather_push_device(&dp, k, &dg, axis, formula, c.status_dev, s, 1, nullptr, 0, nullptr);
                         });
         if (rc) return rc;
@@ -335,7 +350,8 @@ extern "C" int tp_host_release(void) {
         }
         if (c.grid_dev) cudaFree(c.grid_dev);
         if (c.status_dev) cudaFree(c.status_dev);
-        c.grid_dev = nullptr; c.status_dev = nullptr; c.cap = 0; c.grid_cap = 0; c.init = false;
+        if (c.grid_ready) cudaEventDestroy(c.grid_ready);
+        c.grid_dev = nullptr; c.status_dev = nullptr; c.grid_ready = nullptr; c.cap = 0; c.grid_cap = 0; c.init = false;
     }
     cudaSetDevice(keep);
     return TP_OK;
