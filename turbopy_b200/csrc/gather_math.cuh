@@ -235,6 +235,33 @@ __device__ __forceinline__ unsigned present_mask(const GridView& g) {
     return m;
 }
 
+// PMASK != 0: the set of components on the grid is known at COMPILE time (the specialised kernels of the common
+// shapes: 0x02 = E_y only, the particle-in-field example; 0x07 = E only).  Absent components then cost nothing --
+// no null checks, no zeroing, no selects: ~100 of the generic kernel's 692 warp instructions per two particles in
+// the pif shape (profiles/r2_window_kernel.md), which is what a power-capped GPU wants back.
+template <int FORMULA, unsigned PMASK>
+__device__ __forceinline__ bool gather6_fast_mask(const GridView& g, double x, double (&F)[6], Guard& gd) {
+    NodePair np;
+    const int j = guess_cell(x, g.r_first, g.inv_dr, g.ng);
+    np.j = j;
+    np.x0 = g.r[j];
+    np.x1 = g.r[j + 1];
+    if (FORMULA == TP_INTERP_A) {
+        np.xm = g.r[max(j - 1, 0)];
+        np.xp = g.r[min(j + 2, g.ng - 1)];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        np.y0[k] = 0.0; np.y1[k] = 0.0;
+        if (PMASK & (1u << k)) {
+            const double* y = g.comp[k] + static_cast<int64_t>(j) * g.stride[k];
+            np.y0[k] = y[0];
+            np.y1[k] = y[g.stride[k]];
+        }
+    }
+    return interp_nodes<FORMULA>(np, x, g.dr, g.ng, PMASK, F, gd);
+}
+
 template <int FORMULA>
 __device__ __forceinline__ bool gather6_fast(const GridView& g, double x, double (&F)[6], Guard& gd) {
     NodePair np;

@@ -96,11 +96,12 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) push_kernel(const __g
 // a particle that is off the grid makes it false; the clamped index keeps the loads in bounds.  Multi-step passes
 // (GatherArgs::nsteps) loop around this at the call sites, both particles of a thread inside one iteration, so
 // that the two independent dependency chains stay interleaved.
-template <int FORMULA>
+template <int FORMULA, unsigned PMASK = 0u>
 __device__ __forceinline__ bool gather_step_fast(const GatherArgs& a, const GridView& g, Vec3& x, Vec3& p) {
     double F[6];
     Guard gd;
-    bool ok = gather6_fast<FORMULA>(g, axis_of(x, a.axis), F, gd);
+    bool ok = PMASK ? gather6_fast_mask<FORMULA, PMASK>(g, axis_of(x, a.axis), F, gd)
+                    : gather6_fast<FORMULA>(g, axis_of(x, a.axis), F, gd);
     Vec3 E, B;
     E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
     boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
@@ -292,7 +293,9 @@ __device__ __noinline__ void gather_step_exact_slot(const GatherArgs& a, unsigne
 // GMODE: 0 = field arrays read from global memory / L2, 1 = arrays staged in
 // shared memory by the TMA, 2 = packed node records in L2 (fast path only; the
 // recovery path always reads the original arrays).
-template <int FORMULA, int GMODE, bool AOS>
+// PMASK: 0 = which components are on the grid is a run-time property (any shape); otherwise the compile-time mask of
+// a specialised shape (staged grids only: see gather6_fast_mask).
+template <int FORMULA, int GMODE, bool AOS, unsigned PMASK = 0u>
 __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const __grid_constant__ TmaArgs ta) {
     constexpr bool STAGED = GMODE == 1;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const _
     tma_ring<AOS>(
         a.p, ta.ring, smem,
         [&](Vec3& x, Vec3& p) {
-            return GMODE == 2 ? gather_step_fast_records<FORMULA>(a, rv, x, p) : gather_step_fast<FORMULA>(a, g, x, p);
+            return GMODE == 2 ? gather_step_fast_records<FORMULA>(a, rv, x, p) : gather_step_fast<FORMULA, PMASK>(a, g, x, p);
         },
         [&](int64_t i, double* xs, double* ps, int pitch) {
             gather_step_exact_slot<FORMULA, STAGED>(a, smem, i, xs, ps, pitch);
@@ -847,9 +850,9 @@ static int launch_gather_push_f(const GatherArgs& a, int formula, size_t smem, b
 }
 
 // TMA-pipelined variant: SoA or AoS, 16-byte aligned arrays, at least one full tile per SM.
-template <int FORMULA, int GMODE, bool AOS>
+template <int FORMULA, int GMODE, bool AOS, unsigned PMASK = 0u>
 static int launch_gather_push_tma(const TmaArgs& ta, size_t smem, int blocks, cudaStream_t s) {
-    auto kern = gather_push_tma_kernel<FORMULA, GMODE, AOS>;
+    auto kern = gather_push_tma_kernel<FORMULA, GMODE, AOS, PMASK>;
     int rc = set_smem(kern, smem);
     if (rc) return rc;
     kern<<<blocks, kTmaThreads, smem, s>>>(ta);
@@ -857,8 +860,26 @@ static int launch_gather_push_tma(const TmaArgs& ta, size_t smem, int blocks, cu
     return static_cast<int>(cudaGetLastError());
 }
 
+static bool mask_kernels_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("TURBOPY_B200_MASK_KERNELS");     // tuning / A-B switch, default on
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 template <int FORMULA>
 static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, int gmode, bool aos, cudaStream_t s) {
+    if (gmode == 1 && mask_kernels_enabled()) {              // staged grid: the specialised shapes
+        unsigned mask = 0;
+        for (int k = 0; k < 6; ++k) mask |= ta.g.comp[k] ? (1u << k) : 0u;
+        if (mask == 0x02u)
+            return aos ? launch_gather_push_tma<FORMULA, 1, true, 0x02u>(ta, smem, blocks, s)
+                       : launch_gather_push_tma<FORMULA, 1, false, 0x02u>(ta, smem, blocks, s);
+        if (mask == 0x07u)
+            return aos ? launch_gather_push_tma<FORMULA, 1, true, 0x07u>(ta, smem, blocks, s)
+                       : launch_gather_push_tma<FORMULA, 1, false, 0x07u>(ta, smem, blocks, s);
+    }
     switch (gmode) {
         case 1: return aos ? launch_gather_push_tma<FORMULA, 1, true>(ta, smem, blocks, s)
                            : launch_gather_push_tma<FORMULA, 1, false>(ta, smem, blocks, s);
