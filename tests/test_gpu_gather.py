@@ -322,3 +322,35 @@ def test_interpolate1d_linspace_abscissas_same_bits(tp, ng, monkeypatch):
         assert_bits_equal(np.nan_to_num(got, nan=-7.0), np.nan_to_num(want, nan=-7.0))
     monkeypatch.delenv("TURBOPY_B200_LINSPACE")
     assert tool.interpolate1D(grid.r ** 3, y)._lin is None or ng == 2        # stretched abscissas: not a linspace
+
+
+@pytest.mark.parametrize("formula", ["A", "B", "C"])
+@pytest.mark.parametrize("shape", ["ey_only", "e_only", "ey_bz"])
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_mask_specialised_kernels_vs_oracle(tp, formula, shape, layout, monkeypatch):
+    """The staged TMA kernel has compile-time instances for the common component sets (0x02 = E_y only, the pif shape;
+    0x07 = E only); any other set (here E_y + B_z) runs the generic kernel.  Same bits as the oracle, with the
+    specialised kernels switched on and off, incl. on-node / out-of-grid particles inside full tiles."""
+    ng = 513
+    grid = make_grid(ng)
+    dt = 2e-12
+    n = 148 * 960 * 2 + 77
+    pos0, mom0 = thermal_ensemble(n, seed=ng + len(shape))
+    pos0[:, 0] = np.random.default_rng(ng).uniform(0.02, 0.98, n)
+    pos0[np.arange(0, n, 9973), 0] = grid.r[(np.arange(0, n, 9973) * 7) % (ng - 2) + 1]
+    comps = smooth_fields(grid)
+    keep = {"ey_only": [1], "e_only": [0, 1, 2], "ey_bz": [1, 5]}[shape]
+    comps = [c if k in keep else None for k, c in enumerate(comps)]
+    dev = [None if c is None else torch.from_numpy(c).cuda() for c in comps]
+    E = tuple(dev[:3]); B = None if all(c is None for c in dev[3:]) else tuple(dev[3:])
+    rp, rm = fused_reference(formula, pos0, mom0, grid, comps, 0, dt, 2)
+    for switch in ("1", "0"):
+        monkeypatch.setenv("TURBOPY_B200_MASK_KERNELS", switch)   # (read once per process: the second pass re-checks the default)
+        tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+        pos = tp.to_soa(pos0) if layout == "soa" else torch.from_numpy(pos0).cuda()
+        mom = tp.to_soa(mom0) if layout == "soa" else torch.from_numpy(mom0).cuda()
+        for _ in range(2):
+            tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, formula={"A": "create_interpolator", "B": "interp", "C": "interp1d_nd"}[formula])
+        tool.check_status()
+        assert_bits_equal(pos.cpu().numpy(), rp, f"position ({switch})")
+        assert_bits_equal(mom.cpu().numpy(), rm, f"momentum ({switch})")
