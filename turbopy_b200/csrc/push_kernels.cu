@@ -873,12 +873,20 @@ static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, 
     if (gmode == 1 && mask_kernels_enabled()) {              // staged grid: the specialised shapes
         unsigned mask = 0;
         for (int k = 0; k < 6; ++k) mask |= ta.g.comp[k] ? (1u << k) : 0u;
+        // Pacing.  The specialised consumers finish a tile in about half the time the memory system needs to deliver
+        // the next one; releasing the stage that early keeps all three stages of all 148 rings in flight at once,
+        // which over-subscribes HBM (the same effect as a fourth stage: measured 262 us per launch instead of 254).
+        // They therefore sleep ~0.8 us per tile before touching it (no issue slots, no power): 254 us per launch,
+        // 97 % of the HBM peak over 8000 steps (profiles/r2_window_kernel.md).
+        static const int pace = [] { const char* e = std::getenv("TURBOPY_B200_CONSUMER_DELAY_NS"); return e ? std::atoi(e) : 800; }();
+        TmaArgs tb = ta;
+        tb.ring.consumer_delay_ns = pace;
         if (mask == 0x02u)
-            return aos ? launch_gather_push_tma<FORMULA, 1, true, 0x02u>(ta, smem, blocks, s)
-                       : launch_gather_push_tma<FORMULA, 1, false, 0x02u>(ta, smem, blocks, s);
+            return aos ? launch_gather_push_tma<FORMULA, 1, true, 0x02u>(tb, smem, blocks, s)
+                       : launch_gather_push_tma<FORMULA, 1, false, 0x02u>(tb, smem, blocks, s);
         if (mask == 0x07u)
-            return aos ? launch_gather_push_tma<FORMULA, 1, true, 0x07u>(ta, smem, blocks, s)
-                       : launch_gather_push_tma<FORMULA, 1, false, 0x07u>(ta, smem, blocks, s);
+            return aos ? launch_gather_push_tma<FORMULA, 1, true, 0x07u>(tb, smem, blocks, s)
+                       : launch_gather_push_tma<FORMULA, 1, false, 0x07u>(tb, smem, blocks, s);
     }
     switch (gmode) {
         case 1: return aos ? launch_gather_push_tma<FORMULA, 1, true>(ta, smem, blocks, s)
@@ -960,6 +968,7 @@ static bool plan_ring(int64_t n, size_t front, RingArgs& ring, size_t& smem, int
     const DeviceProps& d = device_props();
     ring.ntiles = n / tile;
     ring.stream_hint = 0;
+    ring.consumer_delay_ns = 0;
     if (!tma_enabled() || ring.ntiles < d.sm_count) return false;
     ring.tiles_off = static_cast<uint32_t>((front + 127) & ~size_t(127));
     const int64_t room = d.smem_optin - 1024 - static_cast<int64_t>(ring.tiles_off);

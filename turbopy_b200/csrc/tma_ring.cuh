@@ -46,6 +46,7 @@ struct RingArgs {
     uint32_t tiles_off;        // byte offset of stage 0 in dynamic shared memory (128-B aligned)
     int64_t ntiles;            // full tiles; the remaining n - ntiles*kTile particles use the scalar path
     int stream_hint;           // 1: particle loads / stores carry the L2 evict_first policy
+    int consumer_delay_ns;     // pacing of fast consumers: sleep this long per tile before touching it (0 = none)
 };
 
 __device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
@@ -209,6 +210,7 @@ __device__ __forceinline__ void tma_ring(const ParticleArgs& P, const RingArgs& 
     // -------------------- consumer warps --------------------
     for (int64_t t = t0; t < ra.ntiles; t += tstep) {
         mbar_wait(&full[s], parity);
+        if (ra.consumer_delay_ns) __nanosleep(ra.consumer_delay_ns);
         double* stage = reinterpret_cast<double*>(tiles + s * kTileBytes);
         Vec3 x[2], p[2];
         stage_read<AOS>(stage, x, p);
