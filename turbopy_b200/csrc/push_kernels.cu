@@ -1184,6 +1184,8 @@ static int boris_push_device(const tp_particles* p, const tp_push_consts* k, con
             int nst = kPushStages;
             if (const char* cap = std::getenv("TURBOPY_B200_STAGES")) nst = std::min(kRingMaxStages, std::max(2, std::atoi(cap)));
             ta.ring.nstages = nst;
+            static const int push_pace = [] { const char* e = std::getenv("TURBOPY_B200_PUSH_DELAY_NS"); return e ? std::atoi(e) : 0; }();
+            ta.ring.consumer_delay_ns = push_pace;
             smem = ta.ring.tiles_off + static_cast<size_t>(nst) * 2 * kArrayF;
             if (aos16) {
                 if ((rc = set_smem(push_tma_kernel<true>, smem))) return rc;

@@ -107,6 +107,7 @@ __device__ __forceinline__ void tma_ring_fields(const PushArgs& a, const RingArg
     constexpr int pitch = PA ? 1 : kTileF;
     for (int64_t t = t0; t < ra.ntiles; t += tstep) {
         mbar_wait(&full[s], parity);
+        if (ra.consumer_delay_ns) __nanosleep(ra.consumer_delay_ns);          // pacing of fast consumers (tma_ring.cuh)
         unsigned char* st = tiles + s * kStage;
         Vec3 x = slot_read<PA>(st), p = slot_read<PA>(st + kArrayF);
         Vec3 E = {0.0, 0.0, 0.0}, B = {0.0, 0.0, 0.0};
