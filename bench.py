@@ -584,7 +584,8 @@ def run_b200(args):
         ms, launches, window = b.timed((lambda k: graph.replay()) if graph is not None else
                                        (lambda k: [step(W + s) for s in range(k)]), K, sampler)
         pusher.check_status()
-        kernel = "gather_push_tma_kernel<interp(B), staged> (TMA-pipelined fused gather + Boris push)"
+        kernel = ("gather_push_tma_kernel<interp(B), staged, SoA, PMASK=0x02> (TMA-pipelined fused gather + Boris push; "
+                  "the instance specialised for E_y-only grids, consumers paced 0.8 us per tile)")
         layout_note = "SoA fp64 resident"
         order_note = None
     else:
