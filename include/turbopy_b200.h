@@ -171,6 +171,8 @@ int tp_gather_push_windows_f64(const tp_particles* p, const tp_push_consts* k,
                                double* records_scratch /* DEVICE, TP_RECORDS_DOUBLES_PER_NODE*ng doubles, or NULL: library-owned */,
                                uint64_t* status, tp_stream_t stream);
 int64_t tp_gather_windows_len(const tp_particles* p, const tp_grid_fields* g);
+/* cells per tile a staged window can hold (formula-dependent record size); 0 when windows would not be used */
+int64_t tp_gather_windows_capacity(const tp_particles* p, const tp_grid_fields* g, int formula);
 /* prime tile_bounds from the particles' current coordinates (8 B read per particle); a zeroed array is valid too */
 int tp_gather_windows_init(const tp_particles* p, const tp_grid_fields* g, int axis,
                            int32_t* tile_bounds, int64_t tile_bounds_len, tp_stream_t stream);

@@ -60,6 +60,7 @@ SIGNATURES = {
                                              C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p]),
     "tp_gather_windows_len": (C.c_int64, [C.POINTER(Particles), C.POINTER(GridFields)]),
+    "tp_gather_windows_capacity": (C.c_int64, [C.POINTER(Particles), C.POINTER(GridFields), C.c_int]),
     "tp_gather_windows_init": (C.c_int, [C.POINTER(Particles), C.POINTER(GridFields), C.c_int, C.c_void_p, C.c_int64,
                                          C.c_void_p]),
     "tp_status_reset": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1277,6 +1277,23 @@ extern "C" int64_t tp_gather_windows_len(const tp_particles* p, const tp_grid_fi
     return 2 * ring.ntiles;
 }
 
+// Cells per tile the staged window can hold for this ensemble / grid / formula (0: the windowed kernel would not run).
+// The Python tool compares it with the primed bounds to decide whether windows pay at all (particles in random order:
+// they do not, and the packed 64-byte node records of tp_gather_push_f64 are the better table for the L2 path).
+extern "C" int64_t tp_gather_windows_capacity(const tp_particles* p, const tp_grid_fields* g, int formula) {
+    const DeviceProps& d = device_props();
+    if (d.status != TP_OK) return 0;
+    GatherArgs a;
+    std::memset(&a, 0, sizeof(a));
+    bool vec2 = false, aos16 = false;
+    if (fill_particles(p, a.p, vec2, &aos16) || !(vec2 || aos16)) return 0;
+    size_t smem = 0; bool staged = false;
+    if (fill_grid(g, a, smem, staged) || staged) return 0;
+    RingArgs ring; WindowArgs win; int blocks = 0;
+    if (!plan_window_ring(a.p.n, ring, win, smem, blocks)) return 0;
+    return formula == TP_INTERP_B ? win.win_bytes / kCellBytes : static_cast<int64_t>(win.win_bytes / kRecBytes) - 3;
+}
+
 // Prime the tile bounds from the particles' current coordinates along `axis` (first call for an ensemble, or after
 // the caller re-ordered it); a zeroed buffer is also valid (the first step then gathers through L2 and primes it).
 extern "C" int tp_gather_windows_init(const tp_particles* p, const tp_grid_fields* g, int axis, int32_t* tile_bounds,

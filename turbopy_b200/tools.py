@@ -578,7 +578,7 @@ class BorisPush(ComputeTool):
                 self._sort_calls[ck] = calls + 1
             with _on_device(dev):
                 if _steps is None:
-                    win = self._tile_windows(p, g, position, momentum, axis, grid, dev)
+                    win = self._tile_windows(p, g, position, momentum, axis, grid, dev, code)
                     if win is not None:
                         stream = _stream_ptr(dev)
                         rkey = (ng, dev, stream.value)       # one scratch per stream: calls on a stream are ordered
@@ -623,7 +623,7 @@ class BorisPush(ComputeTool):
             return None
         raise TypeError("position/momentum must both be CUDA float64 tensors or both numpy float64 arrays")
 
-    def _tile_windows(self, p, g, position, momentum, axis, grid, dev):
+    def _tile_windows(self, p, g, position, momentum, axis, grid, dev, code=_lib.TP_INTERP_B):
         """The int32 tile-bounds tensor of this ensemble for tp_gather_push_windows_f64 (None when the library would
         not use per-tile windows: grid staged whole in shared memory, small ensemble, odd layout).  Primed from the
         current coordinates the first time an ensemble is seen and whenever the particles were re-ordered
@@ -636,15 +636,24 @@ class BorisPush(ComputeTool):
             need = int(_lib.lib().tp_gather_windows_len(C.byref(p), C.byref(g)))
             if len(self._windows) > 8:
                 self._windows.clear()
-            hit = self._windows[key] = [torch.zeros(need, dtype=torch.int32, device=dev) if need else None, -1]
-        buf, generation = hit
+            hit = self._windows[key] = [torch.zeros(need, dtype=torch.int32, device=dev) if need else None, -1, True]
+        buf, generation, pays = hit
         if buf is None:
             return None
         if generation != particles.order_generation:
             _lib.check(_lib.lib().tp_gather_windows_init(C.byref(p), C.byref(g), axis, C.c_void_p(buf.data_ptr()),
                                                          buf.shape[0], _stream_ptr(dev)))
             hit[1] = particles.order_generation
-        return buf
+            # Do windows pay for this ensemble?  In random order no tile's cells fit a window and every particle takes
+            # the L2 path, for which round 1's packed 64-byte node records (tp_gather_push_f64) are the better table
+            # (the 144-byte cell records do not fit L2 next to the particle stream: 31 vs 25 G pushes/s).  Decided
+            # from the primed bounds, once per ensemble and re-ordering (one small D2H read; skipped under capture).
+            hit[2] = True
+            if not torch.cuda.is_current_stream_capturing():
+                cap = int(_lib.lib().tp_gather_windows_capacity(C.byref(p), C.byref(g), code))
+                spans = buf.view(-1, 2)[: int(p.n) // 960, 1]
+                hit[2] = bool(((spans > 0) & (spans <= cap)).float().mean().item() >= 0.5) if spans.numel() else True
+        return buf if hit[2] else None
 
     def check_status(self):
         """Poll the device error flags of :meth:`gather_push` (one small D2H
