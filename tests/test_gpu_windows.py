@@ -50,12 +50,14 @@ def expected_bounds(x, grid, ntiles):
 
 
 @pytest.mark.parametrize("formula", ["A", "B", "C"])
-@pytest.mark.parametrize("ng", [20_001, (1 << 20) + 1])
+@pytest.mark.parametrize("ng", [5_001, 20_001, (1 << 20) + 1])
 @pytest.mark.parametrize("layout", ["soa", "aos"])
 @pytest.mark.parametrize("ordered", [True, False])
 def test_windowed_gather_vs_oracle(tp, formula, ng, layout, ordered):
+    """ng = 5001: 17 cells per cell-ordered tile, the windows fit and serve every particle; 20 001: 67 cells, at the
+    edge of a window's capacity; 2^20+1 with this few particles: 3500 cells per tile, windows never fit (L2 path)."""
     if layout == "aos" and (ng > 100_000 or not ordered):
-        pytest.skip("AoS covered by the ordered mid-size case")
+        pytest.skip("AoS covered by the ordered mid-size cases")
     grid = make_grid(ng)
     dt = 0.5 * grid.dr / 2.9979e8                                  # config 3: half a cell per step at most
     tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
@@ -75,9 +77,23 @@ def test_windowed_gather_vs_oracle(tp, formula, ng, layout, ordered):
     rp, rm = fused_reference(formula, pos0, mom0, grid, comps, 0, dt, steps)
     assert_bits_equal(pos.cpu().numpy(), rp, "position")
     assert_bits_equal(mom.cpu().numpy(), rm, "momentum")
+    # the tool decides from the primed bounds whether windows pay (at least half of the tiles fit a window); in random
+    # order, or with fewer particles per cell than a window can span, they do not and the L2 path runs instead
+    from turbopy_b200 import _lib
+    import ctypes as C
+    ps = tp.tools._particles_struct(pos, mom)
+    gf = _lib.GridFields()
+    gf.ng, gf.dr, gf.r = ng, float(grid.dr), tp.GridOnDevice.of(grid, pos.device).r.data_ptr()
+    gf.r_first, gf.r_last = float(grid.r[0]), float(grid.r[-1])
+    for c in range(3):
+        gf.comp[c], gf.comp_stride[c] = E[:, c].data_ptr(), 3
+        gf.comp[3 + c], gf.comp_stride[3 + c] = B[:, c].data_ptr(), 3
+    cap = int(_lib.lib().tp_gather_windows_capacity(C.byref(ps), C.byref(gf), {"A": 1, "B": 2, "C": 3}[formula]))
+    spans0 = expected_bounds(pos0[:, 0], grid, n // TILE)[:, 1]
+    expect_pays = bool(((spans0 > 0) & (spans0 <= cap)).mean() >= 0.5)
     pays = [w[2] for w in tool._windows.values() if w[0] is not None]
-    assert pays == [ordered]          # random order: the tool saw from the primed bounds that windows do not pay -> L2 path
-    if not ordered:
+    assert pays == [expect_pays] and (ordered or not expect_pays) and cap > 16
+    if not expect_pays:
         return
     # the bounds the last call left behind describe the cells the particles are in NOW
     ntiles = n // TILE

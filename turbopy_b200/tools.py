@@ -578,8 +578,9 @@ class BorisPush(ComputeTool):
                 self._sort_calls[ck] = calls + 1
             with _on_device(dev):
                 if _steps is None:
-                    win = self._tile_windows(p, g, position, momentum, axis, grid, dev, code)
-                    if win is not None:
+                    hit = self._tile_windows(p, g, position, momentum, axis, grid, dev, code)
+                    if hit is not None:             # grid too large for shared memory: caller-owned record scratch
+                        win = hit[0] if hit[2] else None        # (capturable on any stream); windows only if they pay
                         stream = _stream_ptr(dev)
                         rkey = (ng, dev, stream.value)       # one scratch per stream: calls on a stream are ordered
                         rec = self._records.get(rkey)
@@ -588,7 +589,8 @@ class BorisPush(ComputeTool):
                                 self._records.clear()
                             rec = self._records[rkey] = torch.empty(18 * ng, dtype=torch.float64, device=dev)
                         _lib.check(lib.tp_gather_push_windows_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
-                                                                  C.c_void_p(win.data_ptr()), win.shape[0],
+                                                                  C.c_void_p(win.data_ptr()) if win is not None else None,
+                                                                  win.shape[0] if win is not None else 0,
                                                                   C.c_void_p(rec.data_ptr()),
                                                                   C.c_void_p(status.words.data_ptr()), _stream_ptr(dev)))
                     else:
@@ -624,8 +626,9 @@ class BorisPush(ComputeTool):
         raise TypeError("position/momentum must both be CUDA float64 tensors or both numpy float64 arrays")
 
     def _tile_windows(self, p, g, position, momentum, axis, grid, dev, code=_lib.TP_INTERP_B):
-        """The int32 tile-bounds tensor of this ensemble for tp_gather_push_windows_f64 (None when the library would
-        not use per-tile windows: grid staged whole in shared memory, small ensemble, odd layout).  Primed from the
+        """``[tile-bounds tensor, order generation, windows pay]`` of this ensemble for tp_gather_push_windows_f64
+        (None when the library would not use per-tile windows: grid staged whole in shared memory, small ensemble,
+        odd layout).  Primed from the
         current coordinates the first time an ensemble is seen and whenever the particles were re-ordered
         (``sort_every``, or a ``tp.sort_by_cell`` call by anyone); afterwards each call leaves the next call's
         windows behind.  Stale bounds cost speed for one step, never correctness (include/turbopy_b200.h)."""
@@ -639,7 +642,7 @@ class BorisPush(ComputeTool):
             hit = self._windows[key] = [torch.zeros(need, dtype=torch.int32, device=dev) if need else None, -1, True]
         buf, generation, pays = hit
         if buf is None:
-            return None
+            return None                     # windows do not apply (grid staged whole, small ensemble, odd layout)
         if generation != particles.order_generation:
             _lib.check(_lib.lib().tp_gather_windows_init(C.byref(p), C.byref(g), axis, C.c_void_p(buf.data_ptr()),
                                                          buf.shape[0], _stream_ptr(dev)))
@@ -653,7 +656,7 @@ class BorisPush(ComputeTool):
                 cap = int(_lib.lib().tp_gather_windows_capacity(C.byref(p), C.byref(g), code))
                 spans = buf.view(-1, 2)[: int(p.n) // 960, 1]
                 hit[2] = bool(((spans > 0) & (spans <= cap)).float().mean().item() >= 0.5) if spans.numel() else True
-        return buf if hit[2] else None
+        return hit
 
     def check_status(self):
         """Poll the device error flags of :meth:`gather_push` (one small D2H
