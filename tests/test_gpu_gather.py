@@ -1,6 +1,8 @@
 """GPU parity of the linear field gather (Interpolators.interpolate1D, formulas
 A/B/C) and of the fused gather+push kernel, bit-for-bit against the oracle and
 the reference-generated golden vectors."""
+from types import SimpleNamespace
+
 import numpy as np
 import pytest
 import torch
@@ -354,3 +356,63 @@ def test_mask_specialised_kernels_vs_oracle(tp, formula, shape, layout, monkeypa
         tool.check_status()
         assert_bits_equal(pos.cpu().numpy(), rp, f"position ({switch})")
         assert_bits_equal(mom.cpu().numpy(), rm, f"momentum ({switch})")
+
+
+@pytest.mark.parametrize("formula", ["A", "B", "C"])
+@pytest.mark.parametrize("gridkind", ["linspace01", "linspace_offset", "jitter_small", "jitter_large"])
+@pytest.mark.parametrize("n", [7001, 148 * 960 * 2 + 301])
+def test_formula_a_window_margin_edges(tp, gridkind, n, formula):
+    """Formula A's fast path decides 'the window holds exactly nodes j, j+1' from a margin around the two nodes
+    instead of loading r[j-1] and r[j+2] (csrc/gather_math.cuh: window_margin).  Particles a few ulps / a few 1e-16 dr
+    away from a node sit inside that margin and must take the complete semantics; on a grid whose cells are
+    narrower than Grid.dr the window can hold three nodes (core.py:729 assert -> flagged, untouched); with large
+    jitter the margin is switched off.  Register-path (small n) and TMA kernel (large n), staged grids.
+    Formulas B and C ride along on the same points and grids (no window, nothing flagged)."""
+    if formula != "A" and gridkind == "linspace_offset":
+        pytest.skip("formula A only")
+    ng = 1025
+    rng = np.random.default_rng(n + len(gridkind))
+    if gridkind == "linspace01":
+        grid = make_grid(ng)
+    elif gridkind == "linspace_offset":
+        grid = make_grid(ng, -3.7, 11.3)
+    else:
+        grid = make_grid(ng)
+        amp = 1e-3 if gridkind == "jitter_small" else 0.2
+        r = grid.r.copy()
+        r[1:-1] += amp * grid.dr * rng.uniform(-1, 1, ng - 2)
+        grid.r = r
+        grid.cell_widths = r[1:] - r[:-1]
+    span = grid.r[-1] - grid.r[0]
+    dt = 1e-13
+    tool = tp.BorisPush(make_owner(dt=dt, grid=grid), {"type": "BorisPush"})
+    pos0, mom0 = thermal_ensemble(n, seed=n)
+    pos0[:, 0] = grid.r[0] + span * rng.uniform(0.01, 0.99, n)
+    # every third particle next to a node: k ulps or a tiny fraction of dr off, both sides
+    near = np.arange(0, n, 3)
+    j = rng.integers(1, ng - 1, len(near))
+    kind = rng.integers(0, 3, len(near))
+    node = grid.r[j]
+    ulps = rng.choice([1, 2, 3, 5, 8, 16, 100, 10_000], len(near)) * rng.choice([-1, 1], len(near))
+    frac = rng.choice([1e-15, 1e-14, 1e-13, 1e-12, 1e-10, 1e-6, 2e-3, 1.6e-2], len(near)) * rng.choice([-1, 1], len(near))
+    x_ulp = node + ulps * np.spacing(np.abs(node))
+    x_frac = node + frac * grid.dr
+    pos0[near, 0] = np.where(kind == 0, node, np.where(kind == 1, x_ulp, x_frac))
+    comps = smooth_fields(grid)
+    _, st = oracle_gather(formula, pos0[:, 0], SimpleNamespace(r=grid.r, dr=grid.dr, r_min=grid.r[0], r_max=grid.r[-1]), comps[0])
+    bad = st != 0
+    if gridkind.startswith("linspace") or formula != "A":
+        assert not bad.any()
+    E = torch.from_numpy(np.stack(comps[:3], axis=1)).cuda()
+    B = torch.from_numpy(np.stack(comps[3:], axis=1)).cuda()
+    pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+    tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, axis=0, formula=formula)
+    if bad.any():
+        with pytest.raises((ValueError, AssertionError), match=rf"^{int(bad.sum())} particle"):
+            tool.check_status()
+    else:
+        tool.check_status()
+    rp, rm = fused_reference(formula, pos0[~bad], mom0[~bad], grid, comps, 0, dt, 1)
+    gp, gm = pos.cpu().numpy(), mom.cpu().numpy()
+    assert_bits_equal(gp[~bad], rp, "position"); assert_bits_equal(gm[~bad], rm, "momentum")
+    assert_bits_equal(gp[bad], pos0[bad]); assert_bits_equal(gm[bad], mom0[bad])

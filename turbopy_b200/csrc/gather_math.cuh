@@ -28,6 +28,7 @@ struct GridView {
     double        r_first, r_last;
     double        inv_dr;     // only an index guess, never enters a result
     double        dr;         // Grid.dr, formula A's window half-width
+    double        qa;         // formula A: margin of the load-free window test (window_margin below); 0 = not available
 };
 
 // ---------------------------------------------------------------------------
@@ -51,15 +52,19 @@ __device__ __forceinline__ int guess_cell(double x, double r_first, double inv_d
 
 // ALL: every one of the six components is on the grid (kernel-uniform, tested once by the caller): no null checks,
 // and interp_nodes() below is called with a literal mask so that its per-component selects fold away.
-template <int FORMULA, bool ALL = false>
+// QUICK (formula A): the caller holds a window margin (GridView::qa > 0), the outer neighbours are not needed.
+template <int FORMULA, bool ALL = false, bool QUICK = false>
 __device__ __forceinline__ void fetch_nodes(const GridView& g, double x, NodePair& np) {
     const int j = guess_cell(x, g.r_first, g.inv_dr, g.ng);
     np.j = j;
     np.x0 = g.r[j];
     np.x1 = g.r[j + 1];
     if (FORMULA == TP_INTERP_A) {
-        np.xm = g.r[max(j - 1, 0)];
-        np.xp = g.r[min(j + 2, g.ng - 1)];
+        np.xm = 0.0; np.xp = 0.0;
+        if (!QUICK) {
+            np.xm = g.r[max(j - 1, 0)];
+            np.xp = g.r[min(j + 2, g.ng - 1)];
+        }
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -188,9 +193,9 @@ __device__ __forceinline__ bool interp_cell_b(const double (&c)[16], double x, u
 
 // Interpolate the present components from a NodePair.  `present` bit k = 0 means
 // the component is identically zero (F[k] = +0.0 without touching the data).
-template <int FORMULA>
+template <int FORMULA, bool QUICK = false>
 __device__ __forceinline__ bool interp_nodes(const NodePair& np, double x, double dr, int ng, unsigned present,
-                                             double (&F)[6], Guard& gd) {
+                                             double (&F)[6], Guard& gd, double qa = 0.0) {
     const double x0 = np.x0, x1 = np.x1;
     bool ok = (x0 < x) && (x < x1);                 // strictly inside cell j (false for NaN)
     if (FORMULA == TP_INTERP_B) {
@@ -215,10 +220,19 @@ __device__ __forceinline__ bool interp_nodes(const NodePair& np, double x, doubl
     } else {
         // create_interpolator: the window (x-dr, x+dr) must hold exactly nodes j, j+1
         const double lo_edge = x - dr, hi_edge = x + dr;
-        ok = ok && (lo_edge < x0) && (x1 < hi_edge) && (np.j == 0 || !(lo_edge < np.xm)) &&
-             (np.j == ng - 2 || !(np.xp < hi_edge));
-        const Recip<true> rdx = make_recip<true>(x1 - x0, gd);
         const double dx0 = x - x0;
+        if (QUICK)              // window_margin(): at least qa (> 0) away from both nodes => r[j-1], r[j+2] are outside
+            ok = ok && (lo_edge < x0) && (x1 < hi_edge) && (dx0 >= qa) && (x1 - x >= qa);
+        else
+            // The top cell (j == ng - 2, no node j + 2) is recognised by its data: there fetch_nodes() clamps the
+            // index and hands back xp == r[j+1] == x1 (grids are strictly increasing).  Written as `j == ng - 2`,
+            // ptxas 12.9 takes the test from the predicate output of the VIMNMX.RELU that clamps j in guess_cell(),
+            // and the r[j+2] test then passed for every cell below the top one (found by
+            // tests/test_gpu_gather.py::test_formula_a_window_margin_edges on jittered grids; on turboPy's uniform
+            // grids r[j+2] lies outside the window anyway, which is why no earlier test saw it).
+            ok = ok && (lo_edge < x0) && (x1 < hi_edge) && (np.j == 0 || !(lo_edge < np.xm)) &&
+                 (np.xp == x1 || !(np.xp < hi_edge));
+        const Recip<true> rdx = make_recip<true>(x1 - x0, gd);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             F[k] = 0.0;
@@ -226,6 +240,42 @@ __device__ __forceinline__ bool interp_nodes(const NodePair& np, double x, doubl
         }
     }
     return ok;
+}
+
+// Formula A without the outer-neighbour loads.  The fast path must prove that the window (x-dr, x+dr) holds exactly
+// the nodes j, j+1, i.e. besides lo_edge < r[j] and r[j+1] < hi_edge also r[j-1] <= fl(x-dr) and r[j+2] >= fl(x+dr)
+// (core.py:728-729).  With w = the smallest cell width of the grid, r[j-1] <= r[j] - w and r[j+2] >= r[j+1] + w, so
+//     x - r[j] >= (dr - w) + eps   and   r[j+1] - x >= (dr - w) + eps,     eps >= the rounding of fl(x -+ dr),
+// are sufficient: two compares on values the particle already holds instead of two more random node loads (16 of
+// formula A's 128 shared-memory bytes per particle).  On turboPy's linspace grids dr - w is a few ulps, so all but
+// ~1e-12 of the particles pass; those (and every particle of a grid whose cells are much narrower than Grid.dr, where
+// the margin is switched off) are decided by the loads / the exact path as before.  Rounding: widths are taken
+// from fl(r[j+1]-r[j]) >= true width * (1 - 2^-53); fl(x -+ dr) is off by <= 2^-53 (max|r| + dr); the computed
+// differences fl(x - r[j]), fl(r[j+1] - x) are off by a factor <= 1 + 2^-53; the margin below carries a factor 2
+// on top of a 4x larger eps, which covers all of them.
+// Called by ALL threads of the CTA (two barriers); `slot` = 8 bytes of shared memory.
+__device__ __forceinline__ double window_margin(const double* r, int ng, double dr, double r_first, double r_last,
+                                                unsigned long long* slot) {
+    if (threadIdx.x == 0) *slot = ~0ull;
+    __syncthreads();
+    unsigned long long m = ~0ull;
+    for (int j = threadIdx.x; j < ng - 1; j += blockDim.x) {
+        const double w = r[j + 1] - r[j];
+        // positive doubles order like their bit patterns; a non-positive or NaN width switches the margin off
+        m = min(m, w > 0.0 ? static_cast<unsigned long long>(__double_as_longlong(w)) : 0ull);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(slot, m);
+    __syncthreads();
+    const unsigned long long bits = *slot;
+    if (bits == 0ull || bits == ~0ull) return 0.0;
+    const double wmin = __longlong_as_double(static_cast<long long>(bits));
+    const double wlb = wmin - wmin * 0x1p-52;                       // <= the true smallest width
+    const double gap = fmax(dr - wlb, 0.0);
+    const double eps = (fmax(fabs(r_first), fabs(r_last)) + dr) * 0x1p-51;
+    const double margin = 2.0 * (gap + eps);
+    return (margin < dr * 0.015625 && margin > 0.0) ? margin : 0.0;  // also false for NaN / inf
 }
 
 __device__ __forceinline__ unsigned present_mask(const GridView& g) {
@@ -239,7 +289,7 @@ __device__ __forceinline__ unsigned present_mask(const GridView& g) {
 // shapes: 0x02 = E_y only, the particle-in-field example; 0x07 = E only).  Absent components then cost nothing --
 // no null checks, no zeroing, no selects: ~100 of the generic kernel's 692 warp instructions per two particles in
 // the pif shape (profiles/r2_window_kernel.md), which is what a power-capped GPU wants back.
-template <int FORMULA, unsigned PMASK>
+template <int FORMULA, unsigned PMASK, bool QUICK = false>
 __device__ __forceinline__ bool gather6_fast_mask(const GridView& g, double x, double (&F)[6], Guard& gd) {
     NodePair np;
     const int j = guess_cell(x, g.r_first, g.inv_dr, g.ng);
@@ -247,8 +297,11 @@ __device__ __forceinline__ bool gather6_fast_mask(const GridView& g, double x, d
     np.x0 = g.r[j];
     np.x1 = g.r[j + 1];
     if (FORMULA == TP_INTERP_A) {
-        np.xm = g.r[max(j - 1, 0)];
-        np.xp = g.r[min(j + 2, g.ng - 1)];
+        np.xm = 0.0; np.xp = 0.0;
+        if (!QUICK) {
+            np.xm = g.r[max(j - 1, 0)];
+            np.xp = g.r[min(j + 2, g.ng - 1)];
+        }
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -259,19 +312,19 @@ __device__ __forceinline__ bool gather6_fast_mask(const GridView& g, double x, d
             np.y1[k] = y[g.stride[k]];
         }
     }
-    return interp_nodes<FORMULA>(np, x, g.dr, g.ng, PMASK, F, gd);
+    return interp_nodes<FORMULA, QUICK>(np, x, g.dr, g.ng, PMASK, F, gd, g.qa);
 }
 
-template <int FORMULA>
+template <int FORMULA, bool QUICK = false>
 __device__ __forceinline__ bool gather6_fast(const GridView& g, double x, double (&F)[6], Guard& gd) {
     NodePair np;
     const unsigned present = present_mask(g);
     if (present == 0x3fu) {                          // kernel-uniform
-        fetch_nodes<FORMULA, true>(g, x, np);
-        return interp_nodes<FORMULA>(np, x, g.dr, g.ng, 0x3fu, F, gd);
+        fetch_nodes<FORMULA, true, QUICK>(g, x, np);
+        return interp_nodes<FORMULA, QUICK>(np, x, g.dr, g.ng, 0x3fu, F, gd, g.qa);
     }
-    fetch_nodes<FORMULA>(g, x, np);
-    return interp_nodes<FORMULA>(np, x, g.dr, g.ng, present, F, gd);
+    fetch_nodes<FORMULA, false, QUICK>(g, x, np);
+    return interp_nodes<FORMULA, QUICK>(np, x, g.dr, g.ng, present, F, gd, g.qa);
 }
 
 template <int FORMULA>

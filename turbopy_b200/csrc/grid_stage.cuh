@@ -110,7 +110,7 @@ __device__ __forceinline__ void stage_wait(unsigned char* smem) {
 template <bool STAGED>
 __device__ __forceinline__ GridView make_view(const GatherArgs& a, unsigned char* smem) {
     GridView g;
-    g.ng = a.ng; g.r_first = a.r_first; g.r_last = a.r_last; g.inv_dr = a.inv_dr; g.dr = a.dr;
+    g.ng = a.ng; g.r_first = a.r_first; g.r_last = a.r_last; g.inv_dr = a.inv_dr; g.dr = a.dr; g.qa = 0.0;
     if (STAGED) {
         g.r = reinterpret_cast<const double*>(smem + a.r_smem_off);
 #pragma unroll

@@ -96,12 +96,12 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) push_kernel(const __g
 // a particle that is off the grid makes it false; the clamped index keeps the loads in bounds.  Multi-step passes
 // (GatherArgs::nsteps) loop around this at the call sites, both particles of a thread inside one iteration, so
 // that the two independent dependency chains stay interleaved.
-template <int FORMULA, unsigned PMASK = 0u>
+template <int FORMULA, unsigned PMASK = 0u, bool QUICK = false>
 __device__ __forceinline__ bool gather_step_fast(const GatherArgs& a, const GridView& g, Vec3& x, Vec3& p) {
     double F[6];
     Guard gd;
-    bool ok = PMASK ? gather6_fast_mask<FORMULA, PMASK>(g, axis_of(x, a.axis), F, gd)
-                    : gather6_fast<FORMULA>(g, axis_of(x, a.axis), F, gd);
+    bool ok = PMASK ? gather6_fast_mask<FORMULA, PMASK, QUICK>(g, axis_of(x, a.axis), F, gd)
+                    : gather6_fast<FORMULA, QUICK>(g, axis_of(x, a.axis), F, gd);
     Vec3 E, B;
     E.x = F[0]; E.y = F[1]; E.z = F[2]; B.x = F[3]; B.y = F[4]; B.z = F[5];
     boris_step<true>(a.k, dt_field_q(a.k, E), dt_field_q(a.k, B), x, p, gd);
@@ -303,17 +303,23 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const _
     ring_init(ta.ring, smem);
     if (STAGED) stage_issue(a, smem); else __syncthreads();       // (stage_issue syncs after its own init)
     ring_prologue<AOS>(a.p, ta.ring, smem);
-    const GridView g = make_view<STAGED>(a, smem);
+    GridView g = make_view<STAGED>(a, smem);
     if (STAGED) stage_wait(smem);
+    if (STAGED && FORMULA == TP_INTERP_A)           // formula A without the outer-neighbour loads (gather_math.cuh)
+        g.qa = window_margin(g.r, g.ng, g.dr, g.r_first, g.r_last, reinterpret_cast<unsigned long long*>(smem + kMarginSlot));
     const RecView rv = make_rec_view(a, ta.ring.stream_hint);
-    tma_ring<AOS>(
-        a.p, ta.ring, smem,
-        [&](Vec3& x, Vec3& p) {
-            return GMODE == 2 ? gather_step_fast_records<FORMULA>(a, rv, x, p) : gather_step_fast<FORMULA, PMASK>(a, g, x, p);
-        },
-        [&](int64_t i, double* xs, double* ps, int pitch) {
-            gather_step_exact_slot<FORMULA, STAGED>(a, smem, i, xs, ps, pitch);
-        });
+    auto exact = [&](int64_t i, double* xs, double* ps, int pitch) {
+        gather_step_exact_slot<FORMULA, STAGED>(a, smem, i, xs, ps, pitch);
+    };
+    if (STAGED && FORMULA == TP_INTERP_A && g.qa > 0.0)      // (kernel-uniform) the ring instance without the neighbour loads
+        tma_ring<AOS>(a.p, ta.ring, smem, [&](Vec3& x, Vec3& p) { return gather_step_fast<FORMULA, PMASK, true>(a, g, x, p); }, exact);
+    else
+        tma_ring<AOS>(
+            a.p, ta.ring, smem,
+            [&](Vec3& x, Vec3& p) {
+                return GMODE == 2 ? gather_step_fast_records<FORMULA>(a, rv, x, p) : gather_step_fast<FORMULA, PMASK>(a, g, x, p);
+            },
+            exact);
     // ragged tail (< kTile particles) on the last CTA, scalar path
     if (blockIdx.x == gridDim.x - 1) {
         for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {   // all 16 warps

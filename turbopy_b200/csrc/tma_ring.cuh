@@ -170,7 +170,8 @@ __device__ __forceinline__ void slot_write(double* xs, double* ps, int pitch, co
 constexpr int kRingMaxStages = 6;
 __device__ __forceinline__ uint64_t* ring_full(unsigned char* smem) { return reinterpret_cast<uint64_t*>(smem + 16); }
 __device__ __forceinline__ uint64_t* ring_done(unsigned char* smem) { return reinterpret_cast<uint64_t*>(smem + 64); }
-static_assert(64 + 8 * kRingMaxStages <= kSmemHeader, "mbarriers must fit the shared-memory header");
+constexpr uint32_t kMarginSlot = 112;      // 8 bytes of the header: window_margin()'s block reduction (gather_math.cuh)
+static_assert(64 + 8 * kRingMaxStages <= kMarginSlot && kMarginSlot + 8 <= kSmemHeader, "mbarriers must fit the shared-memory header");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
