@@ -416,3 +416,43 @@ def test_formula_a_window_margin_edges(tp, gridkind, n, formula):
     gp, gm = pos.cpu().numpy(), mom.cpu().numpy()
     assert_bits_equal(gp[~bad], rp, "position"); assert_bits_equal(gm[~bad], rm, "momentum")
     assert_bits_equal(gp[bad], pos0[bad]); assert_bits_equal(gm[bad], mom0[bad])
+
+
+@pytest.mark.parametrize("gridkind", ["linspace", "stretched"])
+@pytest.mark.parametrize("ng", [30, 1025, 4097])
+def test_interpolate1d_ring_kernel_vs_numpy(tp, gridkind, ng):
+    """1-D y with enough points for the TMA-ring kernel (interp_cells_ring_kernel: >= 4 tiles of 1920 points per
+    SM): linspace abscissas (x rebuilt in registers) and stretched ones ({x0, x1} table), points on nodes / at both
+    ends / one ulp off nodes inside full tiles (exact path patches the stage slot), NaN abscissas, a ragged tail;
+    bit-identical to numpy.interp and to the register-path kernel; out-of-range points raise like interp1d."""
+    rng = np.random.default_rng(ng)
+    grid = make_grid(ng, -0.5, 1.5)
+    x = grid.r.copy()
+    if gridkind == "stretched":
+        x = -0.5 + 2.0 * np.linspace(0.0, 1.0, ng) ** 1.7
+    y = np.sin(5.0 * x) + 0.1 * x
+    n = 148 * 1920 * 5 + 1237
+    xq = rng.uniform(x[0], x[-1], n)
+    idx = rng.integers(0, n, 20_000)
+    node = x[rng.integers(0, ng, len(idx))]
+    xq[idx] = np.where(rng.random(len(idx)) < 0.5, node, np.clip(np.nextafter(node, rng.choice([-np.inf, np.inf], len(idx))),
+                                                                  x[0], x[-1]))
+    xq[[0, 1, n - 1, n - 2]] = [x[0], x[-1], x[0], x[-1]]
+    nan_at = rng.integers(0, n, 50)
+    xq[nan_at] = np.nan
+    tool = tp.Interpolators(make_owner(), {"type": "Interpolators"})
+    f = tool.interpolate1D(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+    got = f(torch.from_numpy(xq).cuda()).cpu().numpy()
+    ref = np.interp(xq, x, y)
+    ref[nan_at] = np.nan                                          # numpy.interp hands a NaN abscissa back
+    assert_bits_equal(np.isnan(got), np.isnan(ref), "NaN pattern")
+    ok = ~np.isnan(ref)
+    assert_bits_equal(got[ok], ref[ok], "ring kernel vs numpy.interp")
+    # unaligned query view -> not bulk-copyable -> the register-path kernel; same bits
+    xq_dev = torch.empty(n + 1, dtype=torch.float64, device="cuda")[1:]
+    xq_dev.copy_(torch.from_numpy(xq))
+    got2 = f(xq_dev).cpu().numpy()
+    assert_bits_equal(got2[ok], ref[ok], "register-path kernel vs numpy.interp")
+    xq[12345] = x[-1] + 1e-9
+    with pytest.raises(ValueError, match="above the interpolation range"):
+        f(torch.from_numpy(xq).cuda())

@@ -178,6 +178,13 @@ def main():
             add(label, n16, bpp, timed(lambda: f(xq), it))
             f.check()
         del xq
+        if not args.quick:      # the 16 Mi-point call is a 50 us kernel (launch, table build and drain are ~9 us of it)
+            xq = 0.05 + 0.9 * torch.rand(1 << 27, dtype=torch.float64, device="cuda")
+            f = it_tool.interpolate1D(rr, Y[0].contiguous())
+            f.deferred_check = True
+            add(f"interpolate1D ng={ng}, 1-D y (numpy.interp rounding)", 1 << 27, 16, timed(lambda: f(xq), it))
+            f.check()
+            del xq
 
     # ---- kernel 2: FiniteDifference stencils
     for n in ((1 << 24) + 1, (1 << 28)):

@@ -713,6 +713,130 @@ __global__ void __launch_bounds__(kThreads, 3) interp_cells_kernel(const __grid_
     }
 }
 
+// The same on the TMA ring (round 2): the points stream through shared memory like the particles of
+// the push kernels -- one persistent CTA per SM, a producer lane that fills 15 KB stages of 1920 abscissas with
+// cp.async.bulk and drains the results with bulk stores, 15 consumer warps that turn their four points into values IN
+// PLACE (x -> y in the same slots).  No thread waits on a global load; the register-path kernel above needs ~48 KB of
+// its own loads in flight per SM and reaches 70-78 % of the 16 B/point bound, this one is bound by the copy itself.
+// Stage layout: thread t owns points {2t, 2t+1} and {960+2t, 960+2t+1} of the tile (two conflict-free LDS.128).
+constexpr int kTileI = 4 * kConsumers;                            // points per tile
+constexpr uint32_t kStageI = kTileI * sizeof(double);             // 15 KB
+
+struct InterpRingArgs {
+    InterpArgs a;
+    int nstages;
+    uint32_t table_off, tiles_off;
+    int64_t ntiles;
+};
+
+// value of one point by the complete semantics (on a node, at the ends, outside the grid, NaN, non-uniform x)
+__device__ __noinline__ double interp_point_exact_value(const InterpArgs& a, int64_t i) {
+    GridView gv = interp_view(a, make_view<false>(a.g, nullptr), 0);
+#pragma unroll
+    for (int c = 1; c < 6; ++c) gv.comp[c] = nullptr;
+    double F[6];
+    const unsigned st = gather6_exact<TP_INTERP_B>(gv, a.xq[i], F);
+    if (st != 0u) flag_particle(a.g.status, i, st);
+    return st ? __longlong_as_double(0x7ff8000000000000ll) : F[0];
+}
+
+template <bool LIN>
+__global__ void __launch_bounds__(kTmaThreads, 1) interp_cells_ring_kernel(const __grid_constant__ InterpRingArgs ra) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const InterpArgs& a = ra.a;
+    uint64_t* full = ring_full(smem);
+    uint64_t* done = ring_done(smem);
+    unsigned char* tiles = smem + ra.tiles_off;
+    const int nst = ra.nstages;
+    const int64_t t0 = blockIdx.x, tstep = gridDim.x;
+    if (threadIdx.x == 0)
+        for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kConsumerWarps); }
+    __syncthreads();
+    if (threadIdx.x == kConsumers)                                   // first loads fly while the table is built
+        for (int s = 0; s < nst; ++s) {
+            const int64_t t = t0 + s * tstep;
+            if (t >= ra.ntiles) break;
+            mbar_expect_tx(&full[s], kStageI);
+            tma_bulk_g2s(tiles + s * kStageI, a.xq + t * kTileI, kStageI, &full[s]);
+        }
+    double2* ys = reinterpret_cast<double2*>(smem + ra.table_off);           // {y0, slope} per cell
+    double2* xs = ys + (a.g.ng - 1);                                         // {x0, x1} per cell (not LIN)
+    {
+        const int ncell = a.g.ng - 1;
+        const double* y = a.g.comp[0];
+        const int sn = a.g.stride[0];
+        for (int j = threadIdx.x; j < ncell; j += kTmaThreads) {
+            const double x0 = LIN ? lin_r(a.lin, j) : a.g.r[j], x1 = LIN ? lin_r(a.lin, j + 1) : a.g.r[j + 1];
+            const double y0 = y[static_cast<int64_t>(j) * sn], y1 = y[static_cast<int64_t>(j + 1) * sn];
+            ys[j] = make_double2(y0, (y1 - y0) / (x1 - x0));
+            if (!LIN) xs[j] = make_double2(x0, x1);
+        }
+    }
+    __syncthreads();
+    int s = 0;
+    uint32_t parity = 0;
+    if (threadIdx.x >= kConsumers) {
+        if (threadIdx.x == kConsumers) {                             // the producer lane
+            for (int64_t t = t0; t < ra.ntiles; t += tstep) {
+                mbar_wait(&done[s], parity);
+                tma_bulk_s2g(a.out + t * kTileI, tiles + s * kStageI, kStageI);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                const int64_t tn = t + nst * tstep;
+                if (tn < ra.ntiles) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_expect_tx(&full[s], kStageI);
+                    tma_bulk_g2s(tiles + s * kStageI, a.xq + tn * kTileI, kStageI, &full[s]);
+                }
+                if (++s == nst) { s = 0; parity ^= 1u; }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else {
+        for (int64_t t = t0; t < ra.ntiles; t += tstep) {
+            mbar_wait(&full[s], parity);
+            double* st = reinterpret_cast<double*>(tiles + s * kStageI);
+            double* mine[2] = {st + 2 * threadIdx.x, st + 2 * kConsumers + 2 * threadIdx.x};
+            const double2 u = ld2(mine[0]), v = ld2(mine[1]);
+            const double x[4] = {u.x, u.y, v.x, v.y};
+            double o[4];
+            unsigned bad = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double xv = x[q];
+                const int j = guess_cell(xv, a.g.r_first, a.g.inv_dr, a.g.ng);
+                const double2 tb = ys[j];
+                double x0, x1;
+                if (LIN) {
+                    const double dj = static_cast<double>(j);
+                    x0 = lin_r_at(a.lin, dj, 0, j); x1 = lin_r_at(a.lin, dj, 1, j + 1);
+                } else {
+                    const double2 e = xs[j];
+                    x0 = e.x; x1 = e.y;
+                }
+                o[q] = tb.y * (xv - x0) + tb.x;
+                const bool ok = (x0 < xv) && (xv < x1) && (o[q] == o[q]);        // NaN -> numpy's fallbacks (exact path)
+                if (!ok) bad |= 1u << q;
+            }
+            if (__builtin_expect(bad != 0u, 0)) {
+                const int64_t first = t * kTileI;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (bad & (1u << q))
+                        o[q] = interp_point_exact_value(a, first + (q >> 1) * 2 * kConsumers + 2 * threadIdx.x + (q & 1));
+            }
+            st2(mine[0], make_double2(o[0], o[1]));
+            st2(mine[1], make_double2(o[2], o[3]));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&done[s]);
+            if (++s == nst) { s = 0; parity ^= 1u; }
+        }
+    }
+    // ragged tail (< kTileI points) on the last CTA; it writes plain global stores to a range no bulk store touches
+    if (blockIdx.x == gridDim.x - 1)
+        for (int64_t i = ra.ntiles * kTileI + threadIdx.x; i < a.n; i += kTmaThreads) a.out[i] = interp_point_exact_value(a, i);
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -1379,6 +1503,35 @@ static int interp1d_impl(const double* r, int64_t ng, double dr, double r_first,
             ga.r = r; ga.comp[0] = y; ga.stride[0] = static_cast<int>(y_stride_n);          // the global view (no staging plan)
             ga.nseg = 0;
             const bool vec = xq_stride == 1 && aligned16(xq) && aligned16(out);
+            // enough whole tiles for every SM and bulk-copyable arrays: the TMA ring
+            static const bool ring_on = [] {
+                const char* e = std::getenv("TURBOPY_B200_INTERP_RING");      // tuning / A-B switch, default on
+                return !(e && e[0] == '0');
+            }();
+            InterpRingArgs ra;
+            ra.ntiles = n / kTileI;
+            ra.table_off = kSmemHeader;
+            ra.tiles_off = static_cast<uint32_t>((kSmemHeader + need + 127) & ~size_t(127));
+            const int64_t room = static_cast<int64_t>(d.smem_optin) - 1024 - ra.tiles_off;
+            static const int ring_depth = [] { const char* e = std::getenv("TURBOPY_B200_INTERP_STAGES"); return e ? std::atoi(e) : 6; }();
+            ra.nstages = static_cast<int>(std::min<int64_t>(std::min(kRingMaxStages, std::max(2, ring_depth)), room / kStageI));
+            if (ring_on && tma_enabled() && vec && ra.nstages >= 3 && ra.ntiles >= 4ll * d.sm_count) {
+                ra.a = a;
+                const size_t bytes = ra.tiles_off + static_cast<size_t>(ra.nstages) * kStageI;
+                const int blocks = static_cast<int>(std::min<int64_t>(d.sm_count, ra.ntiles));
+                auto ring = [&](auto kern) {
+                    int rc2 = set_smem(kern, bytes);
+                    if (rc2) return rc2;
+                    kern<<<blocks, kTmaThreads, bytes, s>>>(ra);
+                    count_launch();
+                    return static_cast<int>(cudaGetLastError());
+                };
+                if (lin) {
+                    ra.a.lin = LinGrid{lin->start, lin->span, lin->step, lin->n};
+                    return ring(interp_cells_ring_kernel<true>);
+                }
+                return ring(interp_cells_ring_kernel<false>);
+            }
             auto go = [&](auto kern) {
                 int rc2 = set_smem(kern, need);
                 if (rc2) return rc2;
