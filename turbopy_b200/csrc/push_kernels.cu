@@ -626,6 +626,80 @@ __global__ void __launch_bounds__(kThreads, NC == 1 ? 3 : 2) interp_kernel(const
     }
 }
 
+// Cell tables of the 1-D-y kernels below.  {y0, slope} per cell always; abscissas that are not a tp_linspace grid
+// (interp1d takes ANY increasing x: stretched grids, hand-made node lists) also get {x0, x1} per cell and a BUCKET
+// index: 2 (ng-1) uniform buckets over [x[0], x[-1]], bucket b -> the last cell whose left node lies in an earlier
+// bucket.  A point then starts at its bucket's cell and walks right over the (usually 0-2) nodes of its own bucket
+// -- no binary search, no dependence on x being uniform (the uniform-spacing guess sent every point of a
+// stretched grid to the out-of-line exact path: 19 G points/s instead of 300).  bucket_of() is monotone in x, so
+// a node in an earlier bucket is strictly left of the point whatever the rounding.
+struct CellTables {
+    double2* ys;        // {y[j], slope_j}
+    double2* xs;        // {x[j], x[j+1]}           (not LIN)
+    int* bucket;        // first cell to try        (not LIN)
+    int ncell, nbucket;
+    double inv_bw;
+};
+
+template <bool LIN>
+__device__ __forceinline__ CellTables cell_tables_at(unsigned char* base, const InterpArgs& a) {
+    CellTables t;
+    t.ncell = a.g.ng - 1;
+    t.nbucket = 2 * t.ncell;
+    t.ys = reinterpret_cast<double2*>(base);
+    t.xs = t.ys + t.ncell;
+    t.bucket = reinterpret_cast<int*>(t.xs + t.ncell);
+    t.inv_bw = a.g.inv_dr * 2.0;
+    return t;
+}
+
+__device__ __forceinline__ int bucket_of(const CellTables& t, double x, double x_first) {
+    const int b = __double2int_rz((x - x_first) * t.inv_bw);            // saturates, NaN -> 0
+    return max(0, min(b, t.nbucket - 1));
+}
+
+// Called by all threads of the CTA; the caller syncs afterwards.
+template <bool LIN>
+__device__ __forceinline__ void cell_tables_build(const CellTables& t, const InterpArgs& a, int nthreads) {
+    const double* y = a.g.comp[0];
+    const int sn = a.g.stride[0];
+    for (int j = threadIdx.x; j < t.ncell; j += nthreads) {
+        const double x0 = LIN ? lin_r(a.lin, j) : a.g.r[j], x1 = LIN ? lin_r(a.lin, j + 1) : a.g.r[j + 1];
+        const double y0 = y[static_cast<int64_t>(j) * sn], y1 = y[static_cast<int64_t>(j + 1) * sn];
+        t.ys[j] = make_double2(y0, (y1 - y0) / (x1 - x0));
+        if (!LIN) {
+            t.xs[j] = make_double2(x0, x1);
+            // buckets (gb(x[j]), gb(x[j+1])] start at cell j; the top cell takes everything up to the last bucket
+            const int b0 = j == 0 ? -1 : bucket_of(t, x0, a.g.r_first);
+            const int b1 = j == t.ncell - 1 ? t.nbucket - 1 : bucket_of(t, x1, a.g.r_first);
+            for (int b = b0 + 1; b <= b1; ++b) t.bucket[b] = j;
+        }
+    }
+}
+
+// y(x) by the per-cell table; false when x is not strictly inside the cell that was found (on a node, at the ends,
+// outside, NaN, more than kWalk nodes inside one bucket) or the value is NaN: the caller takes the exact path.
+template <bool LIN>
+__device__ __forceinline__ bool cell_value(const CellTables& t, const InterpArgs& a, double xv, double& out) {
+    double x0, x1;
+    int j;
+    if (LIN) {
+        j = guess_cell(xv, a.g.r_first, a.g.inv_dr, a.g.ng);
+        const double dj = static_cast<double>(j);
+        x0 = lin_r_at(a.lin, dj, 0, j); x1 = lin_r_at(a.lin, dj, 1, j + 1);
+    } else {
+        constexpr int kWalk = 6;
+        j = t.bucket[bucket_of(t, xv, a.g.r_first)];
+        double2 e = t.xs[j];
+#pragma unroll 1
+        for (int w = 0; w < kWalk && xv >= e.y && j < t.ncell - 1; ++w) e = t.xs[++j];
+        x0 = e.x; x1 = e.y;
+    }
+    const double2 tb = t.ys[j];
+    out = tb.y * (xv - x0) + tb.x;
+    return (x0 < xv) && (xv < x1) && (out == out);
+}
+
 // 1-D y, numpy.interp rounding (formula B), the common call (Interpolators.interpolate1D(grid.r, field)(x)):
 // every CTA builds a per-CELL table {y[j], slope_j} in shared memory (slope = (y[j+1]-y[j])/(x[j+1]-x[j]) by IEEE
 // division: numpy.interp's per-cell quantity, ng/256 divisions per thread, once per launch) and a point then costs
@@ -636,17 +710,8 @@ __global__ void __launch_bounds__(kThreads, NC == 1 ? 3 : 2) interp_kernel(const
 template <bool LIN>
 __global__ void __launch_bounds__(kThreads, 3) interp_cells_kernel(const __grid_constant__ InterpArgs a, bool vec) {
     extern __shared__ __align__(128) unsigned char smem[];
-    double2* ys = reinterpret_cast<double2*>(smem);                          // {y0, slope} per cell
-    double2* xs = reinterpret_cast<double2*>(smem) + (a.g.ng - 1);           // {x0, x1} per cell (not LIN)
-    const int ncell = a.g.ng - 1;
-    const double* y = a.g.comp[0];
-    const int sn = a.g.stride[0];
-    for (int j = threadIdx.x; j < ncell; j += kThreads) {
-        const double x0 = LIN ? lin_r(a.lin, j) : a.g.r[j], x1 = LIN ? lin_r(a.lin, j + 1) : a.g.r[j + 1];
-        const double y0 = y[static_cast<int64_t>(j) * sn], y1 = y[static_cast<int64_t>(j + 1) * sn];
-        ys[j] = make_double2(y0, (y1 - y0) / (x1 - x0));
-        if (!LIN) xs[j] = make_double2(x0, x1);
-    }
+    const CellTables tb = cell_tables_at<LIN>(smem, a);
+    cell_tables_build<LIN>(tb, a, kThreads);
     __syncthreads();
     const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * kThreads;
@@ -682,19 +747,7 @@ __global__ void __launch_bounds__(kThreads, 3) interp_cells_kernel(const __grid_
             unsigned bad = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const double xv = x[u][q];
-                const int j = guess_cell(xv, a.g.r_first, a.g.inv_dr, a.g.ng);
-                const double2 t = ys[j];
-                double x0, x1;
-                if (LIN) {
-                    const double dj = static_cast<double>(j);
-                    x0 = lin_r_at(a.lin, dj, 0, j); x1 = lin_r_at(a.lin, dj, 1, j + 1);
-                } else {
-                    const double2 e = xs[j];
-                    x0 = e.x; x1 = e.y;
-                }
-                o[q] = t.y * (xv - x0) + t.x;
-                const bool ok = (x0 < xv) && (xv < x1) && (o[q] == o[q]);        // NaN -> numpy's fallbacks (exact path)
+                const bool ok = cell_value<LIN>(tb, a, x[u][q], o[q]);          // false: numpy's special cases (exact path)
                 if (!ok && i + q < a.n) bad |= 1u << q;
             }
             double* dst = a.out + i;
@@ -759,19 +812,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) interp_cells_ring_kernel(const
             mbar_expect_tx(&full[s], kStageI);
             tma_bulk_g2s(tiles + s * kStageI, a.xq + t * kTileI, kStageI, &full[s]);
         }
-    double2* ys = reinterpret_cast<double2*>(smem + ra.table_off);           // {y0, slope} per cell
-    double2* xs = ys + (a.g.ng - 1);                                         // {x0, x1} per cell (not LIN)
-    {
-        const int ncell = a.g.ng - 1;
-        const double* y = a.g.comp[0];
-        const int sn = a.g.stride[0];
-        for (int j = threadIdx.x; j < ncell; j += kTmaThreads) {
-            const double x0 = LIN ? lin_r(a.lin, j) : a.g.r[j], x1 = LIN ? lin_r(a.lin, j + 1) : a.g.r[j + 1];
-            const double y0 = y[static_cast<int64_t>(j) * sn], y1 = y[static_cast<int64_t>(j + 1) * sn];
-            ys[j] = make_double2(y0, (y1 - y0) / (x1 - x0));
-            if (!LIN) xs[j] = make_double2(x0, x1);
-        }
-    }
+    const CellTables tb = cell_tables_at<LIN>(smem + ra.table_off, a);
+    cell_tables_build<LIN>(tb, a, kTmaThreads);
     __syncthreads();
     int s = 0;
     uint32_t parity = 0;
@@ -801,22 +843,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) interp_cells_ring_kernel(const
             double o[4];
             unsigned bad = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double xv = x[q];
-                const int j = guess_cell(xv, a.g.r_first, a.g.inv_dr, a.g.ng);
-                const double2 tb = ys[j];
-                double x0, x1;
-                if (LIN) {
-                    const double dj = static_cast<double>(j);
-                    x0 = lin_r_at(a.lin, dj, 0, j); x1 = lin_r_at(a.lin, dj, 1, j + 1);
-                } else {
-                    const double2 e = xs[j];
-                    x0 = e.x; x1 = e.y;
-                }
-                o[q] = tb.y * (xv - x0) + tb.x;
-                const bool ok = (x0 < xv) && (xv < x1) && (o[q] == o[q]);        // NaN -> numpy's fallbacks (exact path)
-                if (!ok) bad |= 1u << q;
-            }
+            for (int q = 0; q < 4; ++q)
+                if (!cell_value<LIN>(tb, a, x[q], o[q])) bad |= 1u << q;        // numpy's special cases: exact path
             if (__builtin_expect(bad != 0u, 0)) {
                 const int64_t first = t * kTileI;
 #pragma unroll
@@ -1497,11 +1525,13 @@ static int interp1d_impl(const double* r, int64_t ng, double dr, double r_first,
     }();
     if (cells_on && ncomp == 1 && formula == TP_INTERP_B && n >= 8 * ng) {
         // per-cell {y0, slope} table in shared memory (worth building when there are many more points than cells)
-        const size_t need = static_cast<size_t>(ng - 1) * (lin ? 16 : 32);
-        if (need <= static_cast<size_t>(d.smem_optin) / 3 - 1024 && (!lin || lin->n == ng)) {
-            GatherArgs& ga = a.g;
-            ga.r = r; ga.comp[0] = y; ga.stride[0] = static_cast<int>(y_stride_n);          // the global view (no staging plan)
-            ga.nseg = 0;
+        const size_t need = static_cast<size_t>(ng - 1) * (lin ? 16 : 40);       // CellTables: {y0, slope} (+ {x0, x1} + 2 buckets)
+        const bool fits3 = need <= static_cast<size_t>(d.smem_optin) / 3 - 1024;    // three CTAs per SM (register path)
+        const bool fits1 = need + 3 * kStageI + 2 * kSmemHeader <= static_cast<size_t>(d.smem_optin) - 1024;   // the ring
+        if ((fits3 || fits1) && (!lin || lin->n == ng)) {
+            InterpArgs ac = a;                            // the cell kernels' view: global arrays, no staging plan
+            ac.g.r = r; ac.g.comp[0] = y; ac.g.stride[0] = static_cast<int>(y_stride_n);
+            ac.g.nseg = 0;
             const bool vec = xq_stride == 1 && aligned16(xq) && aligned16(out);
             // enough whole tiles for every SM and bulk-copyable arrays: the TMA ring
             static const bool ring_on = [] {
@@ -1516,7 +1546,7 @@ static int interp1d_impl(const double* r, int64_t ng, double dr, double r_first,
             static const int ring_depth = [] { const char* e = std::getenv("TURBOPY_B200_INTERP_STAGES"); return e ? std::atoi(e) : 6; }();
             ra.nstages = static_cast<int>(std::min<int64_t>(std::min(kRingMaxStages, std::max(2, ring_depth)), room / kStageI));
             if (ring_on && tma_enabled() && vec && ra.nstages >= 3 && ra.ntiles >= 4ll * d.sm_count) {
-                ra.a = a;
+                ra.a = ac;
                 const size_t bytes = ra.tiles_off + static_cast<size_t>(ra.nstages) * kStageI;
                 const int blocks = static_cast<int>(std::min<int64_t>(d.sm_count, ra.ntiles));
                 auto ring = [&](auto kern) {
@@ -1536,15 +1566,17 @@ static int interp1d_impl(const double* r, int64_t ng, double dr, double r_first,
                 int rc2 = set_smem(kern, need);
                 if (rc2) return rc2;
                 const int blocks = grid_blocks(reinterpret_cast<const void*>(kern), need, (n + 3) / 4);
-                kern<<<blocks, kThreads, need, s>>>(a, vec);
+                kern<<<blocks, kThreads, need, s>>>(ac, vec);
                 count_launch();
                 return static_cast<int>(cudaGetLastError());
             };
-            if (lin) {
-                a.lin = LinGrid{lin->start, lin->span, lin->step, lin->n};
-                return go(interp_cells_kernel<true>);
+            if (fits3) {                                  // (else the table only fits the one-CTA-per-SM ring)
+                if (lin) {
+                    ac.lin = LinGrid{lin->start, lin->span, lin->step, lin->n};
+                    return go(interp_cells_kernel<true>);
+                }
+                return go(interp_cells_kernel<false>);
             }
-            return go(interp_cells_kernel<false>);
         }
     }
     if (lin) {
