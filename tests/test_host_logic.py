@@ -177,3 +177,57 @@ def test_additive_apis_validate_before_touching_the_device():
         k = _lib.PushConsts(1.0, 1.0, 1.0, 1.0)
         assert L.tp_boris_push_steps_f64(C.byref(p), C.byref(k), None, 0, 0, 0, None, 0, 0, 0, 3, None) == _lib.TP_E_NODEVICE
         assert L.tp_permute_f64(None, 1, 0, None, None, None) == _lib.TP_E_NODEVICE
+
+
+def test_formula_a_window_margin_is_sufficient():
+    """csrc/gather_math.cuh: window_margin().  Formula A's fast path accepts a particle when it is at least `margin`
+    away from both nodes of its cell and claims that r[j-1] and r[j+2] are then outside (x-dr, x+dr) as the
+    reference evaluates that window (core.py:728, `r0 - dr < r` / `r < r0 + dr` with the sums rounded once).  Here
+    the kernel's margin arithmetic is replayed in numpy on linspace, offset and jittered grids, and the claim is
+    checked for points placed right at the margin (the adversarial spot) and at random."""
+    rng = np.random.default_rng(11)
+
+    def margin_of(r, dr):
+        w = r[1:] - r[:-1]
+        if not (w > 0).all():
+            return 0.0
+        wmin = w.min()
+        wlb = wmin - wmin * 2.0 ** -52
+        gap = max(dr - wlb, 0.0)
+        eps = (max(abs(r[0]), abs(r[-1])) + dr) * 2.0 ** -51
+        m = 2.0 * (gap + eps)
+        return m if (m < dr * 0.015625 and m > 0.0) else 0.0
+
+    checked = 0
+    for trial in range(60):
+        ng = int(rng.integers(5, 3000))
+        lo = float(rng.choice([0.0, -3.7, 1e-3, 12345.678, -1e6]))
+        span = float(rng.choice([1.0, 15.0, 1e-6, 3e4]))
+        r = lo + span * np.linspace(0.0, 1.0, ng)
+        dr = span / (ng - 1)
+        if trial % 3 == 1:
+            r[1:-1] += 1e-3 * dr * rng.uniform(-1, 1, ng - 2)
+        if trial % 3 == 2:
+            r[1:-1] += 7e-3 * dr * rng.uniform(-1, 1, ng - 2)
+        qa = margin_of(r, dr)
+        resolved = dr > 2.0 ** 20 * np.spacing(max(abs(r[0]), abs(r[-1])))      # cells far wider than an ulp of r
+        if trial % 3 != 2 and resolved:
+            assert qa > 0.0                       # turboPy's own grids (and slightly perturbed ones) get a margin
+        if qa == 0.0:
+            continue
+        j = rng.integers(0, ng - 1, 20000)
+        x0, x1 = r[j], r[j + 1]
+        # at the margin from the left node, from the right node (a few ulps either side), and uniformly inside
+        t = rng.integers(0, 3, len(j))
+        k = rng.integers(-3, 4, len(j))
+        x = np.where(t == 0, x0 + qa, np.where(t == 1, x1 - qa, x0 + (x1 - x0) * rng.uniform(0, 1, len(j))))
+        x = x + k * np.spacing(np.abs(x)) * (t != 2)
+        accepted = (x0 < x) & (x < x1) & ((x - x0) >= qa) & ((x1 - x) >= qa)
+        lo_edge, hi_edge = x - dr, x + dr
+        xm = np.where(j > 0, r[np.maximum(j - 1, 0)], -np.inf)
+        xp = np.where(j < ng - 2, r[np.minimum(j + 2, ng - 1)], np.inf)
+        inside = (lo_edge < xm) | (xp < hi_edge)
+        assert not (accepted & inside).any()
+        assert accepted.mean() > 0.3               # and the margin is not so wide that nothing passes
+        checked += int(accepted.sum())
+    assert checked > 100_000
