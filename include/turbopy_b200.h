@@ -235,9 +235,11 @@ int tp_fd_dia_const_apply_f64(const double* coef, const int* offsets, int ndiag,
  * prefix scans, I1 = cumsum(r*s*dr), I2 = cumsum(I1*dr/r with the axis fix),
  * out = I2 - I2[n-1].  mean_dr = np.mean(Grid.cell_widths) formed by the caller
  * (:49).  numpy's cumsum is sequential, a parallel scan is not: results agree to
- * rounding, not bit for bit.  scratch: tp_poisson_scratch_doubles(n) doubles. */
+ * rounding, not bit for bit; out[n-1] is exactly 0.  Two passes over the inputs (round 2): the tile sums of the
+ * second scan are formed from per-tile aggregates of the first pass (csrc/scan_kernels.cu).
+ * scratch: tp_poisson_scratch_doubles(n) doubles. */
 /* The three r-dependent kernels on a tp_linspace grid: same results bit for bit, r (and cell_widths) never read:
- * upwind_left 24 -> 16 B/point, del2_radial 24 -> 16 B/point, the Poisson passes 56 -> 32 B/point. */
+ * upwind_left 24 -> 16 B/point, del2_radial 24 -> 16 B/point, the Poisson passes 40 -> 24 B/point. */
 int tp_fd_upwind_left_lin_f64(const double* y, const tp_linspace* grid, double* d, int64_t n, tp_stream_t stream);
 int tp_fd_del2_radial_apply_lin_f64(const double* f, const tp_linspace* grid, double* out, int64_t n,
                                     double g1, double g2, tp_stream_t stream);

@@ -49,6 +49,7 @@ def test_poisson_ragged_sizes(n):
     phi = tool.solve(torch.from_numpy(src).cuda()).cpu().numpy()
     ref = opoisson.solve(src, grid.r, grid.cell_widths)
     assert np.abs(phi - ref).max() <= TOL * max(np.abs(ref).max(), 1e-300) * 10
+    assert phi[-1] == 0.0                                   # `last` is formed by the instructions that form out[n-1]
 
 
 @pytest.mark.parametrize("n", [1000, 16_384, 100_003])
@@ -75,5 +76,6 @@ def test_poisson_unaligned_pointers_match_aligned(n, shift):
 
     aligned, shifted = run(0), run(shift)
     assert np.array_equal(aligned, shifted)
+    assert aligned[-1] == 0.0
     ref = opoisson.solve(src, grid.r, grid.cell_widths)
     assert np.abs(aligned - ref).max() <= TOL * np.abs(ref).max() * 10

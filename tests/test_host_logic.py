@@ -171,7 +171,7 @@ def test_additive_apis_validate_before_touching_the_device():
     assert L.tp_sort_scratch_bytes(-1, 10, 0) == -1 and L.tp_sort_scratch_bytes(10, 0, 0) == -1
     assert L.tp_sort_scratch_bytes(1 << 33, 10, 0) == -1 and L.tp_sort_scratch_bytes(10, 10, 41) == -1
     assert L.tp_sort_scratch_bytes(1000, 1 << 20, 0) > 2 * 8 * 1000        # two permutations + one scratch plane + counts
-    assert L.tp_poisson_scratch_doubles(2048 * 3 + 1) == 2 * 4 + 8
+    assert L.tp_poisson_scratch_doubles(2048 * 3 + 1) == 4 * 4 + 8
     if not torch.cuda.is_available():
         p = _lib.Particles(0, 1, 1, 0, 1, 1, 0)
         k = _lib.PushConsts(1.0, 1.0, 1.0, 1.0)

@@ -204,8 +204,8 @@ def main():
             add(f"fd {name}() @ f", n, bpp, timed(lambda: D @ y, it),
                 "stored diagonals" if name == "radial_curl" else "constant diagonals in kernel args")
         ps = tp.PoissonSolver1DRadial(ow, {"type": "PoissonSolver1DRadial"})
-        add("PoissonSolver1DRadial.solve (5 launches)", n, 32 if lin else 56, timed(lambda: ps.solve(y), it),
-            ("32" if lin else "56") + " B/pt over the reduce-then-scan passes; 16 B/pt algorithmic; " + lin_note)
+        add("PoissonSolver1DRadial.solve (3 launches)", n, 24 if lin else 40, timed(lambda: ps.solve(y), it),
+            ("24" if lin else "40") + " B/pt over the two reduce-then-scan passes; 16 B/pt algorithmic; " + lin_note)
         del y, fdt, D, ow, ps
         tp.GridOnDevice._cache.clear()
         torch.cuda.empty_cache()
