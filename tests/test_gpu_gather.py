@@ -456,3 +456,45 @@ def test_interpolate1d_ring_kernel_vs_numpy(tp, gridkind, ng):
     xq[12345] = x[-1] + 1e-9
     with pytest.raises(ValueError, match="above the interpolation range"):
         f(torch.from_numpy(xq).cuda())
+
+
+@pytest.mark.parametrize("gridkind", ["linspace", "stretched"])
+@pytest.mark.parametrize("ng,k", [(30, 2), (1025, 6), (1025, 7), (2049, 3), (4097, 6)])
+def test_interpolate1d_nd_cell_planes_vs_scipy(tp, gridkind, ng, k):
+    """(k, ng) y with many more points than cells: interp_cells_nc_kernel ({y0, slope} planes in shared memory, up to
+    six components per pass, so k = 7 takes two passes; (4097, 6) does not fit and stays on interp_kernel).  Points on
+    nodes (searchsorted's LEFT cell), at both ends, one ulp off nodes, NaN abscissas, a ragged tail and an unaligned
+    query view; bit-identical to scipy's interp1d and to the oracle's restatement of _call_linear."""
+    from scipy.interpolate import interp1d
+    rng = np.random.default_rng(ng * 10 + k)
+    grid = make_grid(ng, -0.5, 1.5)
+    x = grid.r.copy()
+    if gridkind == "stretched":
+        x = -0.5 + 2.0 * np.linspace(0.0, 1.0, ng) ** 1.7
+    y = np.stack([np.sin((c + 2.0) * x) * 10.0 ** (c - 2) + 0.1 * c * x for c in range(k)])
+    n = 300_003
+    xq = rng.uniform(x[0], x[-1], n)
+    idx = rng.integers(0, n, 5_000)
+    node = x[rng.integers(0, ng, len(idx))]
+    xq[idx] = np.where(rng.random(len(idx)) < 0.5, node, np.clip(np.nextafter(node, rng.choice([-np.inf, np.inf], len(idx))),
+                                                                  x[0], x[-1]))
+    xq[[0, 1, n - 1, n - 2]] = [x[0], x[-1], x[0], x[-1]]
+    nan_at = rng.integers(0, n, 20)
+    xq[nan_at] = np.nan
+    tool = tp.Interpolators(make_owner(grid=grid), {"type": "Interpolators"})
+    f = tool.interpolate1D(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+    assert (f._lin is not None) == (gridkind == "linspace")
+    got = f(torch.from_numpy(xq).cuda()).cpu().numpy()
+    assert got.shape == (k, n)
+    with np.errstate(all="ignore"):
+        ref = interp1d(x, y)(xq)
+        want, _ = ogather.interp_c(xq, x, y)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.isnan(got[:, nan_at]).all()
+    assert_bits_equal(np.nan_to_num(got, nan=-7.0), np.nan_to_num(ref, nan=-7.0), "vs scipy interp1d")
+    assert_bits_equal(np.nan_to_num(got, nan=-7.0), np.nan_to_num(want, nan=-7.0), "vs the oracle")
+    xq_dev = torch.empty(n + 1, dtype=torch.float64, device="cuda")[1:]          # 8-byte aligned only: scalar accesses
+    xq_dev.copy_(torch.from_numpy(xq))
+    assert_bits_equal(np.nan_to_num(f(xq_dev).cpu().numpy(), nan=-7.0), np.nan_to_num(ref, nan=-7.0), "unaligned queries")
+    xq[777] = x[0] - 1e-9
+    with pytest.raises(ValueError, match="below the interpolation range"):
+        f(torch.from_numpy(xq).cuda())

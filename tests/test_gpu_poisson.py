@@ -79,3 +79,22 @@ def test_poisson_unaligned_pointers_match_aligned(n, shift):
     assert aligned[-1] == 0.0
     ref = opoisson.solve(src, grid.r, grid.cell_widths)
     assert np.abs(aligned - ref).max() <= TOL * np.abs(ref).max() * 10
+
+
+@pytest.mark.parametrize("n,stretched", [(100_003, False), (100_003, True), (1_000_000, False), (16_385, True)])
+def test_poisson_interior_tiles_match_the_generic_tile_path(n, stretched, monkeypatch):
+    """Tiles strictly inside (0, n-1) run without the per-element index tests (csrc/scan_kernels.cu: IN); the
+    arithmetic is the same, so the bits are: TURBOPY_B200_SCAN_INTERIOR=0 sends every tile down the generic path."""
+    import turbopy_b200 as tp
+    grid = make_grid(n, 0.0, 1.5)
+    if stretched:
+        grid.r = grid.r ** 1.25
+        grid.cell_widths = grid.r[1:] - grid.r[:-1]
+    src = torch.from_numpy(np.random.default_rng(n).normal(size=n)).cuda()
+    tool = tp.PoissonSolver1DRadial(make_owner(grid=grid), {"type": "PoissonSolver1DRadial"})
+    fast = tool.solve(src).cpu().numpy()
+    monkeypatch.setenv("TURBOPY_B200_SCAN_INTERIOR", "0")
+    generic = tool.solve(src).cpu().numpy()
+    assert np.array_equal(fast.view(np.uint64), generic.view(np.uint64))
+    ref = opoisson.solve(src.cpu().numpy(), grid.r, grid.cell_widths)
+    assert np.abs(fast - ref).max() <= TOL * np.abs(ref).max() * 10

@@ -677,11 +677,9 @@ __device__ __forceinline__ void cell_tables_build(const CellTables& t, const Int
     }
 }
 
-// y(x) by the per-cell table; false when x is not strictly inside the cell that was found (on a node, at the ends,
-// outside, NaN, more than kWalk nodes inside one bucket) or the value is NaN: the caller takes the exact path.
+// The cell to try for x and its two abscissas: the uniform-spacing guess on a tp_linspace grid, the bucket walk otherwise.
 template <bool LIN>
-__device__ __forceinline__ bool cell_value(const CellTables& t, const InterpArgs& a, double xv, double& out) {
-    double x0, x1;
+__device__ __forceinline__ int cell_find(const CellTables& t, const InterpArgs& a, double xv, double& x0, double& x1) {
     int j;
     if (LIN) {
         j = guess_cell(xv, a.g.r_first, a.g.inv_dr, a.g.ng);
@@ -695,6 +693,15 @@ __device__ __forceinline__ bool cell_value(const CellTables& t, const InterpArgs
         for (int w = 0; w < kWalk && xv >= e.y && j < t.ncell - 1; ++w) e = t.xs[++j];
         x0 = e.x; x1 = e.y;
     }
+    return j;
+}
+
+// y(x) by the per-cell table; false when x is not strictly inside the cell that was found (on a node, at the ends,
+// outside, NaN, more than kWalk nodes inside one bucket) or the value is NaN: the caller takes the exact path.
+template <bool LIN>
+__device__ __forceinline__ bool cell_value(const CellTables& t, const InterpArgs& a, double xv, double& out) {
+    double x0, x1;
+    const int j = cell_find<LIN>(t, a, xv, x0, x1);
     const double2 tb = t.ys[j];
     out = tb.y * (xv - x0) + tb.x;
     return (x0 < xv) && (xv < x1) && (out == out);
@@ -762,6 +769,104 @@ __global__ void __launch_bounds__(kThreads, 3) interp_cells_kernel(const __grid_
             if (__builtin_expect(bad != 0u, 0))              // recovery overwrites the point's output (reads the global arrays)
                 for (int q = 0; q < 4; ++q)
                     if (bad & (1u << q)) interp_point_exact<TP_INTERP_B, false>(a, smem, i + q, 0);
+        }
+    }
+}
+
+// N-D y, scipy interp1d._call_linear rounding (formula C, scipy 1.18: y_new = ((x - x_lo)/(x_hi - x_lo)) * y_hi +
+// ((x_hi - x)/(x_hi - x_lo)) * y_lo -- two weights per POINT, shared by the components, so there is no per-cell slope
+// to tabulate as for numpy.interp).  What can be tabulated is the node PAIR (second half): up to six
+// components per pass get {y[j], y[j+1]} planes in shared memory (plane c at ys + c * ncell), so that a point reads one
+// 16-byte-aligned 128-bit entry per component at the same cell index instead of two 64-bit node values (half the
+// shared-memory instructions of interp_kernel<C, staged, 6>; the bytes are the same).  One 512-thread CTA per SM (the
+// table of a 1025-node grid with six components is 96 KB), four consecutive points per thread, 128-bit loads of x and
+// stores per component; the two quotients go through the guarded fast path like everywhere else.  Points that are
+// not strictly inside the cell that was found (on a node -- searchsorted's left cell --, at the ends, outside, NaN)
+// take interp_point_exact<C>, which writes all components of the pass itself.
+constexpr int kCellsNcThreads = 512;
+
+template <bool LIN>
+__global__ void __launch_bounds__(kCellsNcThreads, 1) interp_cells_nc_kernel(const __grid_constant__ InterpArgs a, bool vec) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    CellTables tb;
+    tb.ncell = a.g.ng - 1;
+    tb.nbucket = 2 * tb.ncell;
+    tb.inv_bw = a.g.inv_dr * 2.0;
+    const int ncmax = min(a.ncomp, 6);
+    tb.ys = reinterpret_cast<double2*>(smem);
+    tb.xs = tb.ys + static_cast<size_t>(ncmax) * tb.ncell;
+    tb.bucket = reinterpret_cast<int*>(tb.xs + tb.ncell);
+    if (!LIN) {
+        for (int j = threadIdx.x; j < tb.ncell; j += kCellsNcThreads) {
+            const double x0 = a.g.r[j], x1 = a.g.r[j + 1];
+            tb.xs[j] = make_double2(x0, x1);
+            const int b0 = j == 0 ? -1 : bucket_of(tb, x0, a.g.r_first);
+            const int b1 = j == tb.ncell - 1 ? tb.nbucket - 1 : bucket_of(tb, x1, a.g.r_first);
+            for (int b = b0 + 1; b <= b1; ++b) tb.bucket[b] = j;
+        }
+    }
+    const int64_t gtid = static_cast<int64_t>(blockIdx.x) * kCellsNcThreads + threadIdx.x;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * kCellsNcThreads;
+    const int64_t nquads = (a.n + 3) >> 2;
+    const int sn = a.g.stride[0];
+    const int64_t sc = a.g.stride[1];
+    for (int c0 = 0; c0 < a.ncomp; c0 += 6) {
+        const int nc = min(6, a.ncomp - c0);
+        __syncthreads();                                     // the previous pass has finished reading the planes
+        for (int idx = threadIdx.x; idx < nc * tb.ncell; idx += kCellsNcThreads) {
+            const int c = idx / tb.ncell, j = idx - c * tb.ncell;
+            const double* y = a.g.comp[0] + static_cast<int64_t>(c0 + c) * sc;
+            const double y0 = y[static_cast<int64_t>(j) * sn], y1 = y[static_cast<int64_t>(j + 1) * sn];
+            tb.ys[idx] = make_double2(y0, y1);
+        }
+        __syncthreads();
+        for (int64_t qd = gtid; qd < nquads; qd += gstride) {
+            const int64_t i = qd * 4;
+            const bool full = vec && i + 4 <= a.n;
+            double x[4];
+            if (full) {
+                const double2 u = ld2(a.xq + i), v = ld2(a.xq + i + 2);
+                x[0] = u.x; x[1] = u.y; x[2] = v.x; x[3] = v.y;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) x[q] = i + q < a.n ? a.xq[(i + q) * a.xq_stride] : 0.0;
+            }
+            double o[6][4];
+            unsigned bad = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double x0, x1;
+                const int j = cell_find<LIN>(tb, a, x[q], x0, x1);
+                Guard gd;
+                const Recip<true> rw = make_recip<true>(x1 - x0, gd);
+                const double w_hi = quot<true>(x[q] - x0, rw, gd), w_lo = quot<true>(x1 - x[q], rw, gd);
+                bool ok = (x0 < x[q]) && (x[q] < x1) && guard_ok(gd);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    if (c < nc) {
+                        const double2 e = tb.ys[c * tb.ncell + j];           // {y_lo, y_hi}
+                        o[c][q] = w_hi * e.y + w_lo * e.x;
+                        ok = ok && (o[c][q] == o[c][q]);
+                    }
+                }
+                if (!ok && i + q < a.n) bad |= 1u << q;
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                if (c >= nc) continue;
+                double* dst = a.out + static_cast<int64_t>(c0 + c) * a.out_stride_c + i;
+                if (full) {
+                    st2(dst, make_double2(o[c][0], o[c][1]));
+                    st2(dst + 2, make_double2(o[c][2], o[c][3]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (i + q < a.n) dst[q] = o[c][q];
+                }
+            }
+            if (__builtin_expect(bad != 0u, 0))              // recovery overwrites the point's outputs (reads the global arrays)
+                for (int q = 0; q < 4; ++q)
+                    if (bad & (1u << q)) interp_point_exact<TP_INTERP_C, false>(a, smem, i + q, c0);
         }
     }
 }
@@ -1577,6 +1682,31 @@ static int interp1d_impl(const double* r, int64_t ng, double dr, double r_first,
                 }
                 return go(interp_cells_kernel<false>);
             }
+        }
+    }
+    if (cells_on && formula == TP_INTERP_C && n >= 8 * ng && (!lin || lin->n == ng)) {
+        // {y[j], y[j+1]} planes for up to six components per pass (+ {x0, x1} and the bucket index when x is not a linspace)
+        const int ncmax = std::min(ncomp, 6);
+        const size_t need = static_cast<size_t>(ng - 1) * (16 * ncmax + (lin ? 0 : 24));
+        if (need <= static_cast<size_t>(d.smem_optin) - 1024) {
+            InterpArgs ac = a;                                // global arrays, no staging plan
+            ac.g.r = r; ac.g.comp[0] = y; ac.g.stride[0] = static_cast<int>(y_stride_n);
+            ac.g.nseg = 0;
+            const bool vec = xq_stride == 1 && aligned16(xq) && aligned16(out) && out_stride_c % 2 == 0;
+            auto go = [&](auto kern) {
+                int rc2 = set_smem(kern, need);
+                if (rc2) return rc2;
+                const int64_t want = ((n + 3) / 4 + kCellsNcThreads - 1) / kCellsNcThreads;
+                const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(d.sm_count, want)));
+                kern<<<blocks, kCellsNcThreads, need, s>>>(ac, vec);
+                count_launch();
+                return static_cast<int>(cudaGetLastError());
+            };
+            if (lin) {
+                ac.lin = LinGrid{lin->start, lin->span, lin->step, lin->n};
+                return go(interp_cells_nc_kernel<true>);
+            }
+            return go(interp_cells_nc_kernel<false>);
         }
     }
     if (lin) {
