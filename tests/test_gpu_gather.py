@@ -459,10 +459,11 @@ def test_interpolate1d_ring_kernel_vs_numpy(tp, gridkind, ng):
 
 
 @pytest.mark.parametrize("gridkind", ["linspace", "stretched"])
-@pytest.mark.parametrize("ng,k", [(30, 2), (1025, 6), (1025, 7), (2049, 3), (4097, 6)])
+@pytest.mark.parametrize("ng,k", [(30, 2), (1025, 6), (1025, 7), (2049, 3), (4097, 6), (5001, 2), (9001, 3)])
 def test_interpolate1d_nd_cell_planes_vs_scipy(tp, gridkind, ng, k):
-    """(k, ng) y with many more points than cells: interp_cells_nc_kernel ({y0, slope} planes in shared memory, up to
-    six components per pass, so k = 7 takes two passes; (4097, 6) does not fit and stays on interp_kernel).  Points on
+    """(k, ng) y with many more points than cells: interp_cells_nc_kernel ({y[j], y[j+1]} planes in shared memory, as
+    many components per pass as fit, at most six: k = 7 takes two passes, (4097, 6) two on a linspace grid and three on
+    a stretched one, (5001, 2) stretched one component per pass; (9001, 3) stays on interp_kernel).  Points on
     nodes (searchsorted's LEFT cell), at both ends, one ulp off nodes, NaN abscissas, a ragged tail and an unaligned
     query view; bit-identical to scipy's interp1d and to the oracle's restatement of _call_linear."""
     from scipy.interpolate import interp1d

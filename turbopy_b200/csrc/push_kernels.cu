@@ -534,6 +534,7 @@ struct InterpArgs {
     double* out; int64_t out_stride_c;
     int ncomp;
     LinGrid lin;                // LIN kernels: the node coordinates as linspace parameters
+    int ncpass;                 // interp_cells_nc_kernel: components per pass (as many planes as fit shared memory, <= 6)
 };
 
 // The view of six consecutive components c0 .. c0+5 of the y block.
@@ -792,7 +793,7 @@ __global__ void __launch_bounds__(kCellsNcThreads, 1) interp_cells_nc_kernel(con
     tb.ncell = a.g.ng - 1;
     tb.nbucket = 2 * tb.ncell;
     tb.inv_bw = a.g.inv_dr * 2.0;
-    const int ncmax = min(a.ncomp, 6);
+    const int ncmax = a.ncpass;
     tb.ys = reinterpret_cast<double2*>(smem);
     tb.xs = tb.ys + static_cast<size_t>(ncmax) * tb.ncell;
     tb.bucket = reinterpret_cast<int*>(tb.xs + tb.ncell);
@@ -810,8 +811,8 @@ __global__ void __launch_bounds__(kCellsNcThreads, 1) interp_cells_nc_kernel(con
     const int64_t nquads = (a.n + 3) >> 2;
     const int sn = a.g.stride[0];
     const int64_t sc = a.g.stride[1];
-    for (int c0 = 0; c0 < a.ncomp; c0 += 6) {
-        const int nc = min(6, a.ncomp - c0);
+    for (int c0 = 0; c0 < a.ncomp; c0 += ncmax) {
+        const int nc = min(ncmax, a.ncomp - c0);
         __syncthreads();                                     // the previous pass has finished reading the planes
         for (int idx = threadIdx.x; idx < nc * tb.ncell; idx += kCellsNcThreads) {
             const int c = idx / tb.ncell, j = idx - c * tb.ncell;
@@ -1685,13 +1686,20 @@ static int interp1d_impl(const double* r, int64_t ng, double dr, double r_first,
         }
     }
     if (cells_on && formula == TP_INTERP_C && n >= 8 * ng && (!lin || lin->n == ng)) {
-        // {y[j], y[j+1]} planes for up to six components per pass (+ {x0, x1} and the bucket index when x is not a linspace)
-        const int ncmax = std::min(ncomp, 6);
-        const size_t need = static_cast<size_t>(ng - 1) * (16 * ncmax + (lin ? 0 : 24));
-        if (need <= static_cast<size_t>(d.smem_optin) - 1024) {
+        // {y[j], y[j+1]} planes for as many components per pass as fit (at most six; + {x0, x1} and the bucket index
+        // when x is not a linspace).  Fewer planes than components means more passes over the points (8 B/point
+        // each): still worth it on a linspace grid while a pass carries >= 2 components, and always on other
+        // abscissas, where the uniform-spacing guess of interp_kernel sends every point to the exact path.
+        const size_t room = static_cast<size_t>(d.smem_optin) - 1024;
+        const size_t fixed = static_cast<size_t>(ng - 1) * (lin ? 0 : 24);
+        const int fit = room > fixed ? static_cast<int>(std::min<size_t>(6, (room - fixed) / (static_cast<size_t>(ng - 1) * 16))) : 0;
+        const int ncpass = std::min(ncomp, fit);
+        const size_t need = fixed + static_cast<size_t>(ng - 1) * 16 * ncpass;
+        if (ncpass >= 1 && (ncpass == ncomp || ncpass >= 2 || !lin)) {
             InterpArgs ac = a;                                // global arrays, no staging plan
             ac.g.r = r; ac.g.comp[0] = y; ac.g.stride[0] = static_cast<int>(y_stride_n);
             ac.g.nseg = 0;
+            ac.ncpass = ncpass;
             const bool vec = xq_stride == 1 && aligned16(xq) && aligned16(out) && out_stride_c % 2 == 0;
             auto go = [&](auto kern) {
                 int rc2 = set_smem(kern, need);
