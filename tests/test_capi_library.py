@@ -64,6 +64,33 @@ def test_sass_is_sm100_with_tma(lib):
     assert "DFMA" in out                      # fp64 pipe, not tensor cores
 
 
+def test_streaming_kernels_fit_the_ctas_they_launch_per_sm(lib):
+    """The register-path streaming kernels launch a fixed number of 256-thread CTAs per SM (csrc/fd_kernels.cu table;
+    the Poisson passes take theirs from the occupancy query but were tuned at four): that many must be RESIDENT, or
+    the surplus runs as a ragged second wave.  fd_centered_kernel once grew from 48 to 52 registers through an
+    unrelated header change and dropped from 98 % to 72 % of the copy peak unnoticed -- this pins the budgets."""
+    import re
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-res-usage", lib.LIB_PATH], capture_output=True, text=True).stdout
+    regs = dict(re.findall(r"Function (\S+?):\s*\n\s*REG:(\d+)", out))
+    assert regs, "cuobjdump -res-usage printed no functions"
+    resident = {"fd_centered_kernel": 5, "fd_upwind_kernel": 4, "fd_del2_radial_kernel": 4, "fd_dia_kernel": 5,
+                "fd_dia_const_kernel": 4, "fd_dia_const_t_kernel": 4, "moments_partial_kernel": 4,
+                "poisson_sums_kernel": 4, "poisson_apply_kernel": 4}
+    seen = set()
+    for name, r in regs.items():
+        for key, ctas in resident.items():
+            if re.search(rf"\d+{key}(I|E)", name):                    # mangled: <len><name> then template args or params
+                seen.add(key)
+                alloc = -(-int(r) // 8) * 8                            # registers are allocated in units of 8 per thread
+                assert alloc * 256 * ctas <= 65536, f"{name}: {r} registers, {ctas} CTAs of 256 threads do not fit one SM"
+    assert seen == set(resident), f"kernels not found in the library: {set(resident) - seen}"
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():

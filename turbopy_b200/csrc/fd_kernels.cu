@@ -91,7 +91,11 @@ __device__ __forceinline__ double div_const(double a, const ConstDiv& c) {
 }
 
 // d[i] = (y[i+1] - y[i-1]) / two_dr for 0 < i < n-1; d[0] = d[n-1] = 0.
-__global__ void __launch_bounds__(kFdThreads) fd_centered_kernel(const double* __restrict__ y,
+// Five CTAs per SM are launched (table above), so five must be RESIDENT: the bound caps the kernel at 48 registers.
+// Without it a later change to the Guard helpers took the kernel from 48 to 52 registers, four CTAs fitted, the fifth
+// ran as a ragged second wave and the stencil fell from 98 % to 72 % of the copy peak (256 Mi points: 0.66 -> 0.90 ms;
+// found in round 2's final kernel table, tools/micro/fd_centered_probe.py).
+__global__ void __launch_bounds__(kFdThreads, 5) fd_centered_kernel(const double* __restrict__ y,
                                                                  double* __restrict__ d, int64_t n,
                                                                  ConstDiv two_dr, bool vec) {
     TP_QUAD_LOOP(n) {
