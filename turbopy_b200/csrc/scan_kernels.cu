@@ -51,7 +51,7 @@ struct PoissonArgs {
     bool vec;                   // r, s, out 32-byte aligned: 256-bit accesses
     bool tvec;                  // the per-tile arrays are 32-byte aligned (K2's 256-bit accesses)
     bool interior;              // interior tiles take the test-free path (A-B switch TURBOPY_B200_SCAN_INTERIOR=0)
-    int pf_dist;                // K1 / K3: L2 bulk prefetch of the tile this many iterations ahead (0 = off, the default)
+    int pf_dist;                // K1 / K3: L2 bulk prefetch of the tile this many iterations ahead (0 = off)
     bool lin;                   // r == nullptr: node coordinates rebuilt from the linspace parameters below
     LinGrid lg;
 };
@@ -174,10 +174,11 @@ __device__ __forceinline__ void tiles_store8(const PoissonArgs& p, double* dst, 
     }
 }
 
-// K1 / K3 tuning knob, OFF by default (TURBOPY_B200_SCAN_PREFETCH=d): the tile this CTA reads d iterations from
-// now goes to L2 with one bulk prefetch per array.  Measured at 256 Mi points: nothing on a linspace grid (the
-// passes are not waiting on DRAM there: 1.84 vs 1.86 ms) and a loss when r is read (d = 1 / 2 / 3: 1.92 / 2.16 /
-// 2.58 ms against 1.85 ms without -- four CTAs per SM already keep HBM at 89 % and the prefetches only disturb it).
+// K1 / K3: the tile this CTA reads d iterations from now goes to L2 with one bulk prefetch per array
+// (TURBOPY_B200_SCAN_PREFETCH=d).  Measured at 256 Mi points on the final kernels: on a linspace grid, where the
+// passes wait on their own loads (long_scoreboard on top), d = 0 / 1 / 2: 1.65 / 1.60 / 1.62 ms; when r is read the
+// four CTAs per SM already keep HBM at 89 % and the prefetches only disturb it: 1.85 / 1.91 / 2.14 ms (d = 3: 2.58).
+// Default: d = 1 on linspace grids, off otherwise.
 __device__ __forceinline__ void prefetch_tile_inputs(const PoissonArgs& p, int64_t t) {
     if (threadIdx.x != 0 || p.pf_dist == 0 || !p.vec) return;
     const int64_t tn = t + static_cast<int64_t>(p.pf_dist) * gridDim.x;
@@ -412,8 +413,8 @@ static int poisson_solve(const double* sources, const double* r, const tp_linspa
     p.tile2 = scratch + 3 * ts;
     p.scalars = scratch + 4 * ts;
     p.tvec = (reinterpret_cast<uintptr_t>(scratch) & 31) == 0;
-    static const int pf_dist = [] { const char* e = std::getenv("TURBOPY_B200_SCAN_PREFETCH"); return e ? std::max(0, std::atoi(e)) : 0; }();
-    p.pf_dist = pf_dist;
+    static const int pf_dist = [] { const char* e = std::getenv("TURBOPY_B200_SCAN_PREFETCH"); return e ? std::max(0, std::atoi(e)) : -1; }();
+    p.pf_dist = pf_dist >= 0 ? pf_dist : (p.lin ? 1 : 0);      // default: one tile ahead on linspace grids only (measured, see prefetch_tile_inputs)
     const char* in_env = std::getenv("TURBOPY_B200_SCAN_INTERIOR");       // read per call: tests compare both paths
     p.interior = !(in_env && in_env[0] == '0');
     p.vec = ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(sources) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
