@@ -50,6 +50,15 @@ def kind():
     return "staged" if os.path.abspath(REFERENCE) == os.path.abspath(STAGED) else "source"
 
 
+def tests_dir():
+    """The reference's own ``tests/`` directory (conftest, test modules, fixtures), or None: ``<reference>/tests``
+    in the build container, ``oracle/_ref/tests`` on the GPU box (staged by oracle/stage_reference.py)."""
+    if REFERENCE is None:
+        return None
+    d = os.path.join(REFERENCE, "tests")
+    return d if os.path.isfile(os.path.join(d, "test_computetools.py")) else None
+
+
 def paths():
     """sys.path entries (shims first) a subprocess needs to import the reference."""
     return [SHIMS, REFERENCE]

@@ -9,6 +9,9 @@ dist-info (tried; recorded in DESIGN.md section 3).  The recipe is therefore a p
 
 * ``turbopy/*.py``                                  (the four modules + ``__init__`` / ``__version__``),
 * ``tests/fixtures/particle_in_field/``             (the pif app, its TOML input and its golden CSVs),
+* ``tests/``                                        (the reference's OWN test-suite, conftest and fixtures, so that
+                                                     ``tests/test_gpu_reference_suite.py`` can run it on the GPU box
+                                                     with the B200 tools substituted for the stock ones),
 * ``LICENSE``                                       (CC0 1.0: copying is permitted),
 
 into ``oracle/_ref/``, which is listed in ``.gitignore`` (build output: it stays out of history) and NOT in
@@ -32,7 +35,7 @@ DEST = os.path.join(HERE, "_ref")
 MANIFEST = os.path.join(HERE, "ref_manifest.json")
 
 # (path below the reference root, path below oracle/_ref)
-TREES = [("turbopy", "turbopy"), ("tests/fixtures/particle_in_field", "fixtures/particle_in_field")]
+TREES = [("turbopy", "turbopy"), ("tests/fixtures/particle_in_field", "fixtures/particle_in_field"), ("tests", "tests")]
 FILES = [("LICENSE", "LICENSE")]
 KEEP = (".py", ".toml", ".csv")
 

@@ -63,3 +63,26 @@ def test_dropin_into_unmodified_turbopy(tmp_path):
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], capture_output=True, text=True,
                        cwd=str(tmp_path), env=env)
     assert r.returncode == 0 and "DROPIN-OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not refload.tests_dir(), reason="the reference's tests are not present")
+def test_reference_suite_substitution_plumbing_and_loud_failure(tmp_path):
+    """tests/test_gpu_reference_suite.py runs the reference's own 48 tests against the B200 tools on the GPU box.
+    Here, without a device: the substitution takes (names and registry resolve to turbopy_b200), the tests that never
+    reach a kernel pass, and every test that does fails with the library's "no CPU fallback" error -- not one of them
+    passes on a silent host path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the GPU test covers this")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_reference_suite as suite
+    rc0, passed0, rep0, tail0 = suite.run_suite(tmp_path, substitute=False)
+    assert rc0 == 0 and passed0 == 48, tail0
+    rc1, passed1, rep1, tail1 = suite.run_suite(tmp_path, substitute=True)
+    assert rc1 != 0 and rep1["launches"] == 0
+    assert all(v.startswith("turbopy_b200.") for v in rep1["classes"].values()), rep1
+    assert all(v.startswith("turbopy_b200.") for v in rep1["registry"].values()), rep1
+    failed = [ln for ln in tail1.splitlines() if ln.startswith("FAILED ")]
+    assert passed1 + len(failed) == 48 and len(failed) >= 15, tail1
+    assert all("test_computetools.py" in ln and " - Runtime" in ln for ln in failed), failed
+    assert "no CPU fallback" in tail1
