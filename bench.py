@@ -49,6 +49,9 @@ WORKLOADS = {
 }
 NG_CONFIG3 = (1 << 20) + 1
 KE_INTERVAL = 10
+# host-side pause between the warm-up steps and the timed region, ms (A-B switch; round 1 slept 50 ms here while the
+# NVML sampler started, which let the GPU go idle in front of a 5 ms timed region)
+GAP_MS = float(os.environ.get("TURBOPY_B200_BENCH_GAP_MS", "0"))
 
 
 def parse():
@@ -573,14 +576,16 @@ def run_b200(args):
     sampler = ClockSampler(b.local)
     if workload == "pif":
         pusher, step = b.setup_pif(n, ng, K + W)
-        for s in range(W):
-            step(s)
+        sampler.start()                          # NVML thread up before the warm-up: no idle gap in front of the timed steps
         graph = None
         if args.graph:
+            step(0)
             with tp.StepGraph(b.dev) as graph:
                 for s in range(K):
                     step(W + s)
-        sampler.start(); time.sleep(0.05)
+        for s in range(W):
+            step(s)
+        time.sleep(GAP_MS * 1e-3)
         ms, launches, window = b.timed((lambda k: graph.replay()) if graph is not None else
                                        (lambda k: [step(W + s) for s in range(k)]), K, sampler)
         pusher.check_status()
@@ -591,9 +596,10 @@ def run_b200(args):
     else:
         st = b.setup_config3(n, ng, "sorted")
         step, pusher = st["step"], st["pusher"]
+        sampler.start()
         for s in range(W):
             step(s)
-        sampler.start(); time.sleep(0.05)
+        time.sleep(GAP_MS * 1e-3)
         ms, launches, window = b.timed(lambda k: [step(W + s) for s in range(k)], K, sampler)
         pusher.check_status()
         kernel = ("gather_push_win_kernel<interp(B)> (TMA particle ring + per-tile windows of cell records; "
