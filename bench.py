@@ -9,7 +9,8 @@ Workloads (one "step" = one gather+push pass over every particle):
 
 * N = 1 -> BASELINE.json configs[1] ("pif"): the particle-in-field example scaled up -- 16 Mi electrons in a 1-D EM
   plane wave E_y(r,t) = E0 cos(2 pi (k (r-0.5) - w t)) on a 4097-node grid, B = 0, linear gather at position[:,0]
-  (Interpolators / numpy.interp rounding), relativistic Boris push.
+  (Interpolators / numpy.interp rounding), relativistic Boris push.  The K timed steps are captured once in a CUDA
+  graph (StepGraph) and replayed inside the timed region (--no-graph launches them from Python instead).
 * N > 1 -> BASELINE.json configs[2] ("config3"): 125 M particles PER GPU (1 B at N = 8), a replicated
   2^20+1-node grid with six field components, fused gather+push every step, kinetic-energy diagnostic every step
   call whose reduction + NCCL all-reduce (8 doubles, on the compute stream) fires every 10th step -- all INSIDE
@@ -71,7 +72,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the `configs` block (other shapes of the kernel)")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the timed steps as one CUDA graph")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=True,
+                    help="configs[1]: replay the K timed steps as one CUDA graph (default; north_star: timesteps are "
+                         "captured in a CUDA graph)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every timed step from Python")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.workload == "auto":
@@ -677,7 +681,12 @@ def run_b200(args):
 
     if b.rank == 0:
         config = config_of(args, b.world)
-        run = {"layout": layout_note, "cuda_graph": bool(args.graph)}
+        run = {"layout": layout_note, "cuda_graph": bool(args.graph and workload == "pif")}
+        if run["cuda_graph"]:
+            run["cuda_graph_note"] = (f"the {K} timed steps are one captured graph of {K} gather_push launches "
+                                      "(StepGraph -> tp_graph_*), replayed once inside the timed region; the warm-up "
+                                      "steps are launched eagerly.  Eager launches measure 0.6 % lower "
+                                      "(profiles/r2_final_ab.txt)")
         if order_note:
             run["particle_order"] = order_note
             run["collective"] = ("tp_nccl_allreduce_sum_f64 (own NCCL communicator) of 8 doubles on the compute stream, "
