@@ -53,6 +53,8 @@ KE_INTERVAL = 10
 # host-side pause between the warm-up steps and the timed region, ms (A-B switch; round 1 slept 50 ms here while the
 # NVML sampler started, which let the GPU go idle in front of a 5 ms timed region)
 GAP_MS = float(os.environ.get("TURBOPY_B200_BENCH_GAP_MS", "0"))
+# configs[2]: the KE diagnostic rides on the push kernel (KineticEnergyDiagnostic fuse_with_push; A-B switch)
+FUSE_KE = os.environ.get("TURBOPY_B200_BENCH_FUSE_KE", "1") != "0"
 
 
 def parse():
@@ -442,7 +444,8 @@ class Bench:
             sort_ms = e0.elapsed_time(e1)
         diag = None
         if diag_interval:
-            diag = tp.KineticEnergyDiagnostic(owner, {"momentum": "p", "mass": M_E, "interval": diag_interval})
+            diag = tp.KineticEnergyDiagnostic(owner, {"momentum": "p", "mass": M_E, "interval": diag_interval,
+                                                      "fuse_with_push": FUSE_KE})
             diag.inspect_resource({"p": mom})
             diag.initialize()
 
@@ -481,8 +484,19 @@ class Bench:
         ke_rel = float(abs(got[0] - want[0]) / abs(want[0]))
         m = min(16_384, pos.shape[0])
         sp, sm = pos[:m].cpu().numpy().copy(), mom[:m].cpu().numpy().copy()
-        for _ in range(3):
+        # the diagnostic riding on the push (fuse_with_push) against the standalone reduction of the same momenta
+        fd = tp.KineticEnergyDiagnostic(st["owner"], {"momentum": "p", "mass": M_E, "allreduce": False,
+                                                      "fuse_with_push": True, "interval": 1 << 20})
+        fd.inspect_resource({"p": mom})
+        fd.initialize()
+        for k in range(3):
+            if k == 0:
+                alone = tp.reduce_moments(mom, M_E, st["pusher"].c2).cpu().numpy()
+                fd.diagnose()
             st["pusher"].gather_push(pos, mom, Q_E, M_E, E_grid=st["E"], B_grid=st["B"])
+        fused = fd.values()[0]
+        fused_rel = float(max(abs(fused[0] - alone[0]) / abs(alone[0]), abs(fused[4] - alone[4]) / abs(alone[4])))
+        fused_ok = fused_rel <= 1e-12 and fused[5] == alone[5] and fd.fused_rows == 1
         st["pusher"].check_status()
         r, dt = st["r"], st["owner"].clock.dt
         for _ in range(3):
@@ -491,8 +505,9 @@ class Bench:
         gp, gm = pos[:m].cpu().numpy(), mom[:m].cpu().numpy()
         exact = bool(np.array_equal(gp.view(np.uint64), sp.view(np.uint64)) and
                      np.array_equal(gm.view(np.uint64), sm.view(np.uint64)))
-        ok = self.max_over_ranks(0.0 if (exact and ke_rel <= 1e-12) else 1.0) == 0.0
+        ok = self.max_over_ranks(0.0 if (exact and ke_rel <= 1e-12 and fused_ok) else 1.0) == 0.0
         return {"ok": ok, "ke_allreduce_vs_sum_of_partials_rel": ke_rel, "ke_tolerance": 1e-12,
+                "ke_fused_in_push_vs_standalone_rel": fused_rel,
                 "count_all_ranks": float(got[5]), "subset_particles_per_rank": m, "subset_steps": 3,
                 "subset_bit_identical_to_oracle": exact, "ranks": self.world}
 
@@ -607,7 +622,8 @@ def run_b200(args):
         ms, launches, window = b.timed(lambda k: [step(W + s) for s in range(k)], K, sampler)
         pusher.check_status()
         kernel = ("gather_push_win_kernel<interp(B)> (TMA particle ring + per-tile windows of cell records; "
-                  "pack_cells_kernel before it, moments_* + ncclAllReduce every 10th step)")
+                  "pack_cells_kernel before it; every 10th step its <MOM> instance also accumulates the KE / moment "
+                  "sums, followed by moments_final_kernel + ncclAllReduce)")
         layout_note = "SoA fp64 resident, cell-ordered once before the timed region (tp.sort_by_cell)"
         order_note = {"sort_ms_per_gpu": st["sort_ms"], "sorted_before_timed_region": True,
                       "steps_since_sort_in_timed_region": [W, W + K],
@@ -691,6 +707,10 @@ def run_b200(args):
             run["particle_order"] = order_note
             run["collective"] = ("tp_nccl_allreduce_sum_f64 (own NCCL communicator) of 8 doubles on the compute stream, "
                                  "every 10th step")
+            run["diagnostic"] = ("KineticEnergyDiagnostic, fuse_with_push: on its steps the sums are accumulated inside "
+                                 "gather_push_win_kernel<MOM> from the momenta it has just loaded "
+                                 "(tp_gather_push_windows_moments_f64)" if FUSE_KE else
+                                 "KineticEnergyDiagnostic: standalone reduction (moments_partial_kernel) in front of the push")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": b.world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

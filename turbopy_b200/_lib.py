@@ -59,6 +59,10 @@ SIGNATURES = {
     "tp_gather_push_windows_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts), C.POINTER(GridFields),
                                              C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p]),
+    "tp_gather_push_windows_moments_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts),
+                                                     C.POINTER(GridFields), C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                                     C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "tp_gather_windows_len": (C.c_int64, [C.POINTER(Particles), C.POINTER(GridFields)]),
     "tp_gather_windows_capacity": (C.c_int64, [C.POINTER(Particles), C.POINTER(GridFields), C.c_int]),
     "tp_gather_windows_init": (C.c_int, [C.POINTER(Particles), C.POINTER(GridFields), C.c_int, C.c_void_p, C.c_int64,

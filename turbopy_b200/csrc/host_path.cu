@@ -16,7 +16,7 @@ namespace tp {
 
 int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
                        int formula, uint64_t* status, cudaStream_t s, int nsteps, int32_t* bounds, int64_t bounds_len,
-                       double* rec_scratch);
+                       double* rec_scratch, const struct MomRequest* mr);
 
 namespace {
 
@@ -294,7 +294,7 @@ extern "C" int tp_gather_push_host_f64(const tp_particles* p, const tp_push_cons
         rc = run_chunks(p, nullptr, false, nullptr, false,
                         [&](const tp_particles& dp, double*, int64_t, cudaStream_t s) {
                             if (s != s0) TP_CUDA_TRY(cudaStreamWaitEvent(s, c.grid_ready, 0));
-                            return gather_push_device(&dp, k, &dg, axis, formula, c.status_dev, s, 1, nullptr, 0, nullptr);
+                            return gather_push_device(&dp, k, &dg, axis, formula, c.status_dev, s, 1, nullptr, 0, nullptr, nullptr);
                         });
         if (rc) return rc;
     }

@@ -20,6 +20,7 @@
 #include "tma_ring.cuh"
 #include "tma_ring_fields.cuh"
 #include "tma_ring_window.cuh"
+#include "moments_math.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -336,6 +337,8 @@ struct TmaWinArgs {
     GatherArgs g;
     RingArgs ring;
     WindowArgs win;
+    MomConsts mom;              // MOM instances: constants of the fused moment diagnostic ...
+    double* mom_partials;       // ... and where CTA b leaves its five partial sums (8 doubles apart)
 };
 
 template <int FORMULA>
@@ -392,7 +395,26 @@ __device__ __forceinline__ void gather_pair_fast_cells(const GatherArgs& a, cons
     }
 }
 
-template <int FORMULA, bool AOS>
+// The moment diagnostic's share of one thread: the two momenta of a tile slot (or one particle of the ragged tail),
+// fast arithmetic under a guard of its own, redone with IEEE operations if an operand left the fast path's range.
+__device__ __forceinline__ void moments_add(const Vec3* p, int count, const MomConsts& k, double (&acc)[kRedVals]) {
+    double c[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    Guard g;
+    for (int v = 0; v < count; ++v) accumulate<true>(p[v].x, p[v].y, p[v].z, k, g, c);
+    if (__builtin_expect(!(guard_ok(g) && k.fast_ok), 0)) {
+#pragma unroll
+        for (int q = 0; q < kRedVals; ++q) c[q] = 0.0;
+        for (int v = 0; v < count; ++v) accumulate<false>(p[v].x, p[v].y, p[v].z, k, g, c);
+    }
+#pragma unroll
+    for (int q = 0; q < kRedVals; ++q) acc[q] += c[q];
+}
+
+// MOM: the kernel also accumulates {KE, Px, Py, Pz, |p|^2} of the momenta AS LOADED (i.e. before this push) and
+// leaves one partial per CTA in ta.mom_partials -- the energy / moment diagnostic of the step without a second pass
+// over the momentum arrays (24 B per particle saved).  Deterministic: static tile -> CTA -> thread assignment,
+// per-thread serial sums, shuffle trees, fixed-order fold of the CTA partials (moments_final_kernel).
+template <int FORMULA, bool AOS, bool MOM = false>
 __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_win_kernel(const __grid_constant__ TmaWinArgs ta) {
     constexpr bool CELLS = FORMULA == TP_INTERP_B;          // (the host packs the matching record table)
     extern __shared__ __align__(128) unsigned char smem[];
@@ -400,6 +422,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_win_kernel(const _
     ring_init(ta.ring, smem);
     __syncthreads();
     const RecView rv = make_rec_view(a, ta.ring.stream_hint);
+    double acc[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
     tma_ring_window<AOS, CELLS>(
         a.p, ta.ring, ta.win, rv, a.axis, smem,
         [&](Vec3 (&x)[2], Vec3 (&p)[2], const WinView& w, bool& ok0, bool& ok1) {
@@ -408,6 +431,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_win_kernel(const _
         },
         [&](int64_t i, double* xs, double* ps, int pitch) {
             gather_step_exact_slot<FORMULA, false>(a, smem, i, xs, ps, pitch);
+        },
+        [&](const Vec3 (&p)[2]) {
+            if (MOM) moments_add(p, 2, ta.mom, acc);
         });
     // ragged tail (< kTile particles) on the last CTA, scalar path over the original arrays
     if (blockIdx.x == gridDim.x - 1) {
@@ -415,10 +441,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_win_kernel(const _
         for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
             Vec3 x, p;
             load_one(a.p, i, x, p);
+            if (MOM) moments_add(&p, 1, ta.mom, acc);
             if (gather_step_fast<FORMULA>(a, g, x, p)) store_one(a.p, i, x, p);
             else gather_step_exact<FORMULA, false>(a, smem, i);
         }
     }
+    if (MOM) block_sum<kTmaThreads>(acc, ta.mom_partials + static_cast<int64_t>(blockIdx.x) * 8);   // all 16 warps
 }
 
 // Cell range of every full tile from the particles' CURRENT coordinates: primes the per-tile windows on the
@@ -1331,13 +1359,38 @@ static int launch_gather_push_win(const TmaWinArgs& ta, size_t smem, int blocks,
     return aos ? go(gather_push_win_kernel<FORMULA, true>) : go(gather_push_win_kernel<FORMULA, false>);
 }
 
-// Returns TP_OK and sets `launched` when the windowed kernel took the call.
+// A moment diagnostic riding on a gather+push call: {KE, Px, Py, Pz, |p|^2, n, 0, 0} of the momenta BEFORE the push,
+// i.e. what tp_reduce_moments_f64 called just before the push would return (to summation-order rounding).
+struct MomRequest {
+    double mass, mass_sq, c2;
+    double* out8;
+    double* scratch;            // tp_reduce_scratch_doubles() doubles
+};
+
+static int moments_standalone(const GatherArgs& a, const MomRequest& mr, cudaStream_t s) {
+    return tp_reduce_moments_f64(a.p.mom, a.p.mom_sn, a.p.mom_sc, a.p.n, mr.mass, mr.mass_sq, mr.c2, mr.out8,
+                                 mr.scratch, s);
+}
+
+static bool fused_moments_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("TURBOPY_B200_FUSED_MOMENTS");      // A-B switch, default on
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+// Returns TP_OK and sets `launched` when the windowed kernel took the call.  `mr` (optional): when the call is
+// taken, the moments are delivered too -- inside the kernel for the formula-B SoA instance, by the standalone
+// reduction in front of it otherwise.
 static int try_gather_push_windows(const GatherArgs& a, int formula, bool aos, int32_t* bounds, int64_t bounds_len,
-                                   double* rec_scratch, cudaStream_t s, bool& launched) {
+                                   double* rec_scratch, const MomRequest* mr, cudaStream_t s, bool& launched) {
     launched = false;
     if (!bounds) return TP_OK;
     TmaWinArgs ta;
     ta.g = a;
+    ta.mom = MomConsts{};
+    ta.mom_partials = nullptr;
     size_t smem = 0; int blocks = 0;
     if (!plan_window_ring(a.p.n, ta.ring, ta.win, smem, blocks)) return TP_OK;
     if (bounds_len < 2 * ta.ring.ntiles) return TP_E_ARG;
@@ -1347,6 +1400,19 @@ static int try_gather_push_windows(const GatherArgs& a, int formula, bool aos, i
     if ((rc = pack_records(a, s, rec_scratch, &rec, formula == TP_INTERP_B ? 2 : 1))) return rc;
     ta.g.records = rec;
     ta.ring.stream_hint = l2_hints_enabled() ? 1 : 0;
+    if (mr && formula == TP_INTERP_B && !aos && blocks <= kRedMaxBlocks && fused_moments_enabled()) {
+        ta.mom = make_mom_consts(mr->mass, mr->mass_sq, mr->c2);
+        ta.mom_partials = mr->scratch;
+        auto kern = gather_push_win_kernel<TP_INTERP_B, false, true>;
+        if ((rc = set_smem(kern, smem))) return rc;
+        kern<<<blocks, kTmaThreads, smem, s>>>(ta);
+        count_launch();
+        if ((rc = static_cast<int>(cudaGetLastError()))) return rc;
+        rc = launch_moments_final(mr->scratch, blocks, a.p.n, mr->out8, s);
+        launched = (rc == TP_OK);
+        return rc;
+    }
+    if (mr && (rc = moments_standalone(a, *mr, s))) return rc;
     switch (formula) {
         case TP_INTERP_A: rc = launch_gather_push_win<TP_INTERP_A>(ta, smem, blocks, aos, s); break;
         case TP_INTERP_B: rc = launch_gather_push_win<TP_INTERP_B>(ta, smem, blocks, aos, s); break;
@@ -1381,7 +1447,7 @@ static int launch_interp_nc(const InterpArgs& a, size_t smem, cudaStream_t s) {
 // Entry point shared with host_path.cu
 int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
                        int formula, uint64_t* status, cudaStream_t s, int nsteps, int32_t* bounds, int64_t bounds_len,
-                       double* rec_scratch) {
+                       double* rec_scratch, const MomRequest* mr) {
     const DeviceProps& d = device_props();
     if (d.status != TP_OK) return d.status;
     if (nsteps < 0) return TP_E_ARG;
@@ -1407,12 +1473,17 @@ int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_
     if ((vec2 || aos16) && a.nsteps == 1) {
         bool launched = false;
         if (!staged) {          // grid too large for shared memory: per-tile record windows (cell-ordered particles)
-            if ((rc = try_gather_push_windows(a, formula, aos16, bounds, bounds_len, rec_scratch, s, launched))) return rc;
+            if ((rc = try_gather_push_windows(a, formula, aos16, bounds, bounds_len, rec_scratch, mr, s, launched))) return rc;
             if (launched) return TP_OK;
+        }
+        if (mr) {                       // no fused instance took the call: the standalone reduction in front of the push
+            if ((rc = moments_standalone(a, *mr, s))) return rc;
+            mr = nullptr;
         }
         if ((rc = try_gather_push_tma(a, formula, smem, staged, aos16, rec_scratch, s, launched))) return rc;
         if (launched) return TP_OK;
     }
+    if (mr && (rc = moments_standalone(a, *mr, s))) return rc;
     return vec2 ? launch_gather_push_f<true>(a, formula, smem, staged, s)
                 : launch_gather_push_f<false>(a, formula, smem, staged, s);
 }
@@ -1510,19 +1581,33 @@ extern "C" int tp_boris_push_steps_f64(const tp_particles* p, const tp_push_cons
 
 extern "C" int tp_gather_push_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
                                   int formula, uint64_t* status, tp_stream_t stream) {
-    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), 1, nullptr, 0, nullptr);
+    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), 1, nullptr, 0, nullptr, nullptr);
 }
 
 extern "C" int tp_gather_push_steps_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g, int axis,
                                         int formula, int nsteps, uint64_t* status, tp_stream_t stream) {
-    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), nsteps, nullptr, 0, nullptr);
+    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), nsteps, nullptr, 0, nullptr, nullptr);
 }
 
 extern "C" int tp_gather_push_windows_f64(const tp_particles* p, const tp_push_consts* k, const tp_grid_fields* g,
                                           int axis, int formula, int32_t* tile_bounds, int64_t tile_bounds_len,
                                           double* records_scratch, uint64_t* status, tp_stream_t stream) {
     return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), 1, tile_bounds,
-                              tile_bounds_len, records_scratch);
+                              tile_bounds_len, records_scratch, nullptr);
+}
+
+extern "C" int tp_gather_push_windows_moments_f64(const tp_particles* p, const tp_push_consts* k,
+                                                  const tp_grid_fields* g, int axis, int formula, int32_t* tile_bounds,
+                                                  int64_t tile_bounds_len, double* records_scratch, double mass,
+                                                  double mass_sq, double c2, double* out8, double* reduce_scratch,
+                                                  uint64_t* status, tp_stream_t stream) {
+    if (!out8 || !reduce_scratch) return TP_E_ARG;
+    MomRequest mr;
+    mr.mass = mass; mr.mass_sq = mass_sq; mr.c2 = c2; mr.out8 = out8; mr.scratch = reduce_scratch;
+    if (p && p->n == 0)             // nothing to push: the diagnostic row of an empty ensemble
+        return tp_reduce_moments_f64(p->mom, 1, 1, 0, mass, mass_sq, c2, out8, reduce_scratch, stream);
+    return gather_push_device(p, k, g, axis, formula, status, static_cast<cudaStream_t>(stream), 1, tile_bounds,
+                              tile_bounds_len, records_scratch, &mr);
 }
 
 // int32 words of tile bounds tp_gather_push_windows_f64 wants for this ensemble and grid; 0 = the call would not use

@@ -7,7 +7,7 @@
 // Deterministic: per-thread serial sums -> warp shuffle tree -> shared-memory
 // tree -> per-CTA partials; a second single-CTA pass folds the partials in a
 // fixed order (no atomics), so two runs on the same data agree bit for bit.
-#include "common.cuh"
+#include "moments_math.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -15,48 +15,6 @@
 #include <cmath>
 
 namespace tp {
-
-constexpr int kRedThreads = 256;
-constexpr int kRedMaxBlocks = 2048;
-constexpr int kRedVals = 5;               // KE, Px, Py, Pz, |p|^2
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-__device__ __forceinline__ void block_sum(double (&v)[kRedVals], double* out) {
-    __shared__ double sh[kRedVals][kRedThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < kRedVals; ++k) {
-        const double w = warp_sum(v[k]);
-        if (lane == 0) sh[k][warp] = w;
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < kRedVals; ++k) {
-            double w = lane < kRedThreads / 32 ? sh[k][lane] : 0.0;
-            w = warp_sum(w);
-            if (lane == 0) out[k] = w;
-        }
-    }
-}
-
-struct MomConsts { double mass, mm, c2, rc2; int fast_ok; };
-
-// FAST: shared-reciprocal quotients and the branch-free sqrt of common.cuh -- the same bits as the IEEE
-// operations whenever the thread's guard stays clean (checked once, after the loop).
-template <bool FAST>
-__device__ __forceinline__ void accumulate(double px, double py, double pz, const MomConsts& k, Guard& g,
-                                           double (&acc)[kRedVals]) {
-    const double p2 = (px * px + py * py) + pz * pz;
-    const double m1 = root<FAST>(k.mm + quot<FAST>(p2, const_recip<FAST>(k.c2, k.rc2), g), g);
-    acc[0] += quot<FAST>(p2, make_recip<FAST>(m1 + k.mass, g), g);
-    acc[1] += px; acc[2] += py; acc[3] += pz; acc[4] += p2;
-}
 
 template <bool FAST>
 __device__ __forceinline__ bool moments_thread(const double* __restrict__ mom, int64_t sn, int64_t sc, int64_t n,
@@ -107,6 +65,12 @@ __global__ void __launch_bounds__(kRedThreads) moments_final_kernel(const double
     }
 }
 
+int launch_moments_final(const double* scratch, int nblocks, int64_t n, double* out8, cudaStream_t s) {
+    moments_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, nblocks, n, out8);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace tp
 
 using namespace tp;
@@ -134,11 +98,9 @@ extern "C" int tp_reduce_moments_f64(const double* mom, int64_t stride_n, int64_
     if (blocks > full) blocks = full;
     if (blocks > kRedMaxBlocks) blocks = kRedMaxBlocks;
     if (blocks < 1) blocks = 1;
-    MomConsts k;
-    k.mass = mass; k.mm = mass_sq; k.c2 = c2; k.rc2 = 1.0 / c2;
-    k.fast_ok = const_divisor_ok(c2) ? 1 : 0;
+    const MomConsts k = make_mom_consts(mass, mass_sq, c2);
     moments_partial_kernel<<<static_cast<int>(blocks), kRedThreads, 0, s>>>(mom, stride_n, stride_c, n, k, vec, scratch);
-    moments_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, static_cast<int>(blocks), n, out8);
-    count_launch(2);
-    return static_cast<int>(cudaGetLastError());
+    count_launch();
+    const int rc = static_cast<int>(cudaGetLastError());
+    return rc ? rc : launch_moments_final(scratch, static_cast<int>(blocks), n, out8, s);
 }

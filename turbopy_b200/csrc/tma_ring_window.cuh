@@ -126,10 +126,12 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t byte
 // Ring driver.  fast(x[2], p[2], win, ok0, ok1) updates the thread's two particles in registers; recover as in tma_ring.
 // CELLS: the record table holds 128-byte cell records (cells jlo .. jhi are staged) instead of 64-byte node records
 // (nodes jlo-1 .. jhi+2, clamped: formula A also looks at the outer neighbours).
-template <bool AOS, bool CELLS, typename Fast, typename Recover>
+// observe(p[2]) sees the thread's two momenta AS LOADED, before `fast` updates them (the fused moment diagnostic
+// accumulates there; the other instances pass a no-op).
+template <bool AOS, bool CELLS, typename Fast, typename Recover, typename Observe>
 __device__ __forceinline__ void tma_ring_window(const ParticleArgs& P, const RingArgs& ra, const WindowArgs& wa,
                                                 const RecView& rv, int axis, unsigned char* smem, Fast fast,
-                                                Recover recover) {
+                                                Recover recover, Observe observe) {
     uint64_t* full = ring_full(smem);
     uint64_t* done = ring_done(smem);
     int4* meta = reinterpret_cast<int4*>(smem + kWinMetaOff);
@@ -199,6 +201,7 @@ __device__ __forceinline__ void tma_ring_window(const ParticleArgs& P, const Rin
         w.base = smem_u32(wins + static_cast<size_t>(s) * wa.win_bytes);
         Vec3 x[2], p[2];
         stage_read<AOS>(stage, x, p);
+        observe(p);
         bool ok0, ok1;
         fast(x, p, w, ok0, ok1);
         stage_write<AOS>(stage, x, p);

@@ -52,12 +52,50 @@ def reduce_moments(momentum, mass, c2, out=None, scratch=None):
     return out
 
 
+#: Deferred moment requests, keyed by (device index, data_ptr) of the momentum tensor: a KineticEnergyDiagnostic with
+#: ``fuse_with_push`` posts its row here instead of launching the reduction, and the next ``BorisPush.gather_push`` on
+#: that momentum tensor takes it along (tp_gather_push_windows_moments_f64: the sums are accumulated from the momenta
+#: the push kernel has just loaded).  Anything that needs the row earlier flushes it with the standalone reduction.
+_PENDING = {}
+
+
+def _pending_key(momentum):
+    return (momentum.device.index, momentum.data_ptr())
+
+
+def take_moments_request(momentum):
+    """The diagnostic waiting for the moments of ``momentum`` (and forget the request), or None."""
+    return _PENDING.pop(_pending_key(momentum), None)
+
+
+def flush_moments_request(momentum):
+    """A caller is about to change ``momentum`` through a path that cannot deliver a posted request (``push``,
+    ``push_steps``, multi-step passes): run the standalone reduction now, while the momenta are still the ones
+    the diagnostic asked about."""
+    diag = _PENDING.get(_pending_key(momentum))
+    if diag is not None:
+        diag._flush()
+
+
 class KineticEnergyDiagnostic(Diagnostic):
     """``input_data``: ``"momentum"`` (resource name of the shared (n,3)
     momentum tensor), ``"mass"``, optional ``"c2"`` (default BorisPush's
     2.9979e8**2), ``"interval"`` (steps between reductions, default 1),
     ``"filename"`` / ``"directory"`` for the CSV, ``"allreduce"`` (default
-    True: sum over ranks when torch.distributed is initialised)."""
+    True: sum over ranks when torch.distributed is initialised),
+    ``"fuse_with_push"`` (default False).
+
+    ``fuse_with_push``: the Simulation loop runs ``diagnose()`` before the
+    modules' ``update()`` (turbopy/core.py:152-158), so the momenta this
+    diagnostic sums are the ones the step's push is about to load anyway.
+    With the option set, ``diagnose()`` only posts a request; the next
+    ``BorisPush.gather_push`` on the same momentum tensor delivers the row
+    from inside its kernel (no second pass over the momentum arrays) and
+    enqueues the all-reduce behind it.  Contract: nothing else writes the
+    momentum between ``diagnose()`` and that push.  ``values()``,
+    ``finalize()`` and the next ``diagnose()`` flush an undelivered request
+    with the standalone reduction, so the rows are the same either way (to
+    summation-order rounding, 1e-12)."""
 
     def __init__(self, owner, input_data):
         super().__init__(owner, input_data)
@@ -66,10 +104,13 @@ class KineticEnergyDiagnostic(Diagnostic):
         self.c2 = float(input_data.get("c2", 2.9979e8 ** 2))
         self.interval = int(input_data.get("interval", 1))
         self.allreduce = bool(input_data.get("allreduce", True))
+        self.fuse_with_push = bool(input_data.get("fuse_with_push", False))
         self.rows = None
         self._scratch = None
         self._calls = 0
         self._used = 0
+        self._pending_row = None
+        self.fused_rows = 0              # rows delivered by a push kernel (the rest came from the standalone reduction)
 
     def inspect_resource(self, resource):
         name = self.input_data["momentum"]
@@ -80,12 +121,35 @@ class KineticEnergyDiagnostic(Diagnostic):
         steps = int(self.owner.clock.num_steps)
         self._capacity = steps // self.interval + 2
 
+    # ---- deferred rows (fuse_with_push)
+    def moments_request(self):
+        """(mass, mass**2, c2, out8 row, scratch) of the posted request -- read by BorisPush.gather_push."""
+        return self.mass, self.mass ** 2, self.c2, self._pending_row, self._scratch
+
+    def moments_delivered(self):
+        """BorisPush.gather_push has enqueued the kernels that fill the posted row (on the current stream)."""
+        row, self._pending_row = self._pending_row, None
+        self.fused_rows += 1
+        if self.allreduce:
+            allreduce_sum_(row)
+
+    def _flush(self):
+        """An undelivered request: the standalone reduction, now."""
+        if self._pending_row is None:
+            return
+        _PENDING.pop(_pending_key(self.momentum), None)
+        row, self._pending_row = self._pending_row, None
+        reduce_moments(self.momentum, self.mass, self.c2, out=row, scratch=self._scratch)
+        if self.allreduce:
+            allreduce_sum_(row)
+
     def diagnose(self):
         self._calls += 1
         if (self._calls - 1) % self.interval:
             return
         if self.momentum is None:
             raise RuntimeError("Diagnostic field {} not found".format(self.input_data["momentum"]))
+        self._flush()
         if self.rows is None:
             dev = self.momentum.device
             cap = getattr(self, "_capacity", 1024)
@@ -96,19 +160,25 @@ class KineticEnergyDiagnostic(Diagnostic):
         if self._scratch is None:
             self._scratch = torch.empty(int(_lib.lib().tp_reduce_scratch_doubles()), dtype=torch.float64,
                                         device=self.momentum.device)
+        self._used += 1
+        if self.fuse_with_push and isinstance(self.momentum, torch.Tensor) and self.momentum.is_cuda:
+            self._pending_row = row                      # filled by the next gather_push on this tensor (or a flush)
+            _PENDING[_pending_key(self.momentum)] = self
+            return
         reduce_moments(self.momentum, self.mass, self.c2, out=row, scratch=self._scratch)
         if self.allreduce:
             allreduce_sum_(row)
-        self._used += 1
 
     def values(self):
         """Host copy of the rows recorded so far: (k, 6) [KE, Px, Py, Pz, |p|^2, n]."""
         if self.rows is None:
             return np.zeros((0, 6))
+        self._flush()
         return self.rows[:self._used, :6].cpu().numpy()
 
     def finalize(self):
         self.diagnose()
+        self._flush()
         filename = self.input_data.get("filename")
         if filename:
             directory = self.input_data.get("directory", "")

@@ -30,6 +30,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import diagnostics as _diagnostics
 from ._host import ComputeTool, stock_tools
 
 _FORMULAS = {
@@ -452,6 +453,8 @@ class BorisPush(ComputeTool):
                 raise TypeError("position and momentum must live on the same CUDA device")
             p = _particles_struct(position, momentum)
             dev = position.device
+            if _diagnostics._PENDING:
+                _diagnostics.flush_moments_request(momentum)
             e = _FieldArg(E, "E", p.n, dev)
             b = _FieldArg(B, "B", p.n, dev)
             with _on_device(dev):
@@ -487,6 +490,8 @@ class BorisPush(ComputeTool):
         k = _push_consts(charge, mass, self.owner.clock.dt, self.c2)
         p = _particles_struct(position, momentum)
         dev = position.device
+        if _diagnostics._PENDING:
+            _diagnostics.flush_moments_request(momentum)
         e = _FieldArg(E, "E", p.n, dev)
         b = _FieldArg(B, "B", p.n, dev)
         with _on_device(dev):
@@ -576,18 +581,31 @@ class BorisPush(ComputeTool):
                     else:
                         particles.resort_local(position, momentum, grid, axis=axis, phase=nth)
                 self._sort_calls[ck] = calls + 1
+            # a KineticEnergyDiagnostic (fuse_with_push) waiting for the moments of exactly these momenta?
+            diag = _diagnostics.take_moments_request(momentum) if _diagnostics._PENDING else None
             with _on_device(dev):
-                if _steps is None:
+                if diag is not None:
+                    hit = self._tile_windows(p, g, position, momentum, axis, grid, dev, code) if _steps is None else None
+                    if hit is None:                 # no windowed kernel for this call: the standalone reduction, first
+                        diag._flush()
+                        diag = None
+                if diag is not None:
+                    win = hit[0] if hit[2] else None
+                    stream = _stream_ptr(dev)
+                    rec = self._record_scratch(ng, dev, stream)
+                    mass_d, mass_sq, c2_d, row, scratch = diag.moments_request()
+                    _lib.check(lib.tp_gather_push_windows_moments_f64(
+                        C.byref(p), C.byref(k), C.byref(g), axis, code,
+                        C.c_void_p(win.data_ptr()) if win is not None else None, win.shape[0] if win is not None else 0,
+                        C.c_void_p(rec.data_ptr()), mass_d, mass_sq, c2_d, C.c_void_p(row.data_ptr()),
+                        C.c_void_p(scratch.data_ptr()), C.c_void_p(status.words.data_ptr()), stream))
+                    diag.moments_delivered()
+                elif _steps is None:
                     hit = self._tile_windows(p, g, position, momentum, axis, grid, dev, code)
                     if hit is not None:             # grid too large for shared memory: caller-owned record scratch
                         win = hit[0] if hit[2] else None        # (capturable on any stream); windows only if they pay
                         stream = _stream_ptr(dev)
-                        rkey = (ng, dev, stream.value)       # one scratch per stream: calls on a stream are ordered
-                        rec = self._records.get(rkey)
-                        if rec is None:
-                            if len(self._records) > 8:
-                                self._records.clear()
-                            rec = self._records[rkey] = torch.empty(18 * ng, dtype=torch.float64, device=dev)
+                        rec = self._record_scratch(ng, dev, stream)
                         _lib.check(lib.tp_gather_push_windows_f64(C.byref(p), C.byref(k), C.byref(g), axis, code,
                                                                   C.c_void_p(win.data_ptr()) if win is not None else None,
                                                                   win.shape[0] if win is not None else 0,
@@ -624,6 +642,16 @@ class BorisPush(ComputeTool):
                 raise exc(GatherStatus.message(int(words[0]), int(words[1]), int(words[2])))
             return None
         raise TypeError("position/momentum must both be CUDA float64 tensors or both numpy float64 arrays")
+
+    def _record_scratch(self, ng, dev, stream):
+        """Caller-owned record scratch of the large-grid calls, one per stream (calls on a stream are ordered)."""
+        rkey = (ng, dev, stream.value)
+        rec = self._records.get(rkey)
+        if rec is None:
+            if len(self._records) > 8:
+                self._records.clear()
+            rec = self._records[rkey] = torch.empty(18 * ng, dtype=torch.float64, device=dev)
+        return rec
 
     def _tile_windows(self, p, g, position, momentum, axis, grid, dev, code=_lib.TP_INTERP_B):
         """``[tile-bounds tensor, order generation, windows pay]`` of this ensemble for tp_gather_push_windows_f64
