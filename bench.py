@@ -709,7 +709,7 @@ def run_b200(args):
                                  "every 10th step")
             run["diagnostic"] = ("KineticEnergyDiagnostic, fuse_with_push: on its steps the sums are accumulated inside "
                                  "gather_push_win_kernel<MOM> from the momenta it has just loaded "
-                                 "(tp_gather_push_windows_moments_f64)" if FUSE_KE else
+                                 "(tp_gather_push_moments_f64)" if FUSE_KE else
                                  "KineticEnergyDiagnostic: standalone reduction (moments_partial_kernel) in front of the push")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": b.world, "steps": K, "warmup": W,

@@ -170,16 +170,18 @@ int tp_gather_push_windows_f64(const tp_particles* p, const tp_push_consts* k,
                                int32_t* tile_bounds, int64_t tile_bounds_len,
                                double* records_scratch /* DEVICE, TP_RECORDS_DOUBLES_PER_NODE*ng doubles, or NULL: library-owned */,
                                uint64_t* status, tp_stream_t stream);
-/* tp_gather_push_windows_f64 with the energy / moment diagnostic of the step riding on it: out8 receives
+/* A gather+push step with the energy / moment diagnostic of the step riding on it: out8 receives
  * {KE, Px, Py, Pz, sum|p|^2, n, 0, 0} of the momenta as they are BEFORE this push -- what
  * tp_reduce_moments_f64(mom, ..., mass, mass_sq, c2, out8, reduce_scratch) called just before the push would
- * deliver, to summation-order rounding (1e-12 relative; both orders are deterministic).  When the windowed
- * formula-B SoA kernel takes the call the sums are accumulated inside it from the momenta it has just loaded, so the
- * diagnostic costs no second pass over the momentum arrays (24 B per particle saved); in every other case the
- * standalone reduction is launched in front of the push.  The reference has no energy diagnostic; the
- * Simulation loop it rides on is diagnose() -> update() (turbopy/core.py:152-158).  reduce_scratch:
- * tp_reduce_scratch_doubles() doubles. */
-int tp_gather_push_windows_moments_f64(const tp_particles* p, const tp_push_consts* k,
+ * deliver, to summation-order rounding (1e-12 relative; both orders are deterministic) -- and the particles are
+ * pushed exactly as by tp_gather_push_windows_f64 with the same arguments (tile_bounds / records_scratch may be
+ * NULL: tp_gather_push_f64).  With formula B and SoA particles the TMA-pipelined kernels (grid staged in shared
+ * memory, or per-tile windows on a large grid) accumulate the sums from the momenta they have just loaded, so the
+ * diagnostic costs no second pass over the momentum arrays (24 B per particle saved on top of the push's 96 B); in
+ * every other case the standalone reduction is launched in front of the push.  The reference has no energy diagnostic
+ * (SURVEY 8a-8); the Simulation loop it rides on is diagnose() -> update() (turbopy/core.py:152-158).
+ * reduce_scratch: tp_reduce_scratch_doubles() doubles. */
+int tp_gather_push_moments_f64(const tp_particles* p, const tp_push_consts* k,
                                        const tp_grid_fields* g, int axis, int formula,
                                        int32_t* tile_bounds, int64_t tile_bounds_len, double* records_scratch,
                                        double mass, double mass_sq, double c2, double* out8, double* reduce_scratch,

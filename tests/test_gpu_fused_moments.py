@@ -1,4 +1,4 @@
-"""The energy / moment diagnostic riding on the push (tp_gather_push_windows_moments_f64,
+"""The energy / moment diagnostic riding on the push (tp_gather_push_moments_f64,
 ``KineticEnergyDiagnostic`` with ``fuse_with_push``): the sums of the momenta BEFORE the push, accumulated inside the
 windowed gather+push kernel from the momenta it has just loaded.  Checked against the standalone reduction
 (tp_reduce_moments_f64, 1e-12: the sum order differs), against the oracle (oracle/moments.py, exactly rounded sums),
@@ -41,15 +41,25 @@ def diag_for(tp, owner, mom, fuse, interval=1):
     return d
 
 
+def launches_of(tp):
+    from turbopy_b200 import _lib
+    return _lib.launch_count()
+
+
+@pytest.mark.parametrize("shape", ["windows", "staged6", "staged_ey"])
 @pytest.mark.parametrize("n", [148 * TILE * 2 + 333, 148 * TILE * 3, 148 * TILE + 1])
-def test_fused_rows_match_standalone_and_oracle(tp, n):
-    """Cell-ordered particles on a grid too large for shared memory: the formula-B SoA window kernel takes the call and
-    delivers the rows itself (ragged tail, no tail, one tile per SM and a one-particle tail)."""
-    ng = 5_001
+def test_fused_rows_match_standalone_and_oracle(tp, n, shape):
+    """The three fused instances (formula B, SoA): per-tile windows on a grid too large for shared memory with
+    cell-ordered particles; the grid staged whole in shared memory with all six components; the pif shape (E_y only,
+    the mask-specialised kernel).  Ragged tail, no tail, one tile per SM and a one-particle tail.  A fused step
+    launches ONE kernel less than reduction + push (moments_partial_kernel is gone)."""
+    ng = 5_001 if shape == "windows" else 1025
     grid = make_grid(ng)
     dt = 0.5 * grid.dr / 2.9979e8
-    pos0, mom0 = ensemble(n, ng, 23, True)
+    pos0, mom0 = ensemble(n, ng, 23, shape == "windows")
     comps, E, B = fields_on(grid)
+    if shape == "staged_ey":
+        E, B = (None, E[:, 1].contiguous(), None), None
     steps = 5
     runs = {}
     for fuse in (False, True):
@@ -58,13 +68,17 @@ def test_fused_rows_match_standalone_and_oracle(tp, n):
         pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
         diag = diag_for(tp, owner, mom, fuse)
         pre = []
+        launched = 0
         for _ in range(steps):
             pre.append(mom.cpu().numpy().copy())
+            l0 = launches_of(tp)
             diag.diagnose()
             tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B)
+            launched += launches_of(tp) - l0
         tool.check_status()
-        runs[fuse] = (pos.cpu().numpy(), mom.cpu().numpy(), diag.values(), diag.fused_rows, pre)
-    assert runs[True][3] == steps and runs[False][3] == 0, "the fused kernel did not deliver the rows"
+        runs[fuse] = (pos.cpu().numpy(), mom.cpu().numpy(), diag.values(), diag.fused_rows, pre, launched)
+    assert runs[True][3] == steps and runs[False][3] == 0, "the push did not deliver the rows"
+    assert runs[True][5] == runs[False][5] - steps, "no fused instance ran (same number of launches as reduction + push)"
     assert_bits_equal(runs[True][0], runs[False][0], "position")
     assert_bits_equal(runs[True][1], runs[False][1], "momentum")
     assert runs[True][2].shape == (steps, 6)
@@ -125,12 +139,12 @@ def test_interval_and_extreme_momenta(tp):
         assert close(g[[0, 4, 5]], w[[0, 4, 5]]), (g, w)
 
 
-@pytest.mark.parametrize("case", ["formula_A", "aos", "random_order", "staged_grid", "small_ensemble", "push",
+@pytest.mark.parametrize("case", ["formula_A", "formula_C_staged", "aos", "random_order", "small_ensemble", "push",
                                   "push_steps", "gather_push_steps", "values_first"])
 def test_paths_that_cannot_fuse_deliver_the_pre_push_row(tp, case):
     """Other formulas / layouts / orders / entry points: the row is the standalone reduction's, bit for bit, of the
     momenta as they were when diagnose() was called."""
-    ng = 1025 if case == "staged_grid" else 5_001
+    ng = 1025 if case == "formula_C_staged" else 5_001
     n = 5 * TILE + 1 if case == "small_ensemble" else 148 * TILE * 2 + 11      # fewer tiles than SMs: no ring kernel
     grid = make_grid(ng)
     dt = 0.5 * grid.dr / 2.9979e8
@@ -156,7 +170,8 @@ def test_paths_that_cannot_fuse_deliver_the_pre_push_row(tp, case):
     elif case == "values_first":
         pass
     else:
-        tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B, formula=NAME["A"] if case == "formula_A" else "interp")
+        tool.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B,
+                         formula=NAME["A"] if case == "formula_A" else NAME["C"] if case == "formula_C_staged" else "interp")
     got = diag.values()
     assert got.shape == (1, 6) and diag._pending_row is None
     from turbopy_b200 import diagnostics
@@ -167,7 +182,7 @@ def test_paths_that_cannot_fuse_deliver_the_pre_push_row(tp, case):
 
 
 def test_capi_fallback_inside_the_library(tp):
-    """tp_gather_push_windows_moments_f64 with NULL tile bounds (no windows): the library itself launches the standalone
+    """tp_gather_push_moments_f64 with NULL tile bounds (no windows): the library itself launches the standalone
     reduction in front of the push -- out8 bit-identical to tp_reduce_moments_f64, particles to tp_gather_push_f64."""
     from turbopy_b200 import _lib
     lib = _lib.lib()
@@ -194,7 +209,7 @@ def test_capi_fallback_inside_the_library(tp):
     rec = torch.empty(18 * ng, dtype=torch.float64, device="cuda")
     status = torch.zeros(4, dtype=torch.int64, device="cuda")
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(lib.tp_gather_push_windows_moments_f64(C.byref(ps), C.byref(k), C.byref(gf), 0, _lib.TP_INTERP_B, None, 0,
+    _lib.check(lib.tp_gather_push_moments_f64(C.byref(ps), C.byref(k), C.byref(gf), 0, _lib.TP_INTERP_B, None, 0,
                                                       C.c_void_p(rec.data_ptr()), M_E, M_E ** 2, C2,
                                                       C.c_void_p(out8.data_ptr()), C.c_void_p(scratch.data_ptr()),
                                                       C.c_void_p(status.data_ptr()), stream))
@@ -204,7 +219,7 @@ def test_capi_fallback_inside_the_library(tp):
     assert_bits_equal(mom.cpu().numpy(), mom_a.cpu().numpy(), "momentum")
     assert int(status[0]) == 0
     # argument validation
-    assert lib.tp_gather_push_windows_moments_f64(C.byref(ps), C.byref(k), C.byref(gf), 0, _lib.TP_INTERP_B, None, 0,
+    assert lib.tp_gather_push_moments_f64(C.byref(ps), C.byref(k), C.byref(gf), 0, _lib.TP_INTERP_B, None, 0,
                                                   C.c_void_p(rec.data_ptr()), M_E, M_E ** 2, C2, None,
                                                   C.c_void_p(scratch.data_ptr()), C.c_void_p(status.data_ptr()),
                                                   stream) == -1            # TP_E_ARG

@@ -59,7 +59,7 @@ SIGNATURES = {
     "tp_gather_push_windows_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts), C.POINTER(GridFields),
                                              C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p]),
-    "tp_gather_push_windows_moments_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts),
+    "tp_gather_push_moments_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts),
                                                      C.POINTER(GridFields), C.c_int, C.c_int, C.c_void_p, C.c_int64,
                                                      C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                                      C.c_void_p, C.c_void_p, C.c_void_p]),

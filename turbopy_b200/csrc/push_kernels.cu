@@ -280,7 +280,31 @@ __global__ void __launch_bounds__(kThreads, TP_MIN_BLOCKS) gather_push_kernel(co
 struct TmaArgs {
     GatherArgs g;
     RingArgs ring;
+    MomConsts mom;              // MOM instances: constants of the fused moment diagnostic ...
+    double* mom_partials;       // ... and where CTA b leaves its five partial sums (8 doubles apart)
 };
+
+// The moment diagnostic's share of one thread: the two momenta of a tile slot (or one particle of the ragged tail),
+// fast arithmetic under a guard of its own, redone with IEEE operations if an operand left the fast path's range.
+// The constants are the push's own (mass**2, c2, 1/c2 from PushK -- the host only fuses when the diagnostic's agree)
+// plus the diagnostic's mass: |p|^2 and m1 = sqrt(mass**2 + |p|^2/c2) are then literally the first quantities
+// boris_step forms from the same momentum, and the compiler merges them; what the diagnostic adds per particle is one
+// reciprocal, one quotient and five additions.
+__device__ __forceinline__ void moments_add(const Vec3* p, int count, const PushK& pk, double mass, double (&acc)[kRedVals]) {
+    MomConsts k;
+    k.mass = mass; k.mm = pk.mm; k.c2 = pk.c2; k.rc2 = pk.rc2; k.fast_ok = pk.fast_ok;
+    double c[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    Guard g;
+    for (int v = 0; v < count; ++v) accumulate<true>(p[v].x, p[v].y, p[v].z, k, g, c);
+    if (__builtin_expect(!(guard_ok(g) && k.fast_ok), 0)) {
+#pragma unroll
+        for (int q = 0; q < kRedVals; ++q) c[q] = 0.0;
+        for (int v = 0; v < count; ++v) accumulate<false>(p[v].x, p[v].y, p[v].z, k, g, c);
+    }
+#pragma unroll
+    for (int q = 0; q < kRedVals; ++q) acc[q] += c[q];
+}
+
 
 template <int FORMULA, bool STAGED>
 __device__ __noinline__ void gather_step_exact_slot(const GatherArgs& a, unsigned char* smem, int64_t i, double* xs,
@@ -296,7 +320,9 @@ __device__ __noinline__ void gather_step_exact_slot(const GatherArgs& a, unsigne
 // recovery path always reads the original arrays).
 // PMASK: 0 = which components are on the grid is a run-time property (any shape); otherwise the compile-time mask of
 // a specialised shape (staged grids only: see gather6_fast_mask).
-template <int FORMULA, int GMODE, bool AOS, unsigned PMASK = 0u>
+// MOM: also accumulate {KE, Px, Py, Pz, |p|^2} of the momenta AS LOADED, one partial per CTA in ta.mom_partials
+// (see gather_push_win_kernel).
+template <int FORMULA, int GMODE, bool AOS, unsigned PMASK = 0u, bool MOM = false>
 __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const __grid_constant__ TmaArgs ta) {
     constexpr bool STAGED = GMODE == 1;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -312,24 +338,31 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_tma_kernel(const _
     auto exact = [&](int64_t i, double* xs, double* ps, int pitch) {
         gather_step_exact_slot<FORMULA, STAGED>(a, smem, i, xs, ps, pitch);
     };
+    double acc[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    auto observe = [&](const Vec3 (&p)[2]) {
+        if (MOM) moments_add(p, 2, a.k, ta.mom.mass, acc);
+    };
     if (STAGED && FORMULA == TP_INTERP_A && g.qa > 0.0)      // (kernel-uniform) the ring instance without the neighbour loads
-        tma_ring<AOS>(a.p, ta.ring, smem, [&](Vec3& x, Vec3& p) { return gather_step_fast<FORMULA, PMASK, true>(a, g, x, p); }, exact);
+        tma_ring<AOS>(a.p, ta.ring, smem, [&](Vec3& x, Vec3& p) { return gather_step_fast<FORMULA, PMASK, true>(a, g, x, p); }, exact,
+                      observe);
     else
         tma_ring<AOS>(
             a.p, ta.ring, smem,
             [&](Vec3& x, Vec3& p) {
                 return GMODE == 2 ? gather_step_fast_records<FORMULA>(a, rv, x, p) : gather_step_fast<FORMULA, PMASK>(a, g, x, p);
             },
-            exact);
+            exact, observe);
     // ragged tail (< kTile particles) on the last CTA, scalar path
     if (blockIdx.x == gridDim.x - 1) {
         for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {   // all 16 warps
             Vec3 x, p;
             load_one(a.p, i, x, p);
+            if (MOM) moments_add(&p, 1, a.k, ta.mom.mass, acc);
             if (gather_step_fast<FORMULA>(a, g, x, p)) store_one(a.p, i, x, p);
             else gather_step_exact<FORMULA, STAGED>(a, smem, i);
         }
     }
+    if (MOM) block_sum<kTmaThreads>(acc, ta.mom_partials + static_cast<int64_t>(blockIdx.x) * 8);   // all 16 warps
 }
 
 // ---- fused gather + push, node records staged per tile (large grids, cell-ordered particles) ----------
@@ -395,21 +428,6 @@ __device__ __forceinline__ void gather_pair_fast_cells(const GatherArgs& a, cons
     }
 }
 
-// The moment diagnostic's share of one thread: the two momenta of a tile slot (or one particle of the ragged tail),
-// fast arithmetic under a guard of its own, redone with IEEE operations if an operand left the fast path's range.
-__device__ __forceinline__ void moments_add(const Vec3* p, int count, const MomConsts& k, double (&acc)[kRedVals]) {
-    double c[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    Guard g;
-    for (int v = 0; v < count; ++v) accumulate<true>(p[v].x, p[v].y, p[v].z, k, g, c);
-    if (__builtin_expect(!(guard_ok(g) && k.fast_ok), 0)) {
-#pragma unroll
-        for (int q = 0; q < kRedVals; ++q) c[q] = 0.0;
-        for (int v = 0; v < count; ++v) accumulate<false>(p[v].x, p[v].y, p[v].z, k, g, c);
-    }
-#pragma unroll
-    for (int q = 0; q < kRedVals; ++q) acc[q] += c[q];
-}
-
 // MOM: the kernel also accumulates {KE, Px, Py, Pz, |p|^2} of the momenta AS LOADED (i.e. before this push) and
 // leaves one partial per CTA in ta.mom_partials -- the energy / moment diagnostic of the step without a second pass
 // over the momentum arrays (24 B per particle saved).  Deterministic: static tile -> CTA -> thread assignment,
@@ -433,7 +451,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_win_kernel(const _
             gather_step_exact_slot<FORMULA, false>(a, smem, i, xs, ps, pitch);
         },
         [&](const Vec3 (&p)[2]) {
-            if (MOM) moments_add(p, 2, ta.mom, acc);
+            if (MOM) moments_add(p, 2, a.k, ta.mom.mass, acc);
         });
     // ragged tail (< kTile particles) on the last CTA, scalar path over the original arrays
     if (blockIdx.x == gridDim.x - 1) {
@@ -441,7 +459,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gather_push_win_kernel(const _
         for (int64_t i = ta.ring.ntiles * kTile + threadIdx.x; i < a.p.n; i += kTmaThreads) {
             Vec3 x, p;
             load_one(a.p, i, x, p);
-            if (MOM) moments_add(&p, 1, ta.mom, acc);
+            if (MOM) moments_add(&p, 1, a.k, ta.mom.mass, acc);
             if (gather_step_fast<FORMULA>(a, g, x, p)) store_one(a.p, i, x, p);
             else gather_step_exact<FORMULA, false>(a, smem, i);
         }
@@ -1160,8 +1178,20 @@ static bool mask_kernels_enabled() {
     return on;
 }
 
+template <int FORMULA, int GMODE, bool AOS, unsigned PMASK = 0u>
+static int launch_gather_push_tma_mom(const TmaArgs& ta, size_t smem, int blocks, cudaStream_t s) {
+    auto kern = gather_push_tma_kernel<FORMULA, GMODE, AOS, PMASK, true>;
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    kern<<<blocks, kTmaThreads, smem, s>>>(ta);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+// `mom` (staged grid, formula B, SoA -- the caller checks): the instances that also accumulate the moment sums.
 template <int FORMULA>
-static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, int gmode, bool aos, cudaStream_t s) {
+static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, int gmode, bool aos, cudaStream_t s,
+                                    bool mom = false) {
     if (gmode == 1 && mask_kernels_enabled()) {              // staged grid: the specialised shapes
         unsigned mask = 0;
         for (int k = 0; k < 6; ++k) mask |= ta.g.comp[k] ? (1u << k) : 0u;
@@ -1173,13 +1203,16 @@ static int launch_gather_push_tma_v(const TmaArgs& ta, size_t smem, int blocks, 
         static const int pace = [] { const char* e = std::getenv("TURBOPY_B200_CONSUMER_DELAY_NS"); return e ? std::atoi(e) : 800; }();
         TmaArgs tb = ta;
         tb.ring.consumer_delay_ns = pace;
+        if (FORMULA == TP_INTERP_B && mom && mask == 0x02u)
+            return launch_gather_push_tma_mom<TP_INTERP_B, 1, false, 0x02u>(tb, smem, blocks, s);
         if (mask == 0x02u)
             return aos ? launch_gather_push_tma<FORMULA, 1, true, 0x02u>(tb, smem, blocks, s)
                        : launch_gather_push_tma<FORMULA, 1, false, 0x02u>(tb, smem, blocks, s);
-        if (mask == 0x07u)
+        if (mask == 0x07u && !mom)
             return aos ? launch_gather_push_tma<FORMULA, 1, true, 0x07u>(tb, smem, blocks, s)
                        : launch_gather_push_tma<FORMULA, 1, false, 0x07u>(tb, smem, blocks, s);
     }
+    if (FORMULA == TP_INTERP_B && mom) return launch_gather_push_tma_mom<TP_INTERP_B, 1, false>(ta, smem, blocks, s);
     switch (gmode) {
         case 1: return aos ? launch_gather_push_tma<FORMULA, 1, true>(ta, smem, blocks, s)
                            : launch_gather_push_tma<FORMULA, 1, false>(ta, smem, blocks, s);
@@ -1288,15 +1321,50 @@ static int pack_records(const GatherArgs& a, cudaStream_t s, double* caller_scra
     return static_cast<int>(cudaGetLastError());
 }
 
+// A moment diagnostic riding on a gather+push call: {KE, Px, Py, Pz, |p|^2, n, 0, 0} of the momenta BEFORE the push,
+// i.e. what tp_reduce_moments_f64 called just before the push would return (to summation-order rounding).
+struct MomRequest {
+    double mass, mass_sq, c2;
+    double* out8;
+    double* scratch;            // tp_reduce_scratch_doubles() doubles
+};
+
+static int moments_standalone(const GatherArgs& a, const MomRequest& mr, cudaStream_t s) {
+    return tp_reduce_moments_f64(a.p.mom, a.p.mom_sn, a.p.mom_sc, a.p.n, mr.mass, mr.mass_sq, mr.c2, mr.out8,
+                                 mr.scratch, s);
+}
+
+static bool fused_moments_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("TURBOPY_B200_FUSED_MOMENTS");      // A-B switch, default on
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 // Returns TP_OK and sets `launched` when the TMA kernel took the call.
 static int try_gather_push_tma(const GatherArgs& a, int formula, size_t grid_smem, bool staged, bool aos,
-                               double* rec_scratch, cudaStream_t s, bool& launched) {
+                               double* rec_scratch, const MomRequest* mr, cudaStream_t s, bool& launched) {
     launched = false;
     TmaArgs ta;
     ta.g = a;
+    ta.mom = MomConsts{};
+    ta.mom_partials = nullptr;
     size_t smem = 0; int blocks = 0;
     if (!plan_ring(a.p.n, staged ? grid_smem : kSmemHeader, ta.ring, smem, blocks)) return TP_OK;
     int rc;
+    // the moment diagnostic rides along on the staged formula-B SoA instances; otherwise the standalone reduction first
+    const bool mom = mr && staged && formula == TP_INTERP_B && !aos && blocks <= kRedMaxBlocks && fused_moments_enabled() &&
+                     mr->mass_sq == a.k.mm && mr->c2 == a.k.c2;
+    if (mr && !mom && (rc = moments_standalone(a, *mr, s))) return rc;
+    if (mom) {
+        ta.mom = make_mom_consts(mr->mass, mr->mass_sq, mr->c2);
+        ta.mom_partials = mr->scratch;
+        rc = launch_gather_push_tma_v<TP_INTERP_B>(ta, smem, blocks, 1, false, s, true);
+        if (rc == TP_OK) rc = launch_moments_final(mr->scratch, blocks, a.p.n, mr->out8, s);
+        launched = (rc == TP_OK);
+        return rc;
+    }
     int gmode = staged ? 1 : 0;
     if (!staged && records_enabled()) {
         // the grid lives in L2: pack {r, E, B} into 64-byte node records first (ng * 64 B, a few us)
@@ -1359,27 +1427,6 @@ static int launch_gather_push_win(const TmaWinArgs& ta, size_t smem, int blocks,
     return aos ? go(gather_push_win_kernel<FORMULA, true>) : go(gather_push_win_kernel<FORMULA, false>);
 }
 
-// A moment diagnostic riding on a gather+push call: {KE, Px, Py, Pz, |p|^2, n, 0, 0} of the momenta BEFORE the push,
-// i.e. what tp_reduce_moments_f64 called just before the push would return (to summation-order rounding).
-struct MomRequest {
-    double mass, mass_sq, c2;
-    double* out8;
-    double* scratch;            // tp_reduce_scratch_doubles() doubles
-};
-
-static int moments_standalone(const GatherArgs& a, const MomRequest& mr, cudaStream_t s) {
-    return tp_reduce_moments_f64(a.p.mom, a.p.mom_sn, a.p.mom_sc, a.p.n, mr.mass, mr.mass_sq, mr.c2, mr.out8,
-                                 mr.scratch, s);
-}
-
-static bool fused_moments_enabled() {
-    static const bool on = [] {
-        const char* e = std::getenv("TURBOPY_B200_FUSED_MOMENTS");      // A-B switch, default on
-        return !(e && e[0] == '0');
-    }();
-    return on;
-}
-
 // Returns TP_OK and sets `launched` when the windowed kernel took the call.  `mr` (optional): when the call is
 // taken, the moments are delivered too -- inside the kernel for the formula-B SoA instance, by the standalone
 // reduction in front of it otherwise.
@@ -1400,7 +1447,8 @@ static int try_gather_push_windows(const GatherArgs& a, int formula, bool aos, i
     if ((rc = pack_records(a, s, rec_scratch, &rec, formula == TP_INTERP_B ? 2 : 1))) return rc;
     ta.g.records = rec;
     ta.ring.stream_hint = l2_hints_enabled() ? 1 : 0;
-    if (mr && formula == TP_INTERP_B && !aos && blocks <= kRedMaxBlocks && fused_moments_enabled()) {
+    if (mr && formula == TP_INTERP_B && !aos && blocks <= kRedMaxBlocks && fused_moments_enabled() &&
+        mr->mass_sq == a.k.mm && mr->c2 == a.k.c2) {       // (the kernel takes mass**2 and c2 from the push's constants)
         ta.mom = make_mom_consts(mr->mass, mr->mass_sq, mr->c2);
         ta.mom_partials = mr->scratch;
         auto kern = gather_push_win_kernel<TP_INTERP_B, false, true>;
@@ -1476,11 +1524,7 @@ int gather_push_device(const tp_particles* p, const tp_push_consts* k, const tp_
             if ((rc = try_gather_push_windows(a, formula, aos16, bounds, bounds_len, rec_scratch, mr, s, launched))) return rc;
             if (launched) return TP_OK;
         }
-        if (mr) {                       // no fused instance took the call: the standalone reduction in front of the push
-            if ((rc = moments_standalone(a, *mr, s))) return rc;
-            mr = nullptr;
-        }
-        if ((rc = try_gather_push_tma(a, formula, smem, staged, aos16, rec_scratch, s, launched))) return rc;
+        if ((rc = try_gather_push_tma(a, formula, smem, staged, aos16, rec_scratch, mr, s, launched))) return rc;
         if (launched) return TP_OK;
     }
     if (mr && (rc = moments_standalone(a, *mr, s))) return rc;
@@ -1596,7 +1640,7 @@ extern "C" int tp_gather_push_windows_f64(const tp_particles* p, const tp_push_c
                               tile_bounds_len, records_scratch, nullptr);
 }
 
-extern "C" int tp_gather_push_windows_moments_f64(const tp_particles* p, const tp_push_consts* k,
+extern "C" int tp_gather_push_moments_f64(const tp_particles* p, const tp_push_consts* k,
                                                   const tp_grid_fields* g, int axis, int formula, int32_t* tile_bounds,
                                                   int64_t tile_bounds_len, double* records_scratch, double mass,
                                                   double mass_sq, double c2, double* out8, double* reduce_scratch,

@@ -177,9 +177,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <bool AOS, typename Fast, typename Recover>
+// observe(p[2]) sees the thread's two momenta AS LOADED, before `fast` updates them (the fused moment diagnostic).
+template <bool AOS, typename Fast, typename Recover, typename Observe>
 __device__ __forceinline__ void tma_ring(const ParticleArgs& P, const RingArgs& ra, unsigned char* smem, Fast fast,
-                                         Recover recover) {
+                                         Recover recover, Observe observe) {
     uint64_t* full = ring_full(smem);
     uint64_t* done = ring_done(smem);
     unsigned char* tiles = smem + ra.tiles_off;
@@ -215,6 +216,7 @@ __device__ __forceinline__ void tma_ring(const ParticleArgs& P, const RingArgs& 
         double* stage = reinterpret_cast<double*>(tiles + s * kTileBytes);
         Vec3 x[2], p[2];
         stage_read<AOS>(stage, x, p);
+        observe(p);
         const bool ok0 = fast(x[0], p[0]);
         const bool ok1 = fast(x[1], p[1]);
         stage_write<AOS>(stage, x, p);
@@ -228,6 +230,12 @@ __device__ __forceinline__ void tma_ring(const ParticleArgs& P, const RingArgs& 
         if ((threadIdx.x & 31) == 0) mbar_arrive(&done[s]);     // one arrival per consumer warp
         if (++s == nst) { s = 0; parity ^= 1u; }
     }
+}
+
+template <bool AOS, typename Fast, typename Recover>
+__device__ __forceinline__ void tma_ring(const ParticleArgs& P, const RingArgs& ra, unsigned char* smem, Fast fast,
+                                         Recover recover) {
+    tma_ring<AOS>(P, ra, smem, fast, recover, [](const Vec3 (&)[2]) {});
 }
 
 // barrier init (before the CTA-wide sync) and the prologue fills (after it)

@@ -54,7 +54,7 @@ def reduce_moments(momentum, mass, c2, out=None, scratch=None):
 
 #: Deferred moment requests, keyed by (device index, data_ptr) of the momentum tensor: a KineticEnergyDiagnostic with
 #: ``fuse_with_push`` posts its row here instead of launching the reduction, and the next ``BorisPush.gather_push`` on
-#: that momentum tensor takes it along (tp_gather_push_windows_moments_f64: the sums are accumulated from the momenta
+#: that momentum tensor takes it along (tp_gather_push_moments_f64: the sums are accumulated from the momenta
 #: the push kernel has just loaded).  Anything that needs the row earlier flushes it with the standalone reduction.
 _PENDING = {}
 

@@ -584,21 +584,23 @@ class BorisPush(ComputeTool):
             # a KineticEnergyDiagnostic (fuse_with_push) waiting for the moments of exactly these momenta?
             diag = _diagnostics.take_moments_request(momentum) if _diagnostics._PENDING else None
             with _on_device(dev):
+                if diag is not None and _steps is not None:      # multi-step pass: the standalone reduction, first
+                    diag._flush()
+                    diag = None
                 if diag is not None:
-                    hit = self._tile_windows(p, g, position, momentum, axis, grid, dev, code) if _steps is None else None
-                    if hit is None:                 # no windowed kernel for this call: the standalone reduction, first
-                        diag._flush()
-                        diag = None
-                if diag is not None:
-                    win = hit[0] if hit[2] else None
+                    # the step's push delivers the diagnostic's row: inside the kernel where a fused instance exists
+                    # (formula B, SoA, TMA-pipelined), by the standalone reduction in front of the push otherwise
+                    hit = self._tile_windows(p, g, position, momentum, axis, grid, dev, code)
+                    win = hit[0] if hit is not None and hit[2] else None
                     stream = _stream_ptr(dev)
-                    rec = self._record_scratch(ng, dev, stream)
+                    rec = self._record_scratch(ng, dev, stream) if hit is not None else None
                     mass_d, mass_sq, c2_d, row, scratch = diag.moments_request()
-                    _lib.check(lib.tp_gather_push_windows_moments_f64(
+                    _lib.check(lib.tp_gather_push_moments_f64(
                         C.byref(p), C.byref(k), C.byref(g), axis, code,
                         C.c_void_p(win.data_ptr()) if win is not None else None, win.shape[0] if win is not None else 0,
-                        C.c_void_p(rec.data_ptr()), mass_d, mass_sq, c2_d, C.c_void_p(row.data_ptr()),
-                        C.c_void_p(scratch.data_ptr()), C.c_void_p(status.words.data_ptr()), stream))
+                        C.c_void_p(rec.data_ptr()) if rec is not None else None, mass_d, mass_sq, c2_d,
+                        C.c_void_p(row.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                        C.c_void_p(status.words.data_ptr()), stream))
                     diag.moments_delivered()
                 elif _steps is None:
                     hit = self._tile_windows(p, g, position, momentum, axis, grid, dev, code)
