@@ -18,7 +18,10 @@ dev = torch.device("cuda", 0)
 peak, _ = bench.measured_peak()
 n = 16 << 20
 out = []
+ONLY = os.environ.get("FUSED_KE_ONLY")          # e.g. "pif:fused" under ncu
 for shape, ng in (("pif (E_y only)", 4097), ("six components", 1025)):
+    if ONLY and not shape.startswith(ONLY.split(":")[0]):
+        continue
     r, dr = bench.grid_points(ng)
     pif = shape.startswith("pif")
     owner = bench.Owner(r, dr, bench.DT_PIF if pif else bench.dt_of("config3", dr))
@@ -31,6 +34,8 @@ for shape, ng in (("pif (E_y only)", 4097), ("six components", 1025)):
         E = torch.from_numpy(np.stack(comps[:3], axis=1)).to(dev)
         B = torch.from_numpy(np.stack(comps[3:], axis=1)).to(dev)
     for fuse in (False, True, None):
+        if ONLY and {"fused": True, "standalone": False, "none": None}[ONLY.split(":")[1]] is not fuse:
+            continue
         pusher = tp.BorisPush(owner, {"type": "BorisPush"})
         pos, mom = tp.to_soa(pos_h, dev), tp.to_soa(mom_h, dev)
         diag = None
@@ -47,7 +52,7 @@ for shape, ng in (("pif (E_y only)", 4097), ("six components", 1025)):
             step()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        K = 100
+        K = int(os.environ.get("FUSED_KE_STEPS", "100"))
         e0.record()
         for _ in range(K):
             step()
