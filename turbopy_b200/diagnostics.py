@@ -14,6 +14,7 @@ all-reduce (NCCL) of that 8-double row -- no host sync until finalize().
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -56,7 +57,7 @@ def reduce_moments(momentum, mass, c2, out=None, scratch=None):
 #: ``fuse_with_push`` posts its row here instead of launching the reduction, and the next ``BorisPush.gather_push`` on
 #: that momentum tensor takes it along (tp_gather_push_moments_f64: the sums are accumulated from the momenta
 #: the push kernel has just loaded).  Anything that needs the row earlier flushes it with the standalone reduction.
-_PENDING = {}
+_PENDING = weakref.WeakValueDictionary()      # (a diagnostic that is dropped un-finalized takes its request with it)
 
 
 def _pending_key(momentum):
