@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 OUT=gpurun_out/final_ab.txt; : > $OUT
 line() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['value']/1e9,2), 'G pushes/s', round(d['roofline']['frac'],4), 'launches', d['gpu_launches'], d['clocks']['sm_mhz'], d['clocks']['reasons'])"; }
-for R in 1 2 3; do
+for R in ${AB_RUNS:-1 2 3}; do
   TURBOPY_B200_BENCH_GAP_MS=50 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline --no-extras --no-graph 2>/dev/null | tail -1 | line "gap50 eager" >> $OUT
   TURBOPY_B200_BENCH_GAP_MS=0  python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline --no-extras --no-graph 2>/dev/null | tail -1 | line "gap0  eager" >> $OUT
   TURBOPY_B200_BENCH_GAP_MS=0  python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline --no-extras --graph 2>/dev/null | tail -1 | line "gap0  graph" >> $OUT
