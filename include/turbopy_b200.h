@@ -124,6 +124,17 @@ int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
                       const double* E, int e_mode, int64_t e_stride_n, int64_t e_stride_c,
                       const double* B, int b_mode, int64_t b_stride_n, int64_t b_stride_c,
                       tp_stream_t stream);
+/* tp_boris_push_f64 with the energy / moment diagnostic of the step riding on it: out8 receives
+ * {KE, Px, Py, Pz, sum|p|^2, n, 0, 0} of the momenta as they are BEFORE this push (what tp_reduce_moments_f64 called
+ * just before it would deliver, to summation-order rounding, 1e-12); the particles are pushed exactly as by
+ * tp_boris_push_f64.  With uniform E, B and SoA particles the TMA ring kernel accumulates the sums from the momenta it
+ * has just loaded (no second pass over the momentum arrays); otherwise the standalone reduction is launched in front
+ * of the push.  See tp_gather_push_moments_f64.  reduce_scratch: tp_reduce_scratch_doubles() doubles. */
+int tp_boris_push_moments_f64(const tp_particles* p, const tp_push_consts* k,
+                              const double* E, int e_mode, int64_t e_stride_n, int64_t e_stride_c,
+                              const double* B, int b_mode, int64_t b_stride_n, int64_t b_stride_c,
+                              double mass, double mass_sq, double c2, double* out8, double* reduce_scratch,
+                              tp_stream_t stream);
 /* nsteps consecutive pushes with the same E and B (the reference's time loop calling
  * BorisPush.push nsteps times with unchanged field arguments, e.g. a uniform static
  * E x B) in ONE pass over the particles: each particle is read once, stepped nsteps

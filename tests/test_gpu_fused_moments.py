@@ -139,8 +139,8 @@ def test_interval_and_extreme_momenta(tp):
         assert close(g[[0, 4, 5]], w[[0, 4, 5]]), (g, w)
 
 
-@pytest.mark.parametrize("case", ["formula_A", "formula_C_staged", "aos", "random_order", "small_ensemble", "push",
-                                  "push_steps", "gather_push_steps", "values_first"])
+@pytest.mark.parametrize("case", ["formula_A", "formula_C_staged", "aos", "random_order", "small_ensemble", "push_aos",
+                                  "push_fields", "push_steps", "gather_push_steps", "values_first"])
 def test_paths_that_cannot_fuse_deliver_the_pre_push_row(tp, case):
     """Other formulas / layouts / orders / entry points: the row is the standalone reduction's, bit for bit, of the
     momenta as they were when diagnose() was called."""
@@ -152,7 +152,7 @@ def test_paths_that_cannot_fuse_deliver_the_pre_push_row(tp, case):
     comps, E, B = fields_on(grid)
     owner = make_owner(dt=dt, grid=grid, num_steps=4)
     tool = tp.BorisPush(owner, {"type": "BorisPush"})
-    if case == "aos":
+    if case in ("aos", "push_aos"):
         pos, mom = torch.from_numpy(pos0).cuda(), torch.from_numpy(mom0).cuda()
     else:
         pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
@@ -161,8 +161,12 @@ def test_paths_that_cannot_fuse_deliver_the_pre_push_row(tp, case):
     diag.diagnose()
     assert diag._pending_row is not None
     Eu, Bu = np.array([0.0, 1e3, 0.0]), np.array([0.0, 0.0, 0.1])
-    if case == "push":
+    if case == "push_aos":
         tool.push(pos, mom, Q_E, M_E, Eu, Bu)
+    elif case == "push_fields":                                     # per-particle (n,3) fields: the field ring, not fused
+        En = torch.from_numpy(np.tile(Eu, (n, 1))).cuda()
+        Bn = torch.from_numpy(np.tile(Bu, (n, 1))).cuda()
+        tool.push(pos, mom, Q_E, M_E, En, Bn)
     elif case == "push_steps":
         tool.push_steps(pos, mom, Q_E, M_E, Eu, Bu, 3)
     elif case == "gather_push_steps":
@@ -179,6 +183,46 @@ def test_paths_that_cannot_fuse_deliver_the_pre_push_row(tp, case):
     assert_bits_equal(got[0], want, f"{case}: row of the pre-push momenta")
     if case != "values_first":
         assert not np.array_equal(mom.cpu().numpy(), mom0), "the push did not run"
+
+
+@pytest.mark.parametrize("n", [148 * 480 * 3 + 77, 148 * 480, 1000])
+def test_push_with_uniform_fields_delivers_the_row(tp, n):
+    """BorisPush.push (uniform E, B; SoA): the ring kernel's MOM instance (tp_boris_push_moments_f64) -- one launch less
+    than reduction + push, particles bit-identical to the plain push, rows within 1e-12 of the oracle.  n = 1000: too
+    few particles for the ring, the library launches the standalone reduction in front of the register-path push."""
+    grid = make_grid(1025)
+    rng = np.random.default_rng(47)
+    pos0 = rng.uniform(0.0, 1.0, (n, 3))
+    mom0 = M_E * 2.9979e8 * rng.normal(0.0, 0.5, (n, 3))
+    Eu, Bu = np.array([0.0, 1e5, 0.0]), np.array([0.0, 0.0, 1.0])
+    steps = 4
+    runs = {}
+    for fuse in (False, True):
+        owner = make_owner(dt=1e-12, grid=grid, num_steps=steps)
+        tool = tp.BorisPush(owner, {"type": "BorisPush"})
+        pos, mom = tp.to_soa(pos0), tp.to_soa(mom0)
+        diag = diag_for(tp, owner, mom, fuse)
+        pre, launched = [], 0
+        for _ in range(steps):
+            pre.append(mom.cpu().numpy().copy())
+            l0 = launches_of(tp)
+            diag.diagnose()
+            tool.push(pos, mom, Q_E, M_E, Eu, Bu)
+            launched += launches_of(tp) - l0
+        runs[fuse] = (pos.cpu().numpy(), mom.cpu().numpy(), diag.values(), diag.fused_rows, pre, launched)
+    assert runs[True][3] == steps and runs[False][3] == 0
+    ring = n >= 148 * 480
+    assert runs[True][5] == runs[False][5] - (steps if ring else 0)
+    assert_bits_equal(runs[True][0], runs[False][0], "position")
+    assert_bits_equal(runs[True][1], runs[False][1], "momentum")
+    assert close(runs[True][2], runs[False][2])
+    if not ring:
+        assert_bits_equal(runs[True][2], runs[False][2], "rows (standalone reduction on both sides)")
+    for s in range(steps):
+        want = oracle_row(runs[True][4][s])
+        assert close(runs[True][2][s, [0, 4, 5]], want[[0, 4, 5]]), (s, runs[True][2][s], want)
+        psum_scale = np.abs(runs[True][4][s]).sum(axis=0)
+        assert np.all(np.abs(runs[True][2][s, 1:4] - want[1:4]) <= 1e-12 * psum_scale)
 
 
 def test_capi_fallback_inside_the_library(tp):

@@ -19,14 +19,17 @@ peak, _ = bench.measured_peak()
 n = 16 << 20
 out = []
 ONLY = os.environ.get("FUSED_KE_ONLY")          # e.g. "pif:fused" under ncu
-for shape, ng in (("pif (E_y only)", 4097), ("six components", 1025)):
+for shape, ng in (("pif (E_y only)", 4097), ("six components", 1025), ("uniform E x B push()", 1025)):
     if ONLY and not shape.startswith(ONLY.split(":")[0]):
         continue
     r, dr = bench.grid_points(ng)
     pif = shape.startswith("pif")
+    uniform = shape.startswith("uniform")
     owner = bench.Owner(r, dr, bench.DT_PIF if pif else bench.dt_of("config3", dr))
     pos_h, mom_h = bench.host_ensemble(n, 2345, thermal=not pif)
-    if pif:
+    if uniform:
+        E, B = np.array([0.0, 1e5, 0.0]), np.array([0.0, 0.0, 1.0])
+    elif pif:
         Ey = torch.from_numpy(bench.wave_fields(r, 1)[0]).to(dev)
         E, B = (None, Ey, None), None
     else:
@@ -47,7 +50,10 @@ for shape, ng in (("pif (E_y only)", 4097), ("six components", 1025)):
         def step():
             if diag is not None:
                 diag.diagnose()
-            pusher.gather_push(pos, mom, bench.Q_E, bench.M_E, E_grid=E, B_grid=B)
+            if uniform:
+                pusher.push(pos, mom, bench.Q_E, bench.M_E, E, B)
+            else:
+                pusher.gather_push(pos, mom, bench.Q_E, bench.M_E, E_grid=E, B_grid=B)
         for _ in range(5):
             step()
         torch.cuda.synchronize()
@@ -58,7 +64,8 @@ for shape, ng in (("pif (E_y only)", 4097), ("six components", 1025)):
             step()
         e1.record()
         torch.cuda.synchronize()
-        pusher.check_status()
+        if not uniform:
+            pusher.check_status()
         ms = e0.elapsed_time(e1) / K
         row = {"shape": shape, "ng": ng, "particles": n,
                "diagnostic": "none" if fuse is None else "fused into the push" if fuse else "standalone reduction + push",

@@ -49,6 +49,10 @@ SIGNATURES = {
     "tp_boris_push_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts),
                                     C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
+    "tp_boris_push_moments_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts),
+                                            C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                                            C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                                            C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tp_boris_push_steps_f64": (C.c_int, [C.POINTER(Particles), C.POINTER(PushConsts),
                                           C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                           C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),

@@ -498,6 +498,8 @@ __global__ void __launch_bounds__(256) tile_bounds_kernel(const double* __restri
 struct PushTmaArgs {
     PushArgs a;
     RingArgs ring;
+    double mom_mass;            // MOM instance: the diagnostic's mass ...
+    double* mom_partials;       // ... and where CTA b leaves its five partial sums (8 doubles apart)
 };
 
 __device__ __noinline__ void push_one_exact_slot(const PushArgs& a, int64_t i, double* xs, double* ps, int pitch) {
@@ -548,27 +550,34 @@ __global__ void __launch_bounds__(kTmaThreads, 1) push_fields_tma_kernel(const _
 // kPushStages of them.  Measured (16 Mi particles): this ring 3 / 4 / 5 / 6 stages = 91.7 / 98.0 / 92.1 / 88.5 % of the
 // HBM peak, the 960-particle ring of the fused kernel 2 / 3 / 4 stages = 92.9 / 94.1 / 89.6 %.  (The fused gather+push
 // is the other way round: 98 % on the 960-particle ring, 83-90 % here.)
+// MOM: also accumulate {KE, Px, Py, Pz, |p|^2} of the momenta AS LOADED (see gather_push_win_kernel).
 constexpr int kPushStages = 4;
-template <bool PA>
+template <bool PA, bool MOM = false>
 __global__ void __launch_bounds__(kTmaThreads, 1) push_tma_kernel(const __grid_constant__ PushTmaArgs ta) {
     extern __shared__ __align__(128) unsigned char smem[];
     const PushArgs& a = ta.a;
     ring_init(ta.ring, smem);
     __syncthreads();
     const Vec3 equ = dt_field_q(a.k, uniform_of(a.E)), bqu = dt_field_q(a.k, uniform_of(a.B));
+    double acc[kRedVals] = {0.0, 0.0, 0.0, 0.0, 0.0};
     tma_ring_fields<PA, false, false>(
         a, ta.ring, smem,
         [&](const Vec3&, const Vec3&, Vec3& x, Vec3& p) { return push_steps_fast(a.k, a.nsteps, equ, bqu, x, p); },
-        [&](int64_t i, double* xs, double* ps, int pitch) { push_one_exact_slot(a, i, xs, ps, pitch); });
+        [&](int64_t i, double* xs, double* ps, int pitch) { push_one_exact_slot(a, i, xs, ps, pitch); },
+        [&](const Vec3& p) {
+            if (MOM) moments_add(&p, 1, a.k, ta.mom_mass, acc);
+        });
     if (blockIdx.x == gridDim.x - 1) {                       // ragged tail, scalar path
         const Vec3 Eu = uniform_of(a.E), Bu = uniform_of(a.B);
         for (int64_t i = ta.ring.ntiles * kTileF + threadIdx.x; i < a.p.n; i += kTmaThreads) {
             Vec3 x, p;
             load_one(a.p, i, x, p);
+            if (MOM) moments_add(&p, 1, a.k, ta.mom_mass, acc);
             if (push_one_fast(a, Eu, Bu, i, x, p)) store_one(a.p, i, x, p);
             else push_one_exact(a, i);
         }
     }
+    if (MOM) block_sum<kTmaThreads>(acc, ta.mom_partials + static_cast<int64_t>(blockIdx.x) * 8);   // all 16 warps
 }
 
 // ---------------------------------------------------------------------------
@@ -1329,9 +1338,11 @@ struct MomRequest {
     double* scratch;            // tp_reduce_scratch_doubles() doubles
 };
 
+static int moments_standalone(const ParticleArgs& p, const MomRequest& mr, cudaStream_t s) {
+    return tp_reduce_moments_f64(p.mom, p.mom_sn, p.mom_sc, p.n, mr.mass, mr.mass_sq, mr.c2, mr.out8, mr.scratch, s);
+}
 static int moments_standalone(const GatherArgs& a, const MomRequest& mr, cudaStream_t s) {
-    return tp_reduce_moments_f64(a.p.mom, a.p.mom_sn, a.p.mom_sc, a.p.n, mr.mass, mr.mass_sq, mr.c2, mr.out8,
-                                 mr.scratch, s);
+    return moments_standalone(a.p, mr, s);
 }
 
 static bool fused_moments_enabled() {
@@ -1538,7 +1549,7 @@ using namespace tp;
 
 static int boris_push_device(const tp_particles* p, const tp_push_consts* k, const double* E, int e_mode,
                              int64_t e_sn, int64_t e_sc, const double* B, int b_mode, int64_t b_sn,
-                             int64_t b_sc, int nsteps, tp_stream_t stream) {
+                             int64_t b_sc, int nsteps, tp_stream_t stream, const MomRequest* mr = nullptr) {
     const DeviceProps& d = device_props();
     if (d.status != TP_OK) return d.status;
     if (nsteps < 0) return TP_E_ARG;
@@ -1552,20 +1563,42 @@ static int boris_push_device(const tp_particles* p, const tp_push_consts* k, con
     if ((rc = fill_consts(k, a.k))) return rc;
     if ((rc = fill_field(E, e_mode, e_sn, e_sc, a.E))) return rc;
     if ((rc = fill_field(B, b_mode, b_sn, b_sc, a.B))) return rc;
-    if (a.p.n == 0) return TP_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // a moment diagnostic riding on this push (tp_boris_push_moments_f64): delivered by the fused instance of the
+    // uniform-field ring kernel (SoA, one step) or by the standalone reduction in front of whatever kernel runs
+    auto standalone = [&]() {
+        if (!mr) return static_cast<int>(TP_OK);
+        const MomRequest* r = mr;
+        mr = nullptr;
+        return moments_standalone(a.p, *r, s);
+    };
+    if (a.p.n == 0) return standalone();
     const bool uniform = a.E.mode != TP_FIELD_PER_PARTICLE && a.B.mode != TP_FIELD_PER_PARTICLE;
     if ((vec2 || aos16) && uniform) {
         PushTmaArgs ta;
         ta.a = a;
+        ta.mom_mass = 0.0;
+        ta.mom_partials = nullptr;
         size_t smem = 0; int blocks = 0;
         if (plan_ring(a.p.n, kSmemHeader, ta.ring, smem, blocks, kTileF)) {
+            const bool mom = mr && !aos16 && nsteps == 1 && blocks <= kRedMaxBlocks && fused_moments_enabled() &&
+                             mr->mass_sq == a.k.mm && mr->c2 == a.k.c2;
+            if (!mom && (rc = standalone())) return rc;
             int nst = kPushStages;
             if (const char* cap = std::getenv("TURBOPY_B200_STAGES")) nst = std::min(kRingMaxStages, std::max(2, std::atoi(cap)));
             ta.ring.nstages = nst;
             static const int push_pace = [] { const char* e = std::getenv("TURBOPY_B200_PUSH_DELAY_NS"); return e ? std::atoi(e) : 0; }();
             ta.ring.consumer_delay_ns = push_pace;
             smem = ta.ring.tiles_off + static_cast<size_t>(nst) * 2 * kArrayF;
+            if (mom) {
+                ta.mom_mass = mr->mass;
+                ta.mom_partials = mr->scratch;
+                if ((rc = set_smem(push_tma_kernel<false, true>, smem))) return rc;
+                push_tma_kernel<false, true><<<blocks, kTmaThreads, smem, s>>>(ta);
+                count_launch();
+                if ((rc = static_cast<int>(cudaGetLastError()))) return rc;
+                return launch_moments_final(mr->scratch, blocks, a.p.n, mr->out8, s);
+            }
             if (aos16) {
                 if ((rc = set_smem(push_tma_kernel<true>, smem))) return rc;
                 push_tma_kernel<true><<<blocks, kTmaThreads, smem, s>>>(ta);
@@ -1577,6 +1610,7 @@ static int boris_push_device(const tp_particles* p, const tp_push_consts* k, con
             return static_cast<int>(cudaGetLastError());
         }
     }
+    if ((rc = standalone())) return rc;
     if ((vec2 || aos16) && a.E.mode == TP_FIELD_PER_PARTICLE && a.B.mode == TP_FIELD_PER_PARTICLE) {
         // both fields in one bulk-copyable layout: three component slices, or one C-order (n,3) block
         auto bulk_layout = [&](const FieldArg& f) {
@@ -1615,6 +1649,16 @@ extern "C" int tp_boris_push_f64(const tp_particles* p, const tp_push_consts* k,
                                  int64_t e_sn, int64_t e_sc, const double* B, int b_mode, int64_t b_sn,
                                  int64_t b_sc, tp_stream_t stream) {
     return boris_push_device(p, k, E, e_mode, e_sn, e_sc, B, b_mode, b_sn, b_sc, 1, stream);
+}
+
+extern "C" int tp_boris_push_moments_f64(const tp_particles* p, const tp_push_consts* k, const double* E, int e_mode,
+                                         int64_t e_sn, int64_t e_sc, const double* B, int b_mode, int64_t b_sn,
+                                         int64_t b_sc, double mass, double mass_sq, double c2, double* out8,
+                                         double* reduce_scratch, tp_stream_t stream) {
+    if (!out8 || !reduce_scratch) return TP_E_ARG;
+    MomRequest mr;
+    mr.mass = mass; mr.mass_sq = mass_sq; mr.c2 = c2; mr.out8 = out8; mr.scratch = reduce_scratch;
+    return boris_push_device(p, k, E, e_mode, e_sn, e_sc, B, b_mode, b_sn, b_sc, 1, stream, &mr);
 }
 
 extern "C" int tp_boris_push_steps_f64(const tp_particles* p, const tp_push_consts* k, const double* E, int e_mode,

@@ -59,9 +59,10 @@ __device__ __forceinline__ Vec3 slot_read(unsigned char* array) {
 // PA / FA: layout of the particle arrays / of the field arrays (true = C-order (n,3)).
 // FIELDS = false: the stage holds only the state (22.5 KB; uniform E, B come from the closure), which
 // allows a deeper ring of smaller tiles.  fast(E, B, x, p) -> bool; recover(i, xs, ps, pitch) as in tma_ring.
-template <bool PA, bool FA, bool FIELDS, typename Fast, typename Recover>
+// observe(p) sees the thread's momentum AS LOADED, before `fast` updates it (the fused moment diagnostic).
+template <bool PA, bool FA, bool FIELDS, typename Fast, typename Recover, typename Observe>
 __device__ __forceinline__ void tma_ring_fields(const PushArgs& a, const RingArgs& ra, unsigned char* smem, Fast fast,
-                                                Recover recover) {
+                                                Recover recover, Observe observe) {
     constexpr uint32_t kStage = FIELDS ? kTileBytes : 2 * kArrayF;
     uint64_t* full = ring_full(smem);
     uint64_t* done = ring_done(smem);
@@ -114,6 +115,7 @@ __device__ __forceinline__ void tma_ring_fields(const PushArgs& a, const RingArg
         if (FIELDS) { E = slot_read<FA>(st + 2 * kArrayF); B = slot_read<FA>(st + 3 * kArrayF); }
         double* xs = slot_of<PA>(st);
         double* ps = slot_of<PA>(st + kArrayF);
+        observe(p);
         if (__builtin_expect(fast(E, B, x, p), 1)) slot_write(xs, ps, pitch, x, p);
         else recover(t * kTileF + threadIdx.x, xs, ps, pitch);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -121,6 +123,12 @@ __device__ __forceinline__ void tma_ring_fields(const PushArgs& a, const RingArg
         if ((threadIdx.x & 31) == 0) mbar_arrive(&done[s]);
         if (++s == nst) { s = 0; parity ^= 1u; }
     }
+}
+
+template <bool PA, bool FA, bool FIELDS, typename Fast, typename Recover>
+__device__ __forceinline__ void tma_ring_fields(const PushArgs& a, const RingArgs& ra, unsigned char* smem, Fast fast,
+                                                Recover recover) {
+    tma_ring_fields<PA, FA, FIELDS>(a, ra, smem, fast, recover, [](const Vec3&) {});
 }
 
 }  // namespace tp

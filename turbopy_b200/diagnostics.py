@@ -70,8 +70,8 @@ def take_moments_request(momentum):
 
 
 def flush_moments_request(momentum):
-    """A caller is about to change ``momentum`` through a path that cannot deliver a posted request (``push``,
-    ``push_steps``, multi-step passes): run the standalone reduction now, while the momenta are still the ones
+    """A caller is about to change ``momentum`` through a path that cannot deliver a posted request (``push_steps``,
+    multi-step passes): run the standalone reduction now, while the momenta are still the ones
     the diagnostic asked about."""
     diag = _PENDING.get(_pending_key(momentum))
     if diag is not None:

@@ -453,14 +453,23 @@ class BorisPush(ComputeTool):
                 raise TypeError("position and momentum must live on the same CUDA device")
             p = _particles_struct(position, momentum)
             dev = position.device
-            if _diagnostics._PENDING:
-                _diagnostics.flush_moments_request(momentum)
+            # a KineticEnergyDiagnostic (fuse_with_push) waiting for the moments of exactly these momenta?
+            diag = _diagnostics.take_moments_request(momentum) if _diagnostics._PENDING else None
             e = _FieldArg(E, "E", p.n, dev)
             b = _FieldArg(B, "B", p.n, dev)
             with _on_device(dev):
-                _lib.check(lib.tp_boris_push_f64(C.byref(p), C.byref(k),
-                                                 C.c_void_p(e.ptr), e.mode, e.sn, e.sc,
-                                                 C.c_void_p(b.ptr), b.mode, b.sn, b.sc, _stream_ptr(dev)))
+                if diag is not None:
+                    mass_d, mass_sq, c2_d, row, scratch = diag.moments_request()
+                    _lib.check(lib.tp_boris_push_moments_f64(C.byref(p), C.byref(k),
+                                                             C.c_void_p(e.ptr), e.mode, e.sn, e.sc,
+                                                             C.c_void_p(b.ptr), b.mode, b.sn, b.sc,
+                                                             mass_d, mass_sq, c2_d, C.c_void_p(row.data_ptr()),
+                                                             C.c_void_p(scratch.data_ptr()), _stream_ptr(dev)))
+                    diag.moments_delivered()
+                else:
+                    _lib.check(lib.tp_boris_push_f64(C.byref(p), C.byref(k),
+                                                     C.c_void_p(e.ptr), e.mode, e.sn, e.sc,
+                                                     C.c_void_p(b.ptr), b.mode, b.sn, b.sc, _stream_ptr(dev)))
             return None
         if isinstance(position, np.ndarray) and isinstance(momentum, np.ndarray):
             p = _particles_struct(position, momentum)
