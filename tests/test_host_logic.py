@@ -231,3 +231,67 @@ def test_formula_a_window_margin_is_sufficient():
         assert accepted.mean() > 0.3               # and the margin is not so wide that nothing passes
         checked += int(accepted.sum())
     assert checked > 100_000
+
+
+def test_deferred_diagnostic_protocol(monkeypatch):
+    """Host side of ``KineticEnergyDiagnostic(fuse_with_push=True)`` (no device: the reduction is replaced by a numpy
+    stand-in and CPU tensors are declared deliverable): diagnose() only posts a request keyed by the momentum tensor;
+    a push takes it exactly once; values() / the next diagnose() / finalize() / flush_moments_request() deliver an
+    untaken request from the momenta as they are at that moment; rows stay in call order."""
+    import torch
+    import turbopy_b200 as tp
+    from turbopy_b200 import diagnostics as D
+
+    calls = []
+
+    def fake_reduce(momentum, mass, c2, out=None, scratch=None):
+        calls.append(float(momentum.sum()))
+        out[:] = 0.0
+        out[0], out[5] = float((momentum * momentum).sum()), float(momentum.shape[0])
+        return out
+
+    monkeypatch.setattr(D, "reduce_moments", fake_reduce)
+    monkeypatch.setattr(D, "_can_ride_on_push", lambda m: True)
+    monkeypatch.setattr(D._lib, "lib", lambda: type("L", (), {"tp_reduce_scratch_doubles": staticmethod(lambda: 8)})())
+    mom = torch.ones((4, 3), dtype=torch.float64)
+    owner = make_owner(num_steps=6)
+    d = tp.KineticEnergyDiagnostic(owner, {"momentum": "p", "mass": 1.0, "fuse_with_push": True, "interval": 2,
+                                           "allreduce": False})
+    d.inspect_resource({"p": mom})
+    d.initialize()
+    assert not D._PENDING
+    d.diagnose()                                            # call 1: a diagnostic step -> posted, nothing reduced
+    assert calls == [] and D._PENDING and d._pending_row is not None
+    got = D.take_moments_request(mom)                       # the push takes it ...
+    assert got is d and not D._PENDING and D.take_moments_request(mom) is None       # ... exactly once
+    mass, mass_sq, c2, row, scratch = d.moments_request()
+    assert (mass, mass_sq) == (1.0, 1.0) and row.shape == (8,) and scratch.numel() == 8
+    row[:] = 0.0
+    row[0] = 12.0                                           # what the fused kernel would write
+    d.moments_delivered()
+    assert d.fused_rows == 1 and d._pending_row is None
+    d.diagnose()                                            # call 2: not a diagnostic step (interval 2)
+    assert not D._PENDING
+    d.diagnose()                                            # call 3: posted again
+    mom.mul_(2.0)                                           # nobody pushed; values() must flush NOW (momenta as they are)
+    rows = d.values()
+    assert calls == [24.0] and not D._PENDING and rows.shape == (2, 6)
+    assert rows[0, 0] == 12.0 and rows[1, 0] == 48.0 and d.fused_rows == 1
+    d.diagnose()                                            # call 4: skipped
+    d.diagnose()                                            # call 5: posted
+    D.flush_moments_request(mom)                            # a path that cannot deliver (push_steps) flushes first
+    assert calls == [24.0, 24.0] and not D._PENDING
+    D.flush_moments_request(mom)                            # nothing pending: no-op
+    assert calls == [24.0, 24.0]
+    d.finalize()                                            # call 6: skipped by the interval; nothing left to flush
+    assert d.values().shape == (3, 6) and calls == [24.0, 24.0]
+    # a diagnostic that goes away un-finalized takes its request with it (weak registry)
+    d2 = tp.KineticEnergyDiagnostic(owner, {"momentum": "p", "mass": 1.0, "fuse_with_push": True, "allreduce": False})
+    d2.inspect_resource({"p": mom})
+    d2.initialize()
+    d2.diagnose()
+    assert len(D._PENDING) == 1
+    del d2
+    import gc
+    gc.collect()
+    assert not D._PENDING

@@ -64,6 +64,11 @@ def _pending_key(momentum):
     return (momentum.device.index, momentum.data_ptr())
 
 
+def _can_ride_on_push(momentum):
+    """Only a resident CUDA tensor is pushed by the kernels that can deliver a request."""
+    return isinstance(momentum, torch.Tensor) and momentum.is_cuda
+
+
 def take_moments_request(momentum):
     """The diagnostic waiting for the moments of ``momentum`` (and forget the request), or None."""
     return _PENDING.pop(_pending_key(momentum), None)
@@ -162,7 +167,7 @@ class KineticEnergyDiagnostic(Diagnostic):
             self._scratch = torch.empty(int(_lib.lib().tp_reduce_scratch_doubles()), dtype=torch.float64,
                                         device=self.momentum.device)
         self._used += 1
-        if self.fuse_with_push and isinstance(self.momentum, torch.Tensor) and self.momentum.is_cuda:
+        if self.fuse_with_push and _can_ride_on_push(self.momentum):
             self._pending_row = row                      # filled by the next gather_push on this tensor (or a flush)
             _PENDING[_pending_key(self.momentum)] = self
             return
