@@ -2,7 +2,7 @@
 # GPU check of the diagnostic fused into the push: its tests, the per-step cost on the staged shapes, then configs[2]
 # per GPU with and without it.
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_fused_moments.py -x -q -m gpu > gpurun_out/fused_tests.log 2>&1; echo "pytest rc $?"; tail -5 gpurun_out/fused_tests.log
+python -m pytest tests/test_gpu_fused_moments.py tests/test_gpu_boris.py -x -q -m gpu > gpurun_out/fused_tests.log 2>&1; echo "pytest rc $?"; tail -5 gpurun_out/fused_tests.log
 python tools/run_fused_ke.py > gpurun_out/fused_ke_staged.jsonl 2> gpurun_out/fused_ke_staged.err; echo "run_fused_ke rc $?"; cat gpurun_out/fused_ke_staged.jsonl | cut -c1-330
 OUT=gpurun_out/fused_ke_ab.txt; : > $OUT
 for F in 1 0 1 0; do
