@@ -91,6 +91,28 @@ def test_streaming_kernels_fit_the_ctas_they_launch_per_sm(lib):
     assert seen == set(resident), f"kernels not found in the library: {set(resident) - seen}"
 
 
+def test_fused_diagnostic_instances_are_in_the_library(lib):
+    """The MOM instances (kernel 3 fused into kernel 1) the launchers select for tp_gather_push_moments_f64 /
+    tp_boris_push_moments_f64: staged grid (generic and E_y-only), per-tile windows, uniform-field push -- formula B
+    (= 2), SoA, and they fit the one-CTA-per-SM ring (512 threads: at most 128 registers, no large spill frame)."""
+    import re
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-res-usage", lib.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {m.group(1): (int(m.group(2)), int(m.group(3)))
+             for m in re.finditer(r"Function (\S+?):\s*\n\s*REG:(\d+) STACK:(\d+)", out)}
+    wanted = ["22gather_push_tma_kernelILi2ELi1ELb0ELj0ELb1EE", "22gather_push_tma_kernelILi2ELi1ELb0ELj2ELb1EE",
+              "22gather_push_win_kernelILi2ELb0ELb1EE", "15push_tma_kernelILb0ELb1EE"]
+    for key in wanted:
+        hits = [(name, v) for name, v in usage.items() if key in name]
+        assert len(hits) == 1, f"{key}: {len(hits)} instances in the library"
+        regs, stack = hits[0][1]
+        assert regs <= 128 and stack <= 256, f"{hits[0][0]}: {regs} registers, {stack} B of stack"
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
