@@ -68,6 +68,7 @@ def main():
         print(f"dist check ok: world={world}, {n_total} particles sharded, KE row0={rows[0,0]:.6e} J "
               f"(ref {ref_rows[0,0]:.6e}), shards bit-identical to the oracle")
     graph_check(rank, world, dev, owner, pos0[lo:hi], mom0[lo:hi], E, B)
+    fused_check(rank, world, dev, owner, pos0[lo:hi], mom0[lo:hi], E, B, ref_rows, rp[lo:hi], rm[lo:hi], n_total)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -122,6 +123,70 @@ def graph_check(rank, world, dev, owner, pos0, mom0, E, B):
     if rank == 0:
         print(f"graph check ok: world={world}, [10 x gather_push, reduce, NCCL all-reduce on the compute stream] captured "
               f"once, replayed 3x == eager; KE after 30 steps {got[2, 0]:.6e} J")
+
+
+def fused_check(rank, world, dev, owner, pos0, mom0, E, B, ref_rows, rp, rm, n_total):
+    """The same with the diagnostic riding on the push (fuse_with_push): rows against the oracle on the whole
+    ensemble, shards bit-identical; then `[diagnose(); 10 x gather_push]` (the first push delivers the row, the NCCL
+    all-reduce follows on the compute stream) captured in a StepGraph and replayed 3x against the eager sequence."""
+    steps = ref_rows.shape[0] - 1
+    pusher = tp.BorisPush(owner, {"type": "BorisPush"})
+    pos, mom = tp.to_soa(pos0, dev), tp.to_soa(mom0, dev)
+    diag = tp.KineticEnergyDiagnostic(owner, {"momentum": "p", "mass": M_E, "fuse_with_push": True})
+    diag.inspect_resource({"p": mom})
+    diag.initialize()
+    for _ in range(steps):
+        diag.diagnose()                                     # posts; the push below delivers and all-reduces
+        pusher.gather_push(pos, mom, Q_E, M_E, E_grid=E, B_grid=B)
+    diag.diagnose()                                         # the last row: flushed by values() (standalone + all-reduce)
+    pusher.check_status()
+    rows = diag.values()
+    assert diag.fused_rows == steps, diag.fused_rows
+    scale = np.maximum(np.abs(ref_rows), np.abs(rm).sum() * world * np.array([0, 1, 1, 1, 0, 0])[None, :] + 1e-300)
+    assert rows.shape == ref_rows.shape and np.all(np.abs(rows - ref_rows) <= 1e-12 * scale), (rows, ref_rows)
+    assert rows[0, 5] == n_total
+    assert np.array_equal(pos.cpu().numpy().view(np.uint64), rp.view(np.uint64))
+    assert np.array_equal(mom.cpu().numpy().view(np.uint64), rm.view(np.uint64))
+
+    def fresh():
+        pusher = tp.BorisPush(owner, {"type": "BorisPush"})
+        p, m = tp.to_soa(pos0, dev), tp.to_soa(mom0, dev)
+        d = tp.KineticEnergyDiagnostic(owner, {"momentum": "p", "mass": M_E, "fuse_with_push": True})
+        d.inspect_resource({"p": m})
+        d.initialize()
+        return pusher, p, m, d
+
+    def block(pusher, p, m, d):
+        d.diagnose()
+        for _ in range(10):
+            pusher.gather_push(p, m, Q_E, M_E, E_grid=E, B_grid=B)
+
+    pusher_e, pe, me, de = fresh()
+    for _ in range(3):
+        block(pusher_e, pe, me, de)
+    rows_e = de.values()
+    assert de.fused_rows == 3
+    pusher_g, pg, mg, dg = fresh()
+    block(pusher_g, pg, mg, dg)                              # warm: buffers, communicator, the diagnostic's row table
+    pg.copy_(tp.to_soa(pos0, dev)); mg.copy_(tp.to_soa(mom0, dev))
+    with tp.StepGraph(dev) as graph:
+        block(pusher_g, pg, mg, dg)
+    captured_row = dg._used - 1
+    rows_g = []
+    for _ in range(3):
+        graph.replay()
+        rows_g.append(dg.rows[captured_row, :6].clone())
+    torch.cuda.synchronize()
+    pusher_g.check_status()
+    assert torch.equal(pe, pg) and torch.equal(me, mg), "fused graph replay differs from eager steps"
+    got = torch.stack(rows_g).cpu().numpy()
+    assert np.array_equal(got, rows_e), (got, rows_e)
+    if world > 1:
+        torch.distributed.barrier()
+    if rank == 0:
+        print(f"fused check ok: world={world}, diagnostic delivered by the push kernel ({steps} rows vs the oracle on the "
+              f"whole ensemble, 1e-12), [diagnose, 10 x gather_push] with the NCCL all-reduce behind the first push captured "
+              f"once, replayed 3x == eager; KE rows {got[:, 0]}")
 
 
 if __name__ == "__main__":
